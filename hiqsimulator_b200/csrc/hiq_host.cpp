@@ -1,0 +1,39 @@
+#include "hiq_host.hpp"
+
+#include <atomic>
+
+namespace hiq {
+
+static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+int set_error(int code, const std::string& msg)
+{
+     g_last_error = msg;
+     return code;
+}
+
+int check_cuda(cudaError_t e, const char* what)
+{
+     if (e == cudaSuccess) return HIQ_OK;
+     return set_error(HIQ_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what); }
+
+void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+}  // namespace hiq
+
+extern "C" const char* hiq_last_error(void) { return hiq::g_last_error.c_str(); }
+extern "C" const char* hiq_version(void) { return "hiq_b200 0.1.0 sm_100a"; }
+extern "C" uint64_t hiqk_launch_count(void) { return hiq::g_launches.load(); }
+extern "C" int hiq_device_count(void)
+{
+     int n = 0;
+     if (cudaGetDeviceCount(&n) != cudaSuccess) {
+          cudaGetLastError();
+          return -1;
+     }
+     return n;
+}

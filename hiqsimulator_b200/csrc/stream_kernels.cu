@@ -1,0 +1,437 @@
+// Streaming (HBM-bound) kernels of the state-vector engine: diagonal gates, global phase,
+// probability / block-norm / entropy reductions, collapse, fill, qubit compaction and the
+// pack/unpack halves of the global<->local qubit swap.  Each launcher cites the reference code it
+// replaces; all of them are one pass over (part of) the local slab with 128-bit accesses.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "hiq_device.cuh"
+#include "hiq_host.hpp"
+
+namespace hiq {
+
+constexpr int kStreamThreads = 256;
+constexpr int kMaxPartials = 8192;  // per-CTA partial sums (x2 for bit_norms)
+
+static unsigned stream_grid(uint64_t items, int per_thread = 4)
+{
+     const uint64_t need = (items + static_cast<uint64_t>(kStreamThreads) * per_thread - 1) /
+                           (static_cast<uint64_t>(kStreamThreads) * per_thread);
+     const uint64_t cap = static_cast<uint64_t>(kNumSMs) * 8 * 4;  // 8 CTAs/SM resident, 4 waves
+     return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(need, cap)));
+}
+
+// ----------------------------------------------------------------------------- diagonal gate
+struct DiagParams {
+     double2* psi;
+     uint64_t n_free;     // indices enumerated (control bits are inserted as fixed ones)
+     uint64_t ctrl_mask;
+     InsertBits ins;      // control slots, ascending
+     int k;
+     int slots[kMaxTargets];
+     double2 d[1 << kMaxTargets];
+};
+
+__global__ void __launch_bounds__(kStreamThreads) diag_kernel(const __grid_constant__ DiagParams p)
+{
+     __shared__ double2 lut[1 << kMaxTargets];
+     if (threadIdx.x < (1 << p.k)) lut[threadIdx.x] = p.d[threadIdx.x];
+     __syncthreads();
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     uint64_t f = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x;
+     // four independent amplitudes in flight per thread
+     for (; f + 3 * stride < p.n_free; f += 4 * stride) {
+          uint64_t idx[4];
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+               idx[u] = insert_zero_bits(f + u * stride, p.ins) | p.ctrl_mask;
+               v[u] = ldg_stream(p.psi + idx[u]);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+               int sel = 0;
+#pragma unroll
+               for (int l = 0; l < kMaxTargets; ++l)
+                    if (l < p.k) sel |= static_cast<int>((idx[u] >> p.slots[l]) & 1ull) << l;
+               p.psi[idx[u]] = cmul(v[u], lut[sel]);
+          }
+     }
+     for (; f < p.n_free; f += stride) {
+          const uint64_t idx = insert_zero_bits(f, p.ins) | p.ctrl_mask;
+          int sel = 0;
+          for (int l = 0; l < p.k; ++l) sel |= static_cast<int>((idx >> p.slots[l]) & 1ull) << l;
+          p.psi[idx] = cmul(p.psi[idx], lut[sel]);
+     }
+}
+
+// ----------------------------------------------------------------------------- scale / fill / collapse
+__global__ void __launch_bounds__(kStreamThreads) scale_kernel(double2* psi, uint64_t n, double2 s)
+{
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x;
+     for (; i + 3 * stride < n; i += 4 * stride) {
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = ldg_stream(psi + i + u * stride);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) psi[i + u * stride] = cmul(v[u], s);
+     }
+     for (; i < n; i += stride) psi[i] = cmul(psi[i], s);
+}
+
+__global__ void __launch_bounds__(kStreamThreads) fill_kernel(double2* psi, uint64_t n, double2 v)
+{
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x; i < n; i += stride) psi[i] = v;
+}
+
+// psi[i] = match ? psi[i] * scale : 0 — amplitudes that do not match are overwritten without being read
+__global__ void __launch_bounds__(kStreamThreads) collapse_kernel(double2* psi, uint64_t n, uint64_t mask, uint64_t val,
+                                                                   double scale)
+{
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x;
+     for (; i + 3 * stride < n; i += 4 * stride) {
+          double2 v[4];
+          bool ok[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+               ok[u] = ((i + u * stride) & mask) == val;
+               v[u] = ok[u] ? ldg_stream(psi + i + u * stride) : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) psi[i + u * stride] = make_double2(v[u].x * scale, v[u].y * scale);
+     }
+     for (; i < n; i += stride) {
+          const bool ok = (i & mask) == val;
+          const double2 v = ok ? psi[i] : make_double2(0.0, 0.0);
+          psi[i] = make_double2(v.x * scale, v.y * scale);
+     }
+}
+
+// ----------------------------------------------------------------------------- reductions
+// Stage 1: one partial per CTA (fixed tree); stage 2: one CTA folds the partials in index order.
+struct ReduceParams {
+     const double2* psi;
+     uint64_t n_free;
+     uint64_t val;
+     InsertBits ins;  // mask bits, ascending (fixed to `val`)
+};
+
+enum { RED_NORM = 0, RED_ENTROPY = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(kStreamThreads) reduce_kernel(const __grid_constant__ ReduceParams p, double* partials)
+{
+     __shared__ double scratch[kStreamThreads / 32];
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+     uint64_t f = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x;
+     auto term = [](double2 v) {
+          const double pr = norm2(v);
+          if (MODE == RED_NORM) return pr;
+          return pr > 0.0 ? pr * log2(pr) : 0.0;
+     };
+     for (; f + 3 * stride < p.n_free; f += 4 * stride) {
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = ldg_stream(p.psi + (insert_zero_bits(f + u * stride, p.ins) | p.val));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += term(v[u]);
+     }
+     for (; f < p.n_free; f += stride) acc[0] += term(p.psi[insert_zero_bits(f, p.ins) | p.val]);
+     const double s = block_sum<kStreamThreads>((acc[0] + acc[1]) + (acc[2] + acc[3]), scratch);
+     if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(1024) fold_kernel(const double* partials, int n, int n_out, double* out)
+{
+     // out[o] = sum_j partials[o * n + j]: fixed order -> run-to-run deterministic
+     __shared__ double scratch[32];
+     for (int o = 0; o < n_out; ++o) {
+          double acc = 0.0;
+          for (int j = threadIdx.x; j < n; j += 1024) acc += partials[o * n + j];
+          const double s = block_sum<1024>(acc, scratch);
+          if (threadIdx.x == 0) out[o] = s;
+     }
+}
+
+__global__ void __launch_bounds__(kStreamThreads) bit_norms_kernel(const double2* psi, uint64_t n, int slot, double* partials)
+{
+     __shared__ double scratch[kStreamThreads / 32];
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     double a0 = 0.0, a1 = 0.0;
+     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x; i < n; i += stride) {
+          const double pr = norm2(ldg_stream(psi + i));
+          if ((i >> slot) & 1ull) a1 += pr;
+          else a0 += pr;
+     }
+     const double s0 = block_sum<kStreamThreads>(a0, scratch);
+     const double s1 = block_sum<kStreamThreads>(a1, scratch);
+     if (threadIdx.x == 0) {
+          partials[blockIdx.x] = s0;
+          partials[gridDim.x + blockIdx.x] = s1;
+     }
+}
+
+// one CTA per block of `len` consecutive amplitudes (len >= kStreamThreads)
+__global__ void __launch_bounds__(kStreamThreads) block_norms_cta_kernel(const double2* psi, uint64_t len, double* out)
+{
+     __shared__ double scratch[kStreamThreads / 32];
+     const double2* p = psi + static_cast<uint64_t>(blockIdx.x) * len;
+     double acc[4] = {0.0, 0.0, 0.0, 0.0};
+     uint64_t i = threadIdx.x;
+     for (; i + 3 * kStreamThreads < len; i += 4 * kStreamThreads) {
+          double2 v[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) v[u] = ldg_stream(p + i + u * kStreamThreads);
+#pragma unroll
+          for (int u = 0; u < 4; ++u) acc[u] += norm2(v[u]);
+     }
+     for (; i < len; i += kStreamThreads) acc[0] += norm2(p[i]);
+     const double s = block_sum<kStreamThreads>((acc[0] + acc[1]) + (acc[2] + acc[3]), scratch);
+     if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// small blocks: one thread per block, sequential like the reference loop
+__global__ void block_norms_thread_kernel(const double2* psi, uint64_t len, uint64_t n_blocks, double* out)
+{
+     const uint64_t b = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+     if (b >= n_blocks) return;
+     double acc = 0.0;
+     for (uint64_t j = 0; j < len; ++j) acc += norm2(psi[b * len + j]);
+     out[b] = acc;
+}
+
+// ----------------------------------------------------------------------------- compaction
+__global__ void __launch_bounds__(kStreamThreads) compact_gather_kernel(const double2* src, double2* scratch, uint64_t j0,
+                                                                         uint64_t count, int slot, uint64_t keep_bit)
+{
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     const uint64_t low_mask = (1ull << slot) - 1ull;
+     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x; i < count; i += stride) {
+          const uint64_t j = j0 + i;
+          const uint64_t s = ((j >> slot) << (slot + 1)) | keep_bit | (j & low_mask);
+          scratch[i] = ldg_stream(src + s);
+     }
+}
+
+__global__ void __launch_bounds__(kStreamThreads) copy_kernel(const double2* src, double2* dst, uint64_t count)
+{
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x; i < count; i += stride)
+          dst[i] = src[i];
+}
+
+// ----------------------------------------------------------------------------- swap pack / unpack
+struct SwapParams {
+     double2* psi;
+     double2* buf;
+     uint64_t begin, count;
+     uint64_t pat_bits;  // pattern spread onto the swapped slots
+     InsertBits ins;     // swapped slots, ascending
+};
+
+template <bool PACK>
+__global__ void __launch_bounds__(kStreamThreads) swap_pack_kernel(const __grid_constant__ SwapParams p)
+{
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kStreamThreads;
+     for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * kStreamThreads + threadIdx.x; i < p.count; i += stride) {
+          const uint64_t idx = insert_zero_bits(p.begin + i, p.ins) | p.pat_bits;
+          if (PACK) p.buf[i] = ldg_stream(p.psi + idx);
+          else p.psi[idx] = ldg_stream(p.buf + i);
+     }
+}
+
+static InsertBits bits_of_mask(uint64_t mask)
+{
+     InsertBits ib;
+     std::memset(&ib, 0, sizeof(ib));
+     for (int s = 0; s < 64; ++s)
+          if ((mask >> s) & 1ull) ib.pos[ib.n++] = static_cast<uint8_t>(s);
+     return ib;
+}
+
+}  // namespace hiq
+
+using namespace hiq;
+
+extern "C" int hiqk_apply_diag(void* slab, int L, int k, const int* slots, const double* diag, uint64_t ctrl_mask,
+                               void* stream)
+{
+     if (!slab || !slots || !diag) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag: null argument");
+     if (k < 1 || k > kMaxTargets || L < k || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag: bad k or L");
+     DiagParams p;
+     std::memset(&p, 0, sizeof(p));
+     uint64_t tmask = 0;
+     for (int l = 0; l < k; ++l) {
+          if (slots[l] < 0 || slots[l] >= L || ((tmask >> slots[l]) & 1))
+               return set_error(HIQ_ERR_ARG, "hiqk_apply_diag: target slots must be distinct and < L");
+          tmask |= 1ull << slots[l];
+          p.slots[l] = slots[l];
+     }
+     if ((ctrl_mask & tmask) || (ctrl_mask >> L)) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag: bad control mask");
+     p.psi = static_cast<double2*>(slab);
+     p.k = k;
+     p.ctrl_mask = ctrl_mask;
+     p.ins = bits_of_mask(ctrl_mask);
+     p.n_free = 1ull << (L - p.ins.n);
+     std::memcpy(p.d, diag, sizeof(double2) << k);
+     diag_kernel<<<stream_grid(p.n_free), kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
+     count_launch();
+     return check_launch("diag_kernel");
+}
+
+extern "C" int hiqk_scale(void* slab, int L, double re, double im, void* stream)
+{
+     if (!slab || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_scale: bad argument");
+     const uint64_t n = 1ull << L;
+     scale_kernel<<<stream_grid(n), kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<double2*>(slab), n,
+                                                                                            make_double2(re, im));
+     count_launch();
+     return check_launch("scale_kernel");
+}
+
+extern "C" size_t hiqk_workspace_bytes(void) { return sizeof(double) * 2 * kMaxPartials; }
+
+static int launch_reduce(int mode, const void* slab, int L, uint64_t mask, uint64_t val, double* d_out, void* workspace,
+                         void* stream)
+{
+     if (!slab || !d_out || !workspace || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "reduce: bad argument");
+     if ((mask >> L) || (val & ~mask)) return set_error(HIQ_ERR_ARG, "reduce: mask/val outside the slab");
+     ReduceParams p;
+     p.psi = static_cast<const double2*>(slab);
+     p.ins = bits_of_mask(mask);
+     p.n_free = 1ull << (L - p.ins.n);
+     p.val = val;
+     const unsigned grid = std::min<unsigned>(stream_grid(p.n_free), kMaxPartials);
+     double* partials = static_cast<double*>(workspace);
+     cudaStream_t st = static_cast<cudaStream_t>(stream);
+     if (mode == RED_NORM) reduce_kernel<RED_NORM><<<grid, kStreamThreads, 0, st>>>(p, partials);
+     else reduce_kernel<RED_ENTROPY><<<grid, kStreamThreads, 0, st>>>(p, partials);
+     fold_kernel<<<1, 1024, 0, st>>>(partials, static_cast<int>(grid), 1, d_out);
+     count_launch(2);
+     return check_launch("reduce_kernel");
+}
+
+extern "C" int hiqk_prob_masked(const void* slab, int L, uint64_t mask, uint64_t val, double* d_out, void* workspace,
+                                void* stream)
+{
+     return launch_reduce(RED_NORM, slab, L, mask, val, d_out, workspace, stream);
+}
+
+extern "C" int hiqk_entropy(const void* slab, int L, double* d_out, void* workspace, void* stream)
+{
+     return launch_reduce(RED_ENTROPY, slab, L, 0, 0, d_out, workspace, stream);
+}
+
+extern "C" int hiqk_bit_norms(const void* slab, int L, int slot, double* d_out, void* workspace, void* stream)
+{
+     if (!slab || !d_out || !workspace || L < 1 || L > 40 || slot < 0 || slot >= L)
+          return set_error(HIQ_ERR_ARG, "hiqk_bit_norms: bad argument");
+     const uint64_t n = 1ull << L;
+     const unsigned grid = std::min<unsigned>(stream_grid(n), kMaxPartials);
+     double* partials = static_cast<double*>(workspace);
+     cudaStream_t st = static_cast<cudaStream_t>(stream);
+     bit_norms_kernel<<<grid, kStreamThreads, 0, st>>>(static_cast<const double2*>(slab), n, slot, partials);
+     fold_kernel<<<1, 1024, 0, st>>>(partials, static_cast<int>(grid), 2, d_out);
+     count_launch(2);
+     return check_launch("bit_norms_kernel");
+}
+
+extern "C" int hiqk_block_norms(const void* slab, int L, uint64_t n_blocks, double* d_out, void* stream)
+{
+     if (!slab || !d_out || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_block_norms: bad argument");
+     const uint64_t n = 1ull << L;
+     if (n_blocks == 0 || (n_blocks & (n_blocks - 1)) || n_blocks > n || n_blocks > (1ull << 20))
+          return set_error(HIQ_ERR_ARG, "hiqk_block_norms: n_blocks must be a power of two <= 2^L");
+     const uint64_t len = n / n_blocks;
+     cudaStream_t st = static_cast<cudaStream_t>(stream);
+     const double2* psi = static_cast<const double2*>(slab);
+     if (len >= kStreamThreads) block_norms_cta_kernel<<<static_cast<unsigned>(n_blocks), kStreamThreads, 0, st>>>(psi, len, d_out);
+     else block_norms_thread_kernel<<<static_cast<unsigned>((n_blocks + 127) / 128), 128, 0, st>>>(psi, len, n_blocks, d_out);
+     count_launch();
+     return check_launch("block_norms_kernel");
+}
+
+extern "C" int hiqk_collapse(void* slab, int L, uint64_t mask, uint64_t val, double scale, void* stream)
+{
+     if (!slab || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_collapse: bad argument");
+     const uint64_t n = 1ull << L;
+     collapse_kernel<<<stream_grid(n), kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<double2*>(slab), n,
+                                                                                               mask, val, scale);
+     count_launch();
+     return check_launch("collapse_kernel");
+}
+
+extern "C" int hiqk_fill(void* slab, uint64_t begin, uint64_t count, double re, double im, void* stream)
+{
+     if (!slab) return set_error(HIQ_ERR_ARG, "hiqk_fill: null slab");
+     if (count == 0) return HIQ_OK;
+     fill_kernel<<<stream_grid(count), kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+         static_cast<double2*>(slab) + begin, count, make_double2(re, im));
+     count_launch();
+     return check_launch("fill_kernel");
+}
+
+extern "C" int hiqk_compact_bit(void* slab, int L, int slot, int keep, void* scratch, uint64_t scratch_amps, void* stream)
+{
+     if (!slab || !scratch || L < 1 || L > 40 || slot < 0 || slot >= L || scratch_amps == 0)
+          return set_error(HIQ_ERR_ARG, "hiqk_compact_bit: bad argument");
+     const uint64_t half = 1ull << (L - 1);
+     double2* psi = static_cast<double2*>(slab);
+     double2* tmp = static_cast<double2*>(scratch);
+     cudaStream_t st = static_cast<cudaStream_t>(stream);
+     const uint64_t keep_bit = keep ? (1ull << slot) : 0ull;
+     // Chunks are processed in index order: chunk c only reads source indices >= its first
+     // destination index, which no earlier chunk has written.
+     for (uint64_t j0 = 0; j0 < half; j0 += scratch_amps) {
+          const uint64_t cnt = std::min(scratch_amps, half - j0);
+          compact_gather_kernel<<<stream_grid(cnt), kStreamThreads, 0, st>>>(psi, tmp, j0, cnt, slot, keep_bit);
+          copy_kernel<<<stream_grid(cnt), kStreamThreads, 0, st>>>(tmp, psi + j0, cnt);
+          count_launch(2);
+     }
+     return check_launch("compact_kernel");
+}
+
+static int launch_swap(bool pack, void* slab, int L, int q, const int* slots, uint64_t pat, uint64_t begin, uint64_t count,
+                       void* buf, void* stream)
+{
+     if (!slab || !buf || !slots || q < 1 || q > L || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_swap_pack: bad argument");
+     SwapParams p;
+     std::memset(&p, 0, sizeof(p));
+     uint64_t mask = 0;
+     std::vector<int> sorted(slots, slots + q);
+     std::sort(sorted.begin(), sorted.end());
+     for (int i = 0; i < q; ++i) {
+          if (sorted[i] < 0 || sorted[i] >= L || ((mask >> sorted[i]) & 1)) return set_error(HIQ_ERR_ARG, "hiqk_swap_pack: bad slots");
+          mask |= 1ull << sorted[i];
+          if ((pat >> i) & 1ull) p.pat_bits |= 1ull << sorted[i];
+     }
+     if (begin + count > (1ull << (L - q))) return set_error(HIQ_ERR_ARG, "hiqk_swap_pack: range outside the slab");
+     if (count == 0) return HIQ_OK;
+     p.psi = static_cast<double2*>(slab);
+     p.buf = static_cast<double2*>(buf);
+     p.begin = begin;
+     p.count = count;
+     p.ins = bits_of_mask(mask);
+     cudaStream_t st = static_cast<cudaStream_t>(stream);
+     if (pack) swap_pack_kernel<true><<<stream_grid(count), kStreamThreads, 0, st>>>(p);
+     else swap_pack_kernel<false><<<stream_grid(count), kStreamThreads, 0, st>>>(p);
+     count_launch();
+     return check_launch("swap_pack_kernel");
+}
+
+extern "C" int hiqk_swap_pack(const void* slab, int L, int q, const int* slots, uint64_t pat, uint64_t begin, uint64_t count,
+                              void* dst, void* stream)
+{
+     return launch_swap(true, const_cast<void*>(slab), L, q, slots, pat, begin, count, dst, stream);
+}
+
+extern "C" int hiqk_swap_unpack(void* slab, int L, int q, const int* slots, uint64_t pat, uint64_t begin, uint64_t count,
+                                const void* src, void* stream)
+{
+     return launch_swap(false, slab, L, q, slots, pat, begin, count, const_cast<void*>(src), stream);
+}

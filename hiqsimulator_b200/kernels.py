@@ -1,0 +1,133 @@
+"""Python-side launchers for the device-level C ABI (``hiqk_*``) operating on torch CUDA tensors.
+
+torch is used here only as the owner of device memory and streams; every computation is one of
+this repository's own CUDA kernels reached through ``libhiq_b200.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+
+from ._lib import check, lib
+
+AUTO, DIRECT, TILED, DMMA = 0, 1, 2, 3
+
+
+def _slab(t):
+    import torch
+    assert t.is_cuda and t.dtype == torch.complex128 and t.is_contiguous()
+    n = t.numel()
+    L = int(round(math.log2(n)))
+    assert 1 << L == n
+    return C.c_void_p(t.data_ptr()), L
+
+
+def _stream():
+    import torch
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ints(v):
+    return (C.c_int * len(v))(*[int(x) for x in v])
+
+
+def _cplx(m):
+    a = np.ascontiguousarray(np.asarray(m, dtype=np.complex128))
+    return a, a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def apply_dense(state, slots, matrix, ctrl_mask=0, variant=AUTO):
+    p, L = _slab(state)
+    keep, mp = _cplx(matrix)
+    check(lib().hiqk_apply_dense(p, L, len(slots), _ints(slots), mp, ctrl_mask, variant, _stream()))
+
+
+def apply_diag(state, slots, diag, ctrl_mask=0):
+    p, L = _slab(state)
+    keep, dp = _cplx(diag)
+    check(lib().hiqk_apply_diag(p, L, len(slots), _ints(slots), dp, ctrl_mask, _stream()))
+
+
+def scale(state, factor):
+    p, L = _slab(state)
+    f = complex(factor)
+    check(lib().hiqk_scale(p, L, f.real, f.imag, _stream()))
+
+
+_ws = {}
+
+
+def _workspace(device):
+    import torch
+    key = str(device)
+    if key not in _ws:
+        _ws[key] = torch.empty(lib().hiqk_workspace_bytes() // 8, dtype=torch.float64, device=device)
+    return _ws[key]
+
+
+def prob_masked(state, mask=0, val=0) -> float:
+    import torch
+    p, L = _slab(state)
+    out = torch.empty(1, dtype=torch.float64, device=state.device)
+    check(lib().hiqk_prob_masked(p, L, mask, val, C.c_void_p(out.data_ptr()),
+                                 C.c_void_p(_workspace(state.device).data_ptr()), _stream()))
+    return float(out.item())
+
+
+def entropy_sum(state) -> float:
+    import torch
+    p, L = _slab(state)
+    out = torch.empty(1, dtype=torch.float64, device=state.device)
+    check(lib().hiqk_entropy(p, L, C.c_void_p(out.data_ptr()),
+                             C.c_void_p(_workspace(state.device).data_ptr()), _stream()))
+    return float(out.item())
+
+
+def bit_norms(state, slot):
+    import torch
+    p, L = _slab(state)
+    out = torch.empty(2, dtype=torch.float64, device=state.device)
+    check(lib().hiqk_bit_norms(p, L, slot, C.c_void_p(out.data_ptr()),
+                               C.c_void_p(_workspace(state.device).data_ptr()), _stream()))
+    return out.cpu().numpy()
+
+
+def block_norms(state, n_blocks):
+    import torch
+    p, L = _slab(state)
+    out = torch.empty(n_blocks, dtype=torch.float64, device=state.device)
+    check(lib().hiqk_block_norms(p, L, n_blocks, C.c_void_p(out.data_ptr()), _stream()))
+    return out.cpu().numpy()
+
+
+def collapse(state, mask, val, scale_factor):
+    p, L = _slab(state)
+    check(lib().hiqk_collapse(p, L, mask, val, float(scale_factor), _stream()))
+
+
+def fill(state, begin, count, value):
+    v = complex(value)
+    check(lib().hiqk_fill(C.c_void_p(state.data_ptr()), begin, count, v.real, v.imag, _stream()))
+
+
+def compact_bit(state, slot, keep, scratch):
+    p, L = _slab(state)
+    check(lib().hiqk_compact_bit(p, L, slot, int(keep), C.c_void_p(scratch.data_ptr()), scratch.numel(), _stream()))
+
+
+def swap_pack(state, slots, pat, begin, count, buf):
+    p, L = _slab(state)
+    check(lib().hiqk_swap_pack(p, L, len(slots), _ints(slots), pat, begin, count, C.c_void_p(buf.data_ptr()), _stream()))
+
+
+def swap_unpack(state, slots, pat, begin, count, buf):
+    p, L = _slab(state)
+    check(lib().hiqk_swap_unpack(p, L, len(slots), _ints(slots), pat, begin, count, C.c_void_p(buf.data_ptr()), _stream()))
+
+
+def microbench(what: int, iters: int = 5) -> float:
+    out = C.c_double(0.0)
+    check(lib().hiqk_microbench(what, iters, C.byref(out)))
+    return out.value

@@ -1,0 +1,214 @@
+"""Parity of the device-level launchers (C ABI, hiqk_*) against the numpy oracle.
+
+Every case runs one kernel pass on cuda:0 through libhiq_b200.so and compares the whole slab
+with oracle/statevec.py (itself pinned against the compiled reference).  Tolerance 1e-12
+absolute on amplitudes (BASELINE.json north_star); reductions 1e-12 absolute.
+"""
+import itertools
+
+import numpy as np
+import pytest
+
+from oracle import statevec
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def rand_state(L, seed):
+    rng = np.random.default_rng(seed)
+    v = rng.normal(size=1 << L) + 1j * rng.normal(size=1 << L)
+    return v / np.linalg.norm(v)
+
+
+def rand_matrix(k, seed):
+    rng = np.random.default_rng(seed)
+    z = rng.normal(size=(1 << k, 1 << k)) + 1j * rng.normal(size=(1 << k, 1 << k))
+    q, r = np.linalg.qr(z)
+    return q * (np.diag(r) / np.abs(np.diag(r)))
+
+
+def dense_cases():
+    from hiqsimulator_b200 import kernels as K
+    cases = []
+    L = 14
+    slot_sets = {
+        1: [[0], [1], [2], [5], [13]],
+        2: [[0, 1], [1, 0], [3, 9], [13, 2], [12, 13]],
+        3: [[0, 1, 2], [2, 0, 7], [4, 5, 6], [13, 6, 1], [11, 12, 13]],
+        4: [[0, 1, 2, 3], [3, 1, 2, 0], [5, 2, 9, 12], [10, 11, 12, 13], [13, 0, 6, 3], [4, 8, 6, 10]],
+        5: [[0, 1, 2, 3, 4], [9, 10, 11, 12, 13], [1, 5, 3, 12, 8], [2, 4, 6, 8, 10]],
+    }
+    for k, sets in slot_sets.items():
+        for slots in sets:
+            for variant in (K.AUTO, K.DIRECT, K.TILED, K.DMMA):
+                for ctrl in (0, "one", "three"):
+                    cases.append((L, k, tuple(slots), variant, ctrl))
+    return cases
+
+
+def _ctrl_mask(L, slots, kind, seed):
+    if kind == 0:
+        return 0
+    free = [s for s in range(L) if s not in slots]
+    rng = np.random.default_rng(seed)
+    n = 1 if kind == "one" else 3
+    pick = rng.choice(free, size=n, replace=False)
+    m = 0
+    for s in pick:
+        m |= 1 << int(s)
+    return m
+
+
+@pytest.mark.parametrize("L,k,slots,variant,ctrl", dense_cases())
+def test_apply_dense(L, k, slots, variant, ctrl):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    seed = hash((L, k, slots, str(ctrl))) & 0xFFFF
+    ref = rand_state(L, seed)
+    m = rand_matrix(k, seed + 1)
+    cm = _ctrl_mask(L, slots, ctrl, seed)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_dense(dev, list(slots), m, cm, variant)
+    statevec.apply_dense(ref, list(slots), m, cm)
+    got = dev.cpu().numpy()
+    assert np.abs(got - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("L", [3, 5, 6, 8, 9, 10, 11, 12])
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5])
+def test_apply_dense_small_slabs(L, k):
+    if k > L:
+        pytest.skip("k > L")
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    rng = np.random.default_rng(L * 10 + k)
+    for trial in range(4):
+        slots = [int(s) for s in rng.choice(L, size=k, replace=False)]
+        for variant in (K.AUTO, K.DMMA):
+            ref = rand_state(L, trial)
+            m = rand_matrix(k, trial + 7)
+            dev = torch.from_numpy(ref.copy()).cuda()
+            K.apply_dense(dev, slots, m, 0, variant)
+            statevec.apply_dense(ref, slots, m, 0)
+            assert np.abs(dev.cpu().numpy() - ref).max() <= TOL, (slots, variant)
+
+
+def test_apply_dense_many_controls():
+    """Huge-gate path: k=1 with a wide control mask (reference: SimulatorMPI.cpp:752-756)."""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 16
+    ref = rand_state(L, 3)
+    m = rand_matrix(1, 4)
+    cm = ((1 << L) - 1) & ~(1 << 7)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_dense(dev, [7], m, cm)
+    statevec.apply_dense(ref, [7], m, cm)
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("k,slots,ctrl", [(1, (0,), 0), (1, (9,), "one"), (2, (3, 0), 0), (3, (13, 1, 6), "three"),
+                                          (4, (2, 3, 4, 5), 0), (5, (0, 13, 5, 7, 2), "one")])
+def test_apply_diag(k, slots, ctrl):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    ref = rand_state(L, 11 + k)
+    rng = np.random.default_rng(k)
+    d = np.exp(1j * rng.uniform(0, 2 * np.pi, size=1 << k))
+    cm = _ctrl_mask(L, slots, ctrl, 5)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_diag(dev, list(slots), d, cm)
+    statevec.apply_diag(ref, list(slots), d, cm)
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+def test_scale_fill_collapse():
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 13
+    ref = rand_state(L, 21)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.scale(dev, 0.3 - 0.4j)
+    assert np.abs(dev.cpu().numpy() - ref * (0.3 - 0.4j)).max() <= TOL
+    dev = torch.from_numpy(ref.copy()).cuda()
+    mask, val = 0b1010010, 0b1000010
+    K.collapse(dev, mask, val, 1.7)
+    i = np.arange(1 << L)
+    exp = np.where((i & mask) == val, ref * 1.7, 0)
+    assert np.abs(dev.cpu().numpy() - exp).max() <= TOL
+    K.fill(dev, 16, 100, 0.25 + 0.5j)
+    got = dev.cpu().numpy()
+    assert np.all(got[16:116] == 0.25 + 0.5j) and np.abs(got[:16] - exp[:16]).max() == 0
+
+
+@pytest.mark.parametrize("L", [1, 4, 9, 14, 20])
+def test_reductions(L):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    ref = rand_state(L, 31 + L)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    p = np.abs(ref) ** 2
+    assert abs(K.prob_masked(dev) - p.sum()) <= TOL
+    i = np.arange(1 << L)
+    for mask, val in [(1, 1), (1, 0), ((1 << L) - 1, 5 % (1 << L)), (0b101 & ((1 << L) - 1), 0b100 & ((1 << L) - 1))]:
+        assert abs(K.prob_masked(dev, mask, val) - p[(i & mask) == val].sum()) <= TOL
+    for slot in {0, L // 2, L - 1}:
+        got = K.bit_norms(dev, slot)
+        bit = (i >> slot) & 1
+        assert abs(got[0] - p[bit == 0].sum()) <= TOL and abs(got[1] - p[bit == 1].sum()) <= TOL
+    e = (p[p > 0] * np.log2(p[p > 0])).sum()
+    assert abs(K.entropy_sum(dev) - e) <= 1e-10
+    for nb in {1, 2, min(1 << L, 1 << 15)}:
+        if nb > (1 << L):
+            continue
+        got = K.block_norms(dev, nb)
+        assert np.abs(got - p.reshape(nb, -1).sum(axis=1)).max() <= TOL
+
+
+@pytest.mark.parametrize("slot,keep", [(0, 0), (0, 1), (5, 1), (11, 0), (12, 1)])
+def test_compact_bit(slot, keep):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 13
+    ref = rand_state(L, 41)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    scratch = torch.empty(300, dtype=torch.complex128, device="cuda")  # forces many chunks
+    K.compact_bit(dev, slot, keep, scratch)
+    exp = ref.reshape(-1, 2, 1 << slot)[:, keep, :].reshape(-1)
+    assert np.abs(dev.cpu().numpy()[: 1 << (L - 1)] - exp).max() == 0
+
+
+@pytest.mark.parametrize("slots", [(0,), (12,), (3, 7), (0, 1, 2), (11, 4, 9)])
+def test_swap_pack_unpack(slots):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 13
+    q = len(slots)
+    ref = rand_state(L, 51)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    n = 1 << (L - q)
+    srt = sorted(slots)
+    i = np.arange(1 << L)
+    for pat in range(1 << q):
+        sel = np.ones(1 << L, dtype=bool)
+        for b, s in enumerate(srt):
+            sel &= ((i >> s) & 1) == ((pat >> b) & 1)
+        buf = torch.zeros(n, dtype=torch.complex128, device="cuda")
+        K.swap_pack(dev, list(slots), pat, 0, n, buf)
+        assert np.abs(buf.cpu().numpy() - ref[sel]).max() == 0
+        # unpack pattern `pat` data into the positions of the complementary pattern
+        other = pat ^ ((1 << q) - 1)
+        K.swap_unpack(dev, list(slots), other, 0, n, buf)
+        sel2 = np.ones(1 << L, dtype=bool)
+        for b, s in enumerate(srt):
+            sel2 &= ((i >> s) & 1) == ((other >> b) & 1)
+        got = dev.cpu().numpy()
+        assert np.abs(got[sel2] - ref[sel]).max() == 0
+        dev = torch.from_numpy(ref.copy()).cuda()
