@@ -59,7 +59,7 @@ def load_library(path: str | None = None):
         raise LibraryMissing(
             "%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
             "(there is no CPU fallback)" % path)
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
         fn.restype = res

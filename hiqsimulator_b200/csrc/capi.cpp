@@ -1,0 +1,271 @@
+// extern "C" surface of the engine (include/hiq_b200.h): plain pointers and sizes in, status
+// codes out; C++ exceptions never cross the boundary.
+#include <cstring>
+
+#include "engine.hpp"
+#include "hiq_host.hpp"
+
+using namespace hiq;
+
+struct hiq_engine {
+     Engine impl;
+     template <class... A>
+     explicit hiq_engine(A&&... a) : impl(std::forward<A>(a)...) {}
+};
+
+template <class F>
+static int guarded(F&& f)
+{
+     try {
+          f();
+          return HIQ_OK;
+     }
+     catch (const EngineError& e) {
+          return set_error(e.code, e.what());
+     }
+     catch (const std::exception& e) {
+          return set_error(HIQ_ERR_RUNTIME, e.what());
+     }
+}
+
+#define NEED(e) \
+     if (!(e)) return set_error(HIQ_ERR_ARG, "null engine handle")
+
+static std::vector<Index> vec_ids(const int64_t* p, int n) { return std::vector<Index>(p, p + (n > 0 ? n : 0)); }
+static std::vector<bool> vec_bits(const uint8_t* p, int n)
+{
+     std::vector<bool> v(n > 0 ? n : 0);
+     for (int i = 0; i < n; ++i) v[i] = p[i] != 0;
+     return v;
+}
+
+extern "C" {
+
+int hiq_create(uint64_t seed, int max_local, int max_cluster_size, int rank, int world_size, const void* nccl_id, int device,
+               int flags, hiq_engine** out)
+{
+     if (!out) return set_error(HIQ_ERR_ARG, "hiq_create: null output");
+     *out = nullptr;
+     return guarded([&] { *out = new hiq_engine(seed, max_local, max_cluster_size, rank, world_size, nccl_id, device, flags); });
+}
+
+int hiq_destroy(hiq_engine* e)
+{
+     delete e;
+     return HIQ_OK;
+}
+
+int hiq_allocate_qubit(hiq_engine* e, int64_t id)
+{
+     NEED(e);
+     return guarded([&] { e->impl.allocate_qubit(id); });
+}
+
+int hiq_allocate_qureg(hiq_engine* e, const int64_t* ids, int n, double init_re, double init_im)
+{
+     NEED(e);
+     return guarded([&] { e->impl.allocate_qureg(vec_ids(ids, n), cplx(init_re, init_im)); });
+}
+
+int hiq_deallocate_qubit(hiq_engine* e, int64_t id)
+{
+     NEED(e);
+     return guarded([&] { e->impl.deallocate_qubit(id); });
+}
+
+int hiq_apply_controlled_gate(hiq_engine* e, const double* matrix, int dim, const int64_t* ids, int n_ids, const int64_t* ctrls,
+                              int n_ctrls)
+{
+     NEED(e);
+     if (!matrix || dim < 1 || dim > 32) return set_error(HIQ_ERR_ARG, "hiq_apply_controlled_gate: bad matrix");
+     return guarded([&] {
+          GateMatrix m(dim);
+          std::memcpy(static_cast<void*>(m.a.data()), matrix, sizeof(cplx) * dim * dim);
+          e->impl.apply_gate(std::move(m), vec_ids(ids, n_ids), vec_ids(ctrls, n_ctrls));
+     });
+}
+
+int hiq_run(hiq_engine* e)
+{
+     NEED(e);
+     return guarded([&] { e->impl.run(); });
+}
+
+int hiq_swap_qubits(hiq_engine* e, const int64_t* pairs, int n)
+{
+     NEED(e);
+     return guarded([&] { e->impl.swap_qubits_stage(vec_ids(pairs, n)); });
+}
+
+int hiq_measure_qubits(hiq_engine* e, const int64_t* ids, int n, uint8_t* out_bits)
+{
+     NEED(e);
+     return guarded([&] {
+          auto r = e->impl.measure_qubits(vec_ids(ids, n));
+          for (int i = 0; i < n; ++i) out_bits[i] = r[i] ? 1 : 0;
+     });
+}
+
+int hiq_get_probability(hiq_engine* e, const uint8_t* bits, const int64_t* ids, int n, double* out)
+{
+     NEED(e);
+     return guarded([&] { *out = e->impl.get_probability(vec_bits(bits, n), vec_ids(ids, n)); });
+}
+
+int hiq_get_amplitude(hiq_engine* e, const uint8_t* bits, const int64_t* ids, int n, double* out_re_im)
+{
+     NEED(e);
+     return guarded([&] {
+          const cplx v = e->impl.get_amplitude(vec_bits(bits, n), vec_ids(ids, n));
+          out_re_im[0] = v.real();
+          out_re_im[1] = v.imag();
+     });
+}
+
+int hiq_collapse_wavefunction(hiq_engine* e, const int64_t* ids, const uint8_t* values, int n)
+{
+     NEED(e);
+     return guarded([&] { e->impl.collapse_wavefunction(vec_ids(ids, n), vec_bits(values, n)); });
+}
+
+int hiq_entropy(hiq_engine* e, double* out)
+{
+     NEED(e);
+     return guarded([&] { *out = e->impl.entropy(); });
+}
+
+int hiq_get_qubits_ids(hiq_engine* e, int kind, int64_t* out, int cap, int* n)
+{
+     NEED(e);
+     return guarded([&] {
+          std::vector<Index> v = kind == 0 ? e->impl.qubits_permutation() : (kind == 1 ? e->impl.locals() : e->impl.globals());
+          *n = static_cast<int>(v.size());
+          if (out) {
+               if (cap < *n) throw EngineError(HIQ_ERR_ARG, "hiq_get_qubits_ids: buffer too small");
+               std::copy(v.begin(), v.end(), out);
+          }
+     });
+}
+
+int hiq_set_qubits_perm(hiq_engine* e, const int64_t* p, int n)
+{
+     NEED(e);
+     return guarded([&] { e->impl.set_qubits_permutation(vec_ids(p, n)); });
+}
+
+int hiq_cheat_local(hiq_engine* e, int64_t* ids, int* pos, int cap, int* n_map, void* host_dst, uint64_t cap_amps, uint64_t* n_amps)
+{
+     NEED(e);
+     return guarded([&] {
+          auto m = e->impl.id2pos();
+          if (n_map) *n_map = static_cast<int>(m.size());
+          if (ids && pos) {
+               if (cap < static_cast<int>(m.size())) throw EngineError(HIQ_ERR_ARG, "hiq_cheat_local: map buffer too small");
+               int i = 0;
+               for (auto& kv: m) {
+                    ids[i] = kv.first;
+                    pos[i] = kv.second;
+                    ++i;
+               }
+          }
+          if (n_amps) *n_amps = 1ull << e->impl.local_qubits();
+          if (host_dst) e->impl.copy_slab_to_host(host_dst, cap_amps);
+     });
+}
+
+int hiq_local_slab(hiq_engine* e, void** dev_ptr, int* L)
+{
+     NEED(e);
+     return guarded([&] {
+          if (e->impl.dry_run()) throw EngineError(HIQ_ERR_RUNTIME, "hiq_local_slab: dry-run engine has no slab");
+          *dev_ptr = e->impl.slab_ptr();
+          *L = e->impl.local_qubits();
+     });
+}
+
+int hiq_set_local_slab(hiq_engine* e, const void* host_src, uint64_t n_amps)
+{
+     NEED(e);
+     return guarded([&] { e->impl.copy_slab_from_host(host_src, n_amps); });
+}
+
+int hiq_synchronize(hiq_engine* e)
+{
+     NEED(e);
+     return guarded([&] { e->impl.synchronize(); });
+}
+
+int hiq_rank(hiq_engine* e, int* rank, int* world_size)
+{
+     NEED(e);
+     *rank = e->impl.rank();
+     *world_size = e->impl.world_size();
+     return HIQ_OK;
+}
+
+int hiq_set_dense_variant(hiq_engine* e, int variant)
+{
+     NEED(e);
+     e->impl.set_dense_variant(variant);
+     return HIQ_OK;
+}
+
+int hiq_get_stats(hiq_engine* e, hiq_stats* out)
+{
+     NEED(e);
+     const EngineStats& s = e->impl.stats();
+     out->total_gates = s.total_gates;
+     out->total_runs = s.total_runs;
+     out->total_stages = s.total_stages;
+     out->total_swaps = s.total_swaps;
+     out->dense_passes = s.dense_passes;
+     out->diag_passes = s.diag_passes;
+     out->scale_passes = s.scale_passes;
+     out->skipped_passes = s.skipped_passes;
+     out->runs_s = s.runs_s;
+     out->swaps_s = s.swaps_s;
+     out->measures_s = s.measures_s;
+     out->allocs_s = s.allocs_s;
+     out->deallocs_s = s.deallocs_s;
+     out->swap_bytes_sent = s.swap_bytes_sent;
+     return HIQ_OK;
+}
+
+int hiq_trace_count(hiq_engine* e, int* n)
+{
+     NEED(e);
+     *n = static_cast<int>(e->impl.trace().size());
+     return HIQ_OK;
+}
+
+int hiq_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux)
+{
+     NEED(e);
+     const auto& t = e->impl.trace();
+     if (i < 0 || i >= static_cast<int>(t.size())) return set_error(HIQ_ERR_ARG, "hiq_trace_get: index out of range");
+     const Descriptor& s = t[i];
+     d->kind = s.kind;
+     d->k = s.k;
+     for (int l = 0; l < 5; ++l) d->slots[l] = s.slots[l];
+     d->ctrl_mask = s.ctrl_mask;
+     d->n_payload = static_cast<int>(s.payload.size());
+     d->n_aux = static_cast<int>(s.aux.size());
+     if (payload) {
+          if (cap_payload < d->n_payload) return set_error(HIQ_ERR_ARG, "hiq_trace_get: payload buffer too small");
+          std::memcpy(payload, s.payload.data(), sizeof(cplx) * s.payload.size());
+     }
+     if (aux) {
+          if (cap_aux < d->n_aux) return set_error(HIQ_ERR_ARG, "hiq_trace_get: aux buffer too small");
+          std::copy(s.aux.begin(), s.aux.end(), aux);
+     }
+     return HIQ_OK;
+}
+
+int hiq_trace_clear(hiq_engine* e)
+{
+     NEED(e);
+     e->impl.clear_trace();
+     return HIQ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,43 @@
+// Rank-to-rank communication of the engine: one process per GPU, NCCL over NVLink/NVSwitch.
+//
+// Replaces the reference's Boost.MPI call sites (reference: SimulatorMPI.cpp:87,289,335,648,692,
+// 863,908,964 and the all_to_all in SwapperMT.cpp:115).  World size 1 needs no communicator and
+// every collective degenerates to a local copy.
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>
+
+#include <cstdint>
+#include <vector>
+
+namespace hiq {
+
+class Comm {
+public:
+     Comm() = default;
+     ~Comm();
+     Comm(const Comm&) = delete;
+     Comm& operator=(const Comm&) = delete;
+
+     // world_size == 1: `unique_id` may be null.  Otherwise all ranks pass the 128-byte id that
+     // rank 0 obtained from hiq_comm_unique_id() (the launcher distributes it).
+     int init(int rank, int world_size, const void* unique_id, int device);
+
+     int rank() const { return rank_; }
+     int size() const { return size_; }
+     ncclComm_t handle() const { return comm_; }
+
+     // host-value collectives (values staged through a small device buffer on `stream`)
+     int allreduce_sum(double* vals, int n, cudaStream_t stream);
+     int broadcast_bytes(void* host, size_t bytes, int root, cudaStream_t stream);
+     // device collective: every rank contributes n doubles, recv holds size()*n (rank-major)
+     int allgather(const double* dev_send, double* dev_recv, size_t n, cudaStream_t stream);
+
+private:
+     int rank_ = 0;
+     int size_ = 1;
+     ncclComm_t comm_ = nullptr;
+     double* stage_ = nullptr;  // 4 KiB device staging
+};
+
+}  // namespace hiq

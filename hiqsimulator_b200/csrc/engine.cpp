@@ -1,0 +1,678 @@
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <sstream>
+
+#include "hiq_host.hpp"
+#include "nccl_api.hpp"
+
+namespace hiq {
+
+namespace {
+constexpr size_t kNpos = static_cast<size_t>(-1);
+constexpr uint64_t kMaxBlocks = 1ull << 15;        // measurement blocks per rank (reference: SimulatorMPI.cpp:903)
+constexpr uint64_t kCompactScratchAmps = 1ull << 21;  // 32 MiB: stays in L2 between gather and copy
+constexpr uint64_t kSwapPieceAmps = 1ull << 24;       // 256 MiB per peer per piece
+
+std::string list_str(const std::vector<Index>& v)
+{
+     std::ostringstream o;
+     o << "[";
+     for (size_t i = 0; i < v.size(); ++i) o << (i ? ", " : "") << v[i];
+     o << "]";
+     return o.str();
+}
+double seconds_since(std::chrono::steady_clock::time_point t0)
+{
+     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+}  // namespace
+
+void Engine::fail(const std::string& msg) const { throw EngineError(HIQ_ERR_RUNTIME, msg); }
+
+void Engine::cu(int rc) const
+{
+     if (rc != HIQ_OK) throw EngineError(rc, hiq_last_error());
+}
+
+void Engine::need_device(const char* what) const
+{
+     if (dry_run_) fail(std::string(what) + ": not available on a dry-run (descriptor-trace) engine");
+}
+
+Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int world_size, const void* nccl_id, int device,
+               int flags)
+    : min_local_(max_cluster),
+      max_local_(max_local),
+      max_cluster_(max_cluster),
+      rank_(rank),
+      world_(world_size),
+      device_(device),
+      dry_run_(flags & HIQ_FLAG_DRY_RUN),
+      tracing_(flags & (HIQ_FLAG_TRACE | HIQ_FLAG_DRY_RUN))
+{
+     if (world_size < 1 || (world_size & (world_size - 1)) || rank < 0 || rank >= world_size)
+          fail("ctor(): world size must be a power of two and 0 <= rank < world size");
+     if (max_local < 1 || max_local > 40 || max_cluster < 1) fail("ctor(): bad max_local / max_cluster_size");
+     max_global_ = 0;
+     while ((1 << max_global_) < world_size) ++max_global_;
+     globals_.assign(max_global_, kNone);
+     // every rank is handed the same seed (the reference broadcasts rank 0's, SimulatorMPI.cpp:87)
+     rnd_eng_ = std::mt19937(seed);
+     std::uniform_real_distribution<double> dist(0., 1.);
+     rng_ = std::bind(dist, std::ref(rnd_eng_));
+     if (!dry_run_) {
+          cu(check_cuda(cudaSetDevice(device_), "cudaSetDevice"));
+          cu(slab_.init(device_, 1ull << max_local_));
+          cu(check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
+          cu(check_cuda(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
+          cu(comm_.init(rank, world_size, nccl_id, device_));
+          cu(check_cuda(cudaMalloc(&workspace_, hiqk_workspace_bytes()), "cudaMalloc workspace"));
+          cu(check_cuda(cudaMalloc(&d_vals_, 64 * sizeof(double)), "cudaMalloc"));
+          cu(slab_.ensure(1));
+          cu(hiqk_fill(slab_.data(), 0, 1, rank_ == 0 ? 1.0 : 0.0, 0.0, stream_));
+     }
+     ++stats_.total_stages;
+}
+
+Engine::~Engine()
+{
+     if (!dry_run_) {
+          cudaSetDevice(device_);
+          cudaDeviceSynchronize();
+          if (workspace_) cudaFree(workspace_);
+          if (d_vals_) cudaFree(d_vals_);
+          if (d_blocks_) cudaFree(d_blocks_);
+          if (swap_buf_) cudaFree(swap_buf_);
+          slab_.release();
+          if (stream_) cudaStreamDestroy(stream_);
+          if (comm_stream_) cudaStreamDestroy(comm_stream_);
+     }
+}
+
+void Engine::synchronize()
+{
+     if (!dry_run_) cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
+}
+
+size_t Engine::find(const std::vector<Index>& v, Index val) const
+{
+     auto it = std::find(v.begin(), v.end(), val);
+     return it == v.end() ? kNpos : static_cast<size_t>(it - v.begin());
+}
+
+size_t Engine::find_sure(const std::vector<Index>& v, Index val) const
+{
+     const size_t pos = find(v, val);
+     if (pos == kNpos) fail("ArrayFindSure(): Can't find " + std::to_string(val) + " in " + list_str(v));
+     return pos;
+}
+
+uint64_t Engine::ids_to_bits(const std::vector<Index>& ids, const std::vector<Index>& perm) const
+{
+     uint64_t mask = 0;
+     for (Index q: ids) {
+          const size_t pos = find(perm, q);
+          if (pos != kNpos) mask |= 1ull << pos;
+     }
+     return mask;
+}
+
+// ------------------------------------------------------------------------------------ allocation
+void Engine::allocate_local(Index id)
+{
+     const uint64_t old = 1ull << locals_.size();
+     locals_.push_back(id);
+     if (tracing_) {
+          Descriptor d;
+          d.kind = HIQ_DESC_GROW;
+          d.k = static_cast<int>(locals_.size());
+          trace_.push_back(d);
+     }
+     if (dry_run_) return;
+     cu(slab_.ensure(2 * old));
+     cu(check_cuda(cudaMemsetAsync(slab_.data() + old, 0, old * sizeof(double2), stream_), "cudaMemsetAsync"));
+}
+
+void Engine::allocate_global(Index id) { globals_[find_sure(globals_, kNone)] = id; }
+
+void Engine::allocate_qubit(Index id)
+{
+     // policy of the reference (SimulatorMPI.cpp:184-216)
+     const auto t0 = Clock::now();
+     const size_t nloc = locals_.size();
+     if (nloc < min_local_) allocate_local(id);
+     else if (find(globals_, kNone) != kNpos) allocate_global(id);
+     else if (nloc < max_local_) allocate_local(id);
+     else fail("AllocateQubit(): can't allocate more than " + std::to_string(globals_.size() + nloc) + " qubits");
+     stats_.allocs_s += seconds_since(t0);
+}
+
+void Engine::allocate_qureg(const std::vector<Index>& ids, cplx init)
+{
+     if (init != cplx(0.0) && !locals_.empty())
+          fail("AllocateQureg(): initialization of only first qureg is supported");
+     for (Index q: ids) allocate_qubit(q);
+     if (init != cplx(0.0)) {
+          uint64_t gmsk = 0;
+          for (size_t pos = 0; pos < globals_.size(); ++pos)
+               if (globals_[pos] != kNone) gmsk |= 1ull << pos;
+          if ((static_cast<uint64_t>(rank_) & ~gmsk) == 0) {
+               if (tracing_) {
+                    Descriptor d;
+                    d.kind = HIQ_DESC_FILL;
+                    d.payload = {init};
+                    trace_.push_back(d);
+               }
+               if (!dry_run_) cu(hiqk_fill(slab_.data(), 0, 1ull << locals_.size(), init.real(), init.imag(), stream_));
+          }
+     }
+}
+
+void Engine::ensure_scratch()
+{
+     if (!swap_buf_ || swap_buf_bytes_ < kCompactScratchAmps * sizeof(double2)) {
+          if (swap_buf_) cudaFree(swap_buf_);
+          swap_buf_ = nullptr;
+          swap_buf_bytes_ = kCompactScratchAmps * sizeof(double2);
+          cu(check_cuda(cudaMalloc(&swap_buf_, swap_buf_bytes_), "cudaMalloc scratch"));
+     }
+}
+
+void Engine::deallocate_local(Index id)
+{
+     need_device("DeallocateLocalQubit()");
+     const size_t pos = find_sure(locals_, id);
+     const int L = static_cast<int>(locals_.size());
+     double sums[2];
+     cu(hiqk_bit_norms(slab_.data(), L, static_cast<int>(pos), d_vals_, workspace_, stream_));
+     cu(check_cuda(cudaMemcpyAsync(sums, d_vals_, sizeof(sums), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+     synchronize();
+     cu(comm_.allreduce_sum(sums, 2, stream_));
+     if (!((sums[0] > max_float_error_) ^ (sums[1] > max_float_error_)))
+          fail("DeallocateLocalQubit(): qubit " + std::to_string(id) + " is entangled");
+     const int keep = sums[0] > max_float_error_ ? 0 : 1;
+     ensure_scratch();
+     cu(hiqk_compact_bit(slab_.data(), L, static_cast<int>(pos), keep, swap_buf_, kCompactScratchAmps, stream_));
+     locals_.erase(locals_.begin() + pos);
+}
+
+void Engine::deallocate_global(Index id)
+{
+     need_device("DeallocateGlobalQubit()");
+     const size_t pos = find_sure(globals_, id);
+     const int L = static_cast<int>(locals_.size());
+     double local_norm = 0.0;
+     cu(hiqk_prob_masked(slab_.data(), L, 0, 0, d_vals_, workspace_, stream_));
+     cu(check_cuda(cudaMemcpyAsync(&local_norm, d_vals_, sizeof(double), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+     synchronize();
+     double sums[2] = {0.0, 0.0};
+     sums[(rank_ >> pos) & 1] = local_norm;
+     cu(comm_.allreduce_sum(sums, 2, stream_));
+     if (!((sums[0] > max_float_error_) ^ (sums[1] > max_float_error_)))
+          fail("DeallocateGlobalQubit(): qubit " + std::to_string(id) + " is entangled");
+     if (sums[1] > max_float_error_) {
+          // |1>: bring it to the last local slot, flip, send it back (reference: SimulatorMPI.cpp:350-361)
+          const Index local_qubit = locals_.back();
+          swap_qubits({id, local_qubit});
+          GateMatrix x(2);
+          x.at(0, 1) = 1.0;
+          x.at(1, 0) = 1.0;
+          apply_gate(x, {id}, {});
+          run();
+          swap_qubits({local_qubit, id});
+     }
+     globals_[pos] = kNone;
+}
+
+void Engine::deallocate_qubit(Index id)
+{
+     // routing of the reference (SimulatorMPI.cpp:369-426)
+     const auto t0 = Clock::now();
+     const size_t nloc = locals_.size();
+     const size_t nglob = globals_.size() - std::count(globals_.begin(), globals_.end(), kNone);
+     if (find(locals_, id) != kNpos) {
+          if (nloc > min_local_ || nglob == 0) {
+               deallocate_local(id);
+          }
+          else {
+               const Index g = *std::find_if(globals_.begin(), globals_.end(), [](Index q) { return q != kNone; });
+               swap_qubits({g, id});
+               deallocate_global(id);
+          }
+     }
+     else {
+          if (nloc > min_local_ || nglob == 0) {
+               if (locals_.empty()) fail("ArrayFindSure(): Can't find " + std::to_string(id) + " in " + list_str(globals_));
+               swap_qubits({id, locals_.back()});
+               deallocate_local(id);
+          }
+          else {
+               deallocate_global(id);
+          }
+     }
+     stats_.deallocs_s += seconds_since(t0);
+}
+
+// ------------------------------------------------------------------------------------ gates
+void Engine::apply_gate(GateMatrix m, std::vector<Index> ids, std::vector<Index> ctrls)
+{
+     // per-rank preprocessing of the reference (SimulatorMPI.cpp:710-815)
+     if (m.dim != (1 << ids.size())) fail("ApplyGate(): matrix size does not match the number of target qubits");
+     const bool diag = is_diagonal(m);
+     const uint64_t global_id_mask = ids_to_bits(ids, globals_);
+     const uint64_t global_ctrl_mask = ids_to_bits(ctrls, globals_);
+     std::vector<Index> local_ctrls;
+     for (Index c: ctrls)
+          if (find(locals_, c) != kNpos) local_ctrls.push_back(c);
+     const bool huge = ids.size() + local_ctrls.size() > max_cluster_;
+     if (huge) run();  // flush whatever is pending before a gate wider than the cluster
+
+     // Deviation: the reference tests this only on ranks that pass the control filter below and
+     // then blocks in a barrier the other ranks never reach; here every rank raises together.
+     if (global_id_mask != 0 && !diag) fail("ApplyGate(): can't apply non-diagonal gate to global qubits");
+     if ((static_cast<uint64_t>(rank_) & global_ctrl_mask) != global_ctrl_mask) return;  // not this rank
+
+     ++stats_.total_gates;
+     if (huge) {
+          fused_.insert(std::move(m), diag, std::move(ids), ctrls);
+          return;
+     }
+     // keep the rows/columns whose global-target bits equal this rank's bits
+     auto ok_bit = [&](int msk) {
+          for (size_t i = 0; i < ids.size(); ++i) {
+               const size_t pos = find(globals_, ids[i]);
+               if (pos != kNpos && ((msk >> i) & 1) != ((rank_ >> pos) & 1)) return false;
+          }
+          return true;
+     };
+     std::vector<int> keep;
+     for (int i = 0; i < m.dim; ++i)
+          if (ok_bit(i)) keep.push_back(i);
+     GateMatrix sub(static_cast<int>(keep.size()));
+     for (int i = 0; i < sub.dim; ++i)
+          for (int j = 0; j < sub.dim; ++j) sub.at(i, j) = m.at(keep[i], keep[j]);
+     FusionAccumulator::add_controls(sub, ids, local_ctrls);
+     ids.erase(std::remove_if(ids.begin(), ids.end(), [&](Index q) { return find(globals_, q) != kNpos; }), ids.end());
+     fused_.insert(std::move(sub), diag, std::move(ids), {});
+}
+
+void Engine::execute(const Descriptor& d)
+{
+     if (tracing_) trace_.push_back(d);
+     if (dry_run_) return;
+     const int L = static_cast<int>(locals_.size());
+     switch (d.kind) {
+          case HIQ_DESC_DENSE:
+               cu(hiqk_apply_dense(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()), d.ctrl_mask,
+                                   dense_variant_, stream_));
+               break;
+          case HIQ_DESC_DIAG:
+               cu(hiqk_apply_diag(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()), d.ctrl_mask,
+                                  stream_));
+               break;
+          case HIQ_DESC_SCALE: cu(hiqk_scale(slab_.data(), L, d.payload[0].real(), d.payload[0].imag(), stream_)); break;
+          default: break;
+     }
+}
+
+void Engine::run()
+{
+     // fuse and dispatch (reference: SimulatorMPI.cpp:441-541)
+     const auto t0 = Clock::now();
+     GateMatrix m;
+     std::vector<Index> ids, ctrls;
+     bool diag = true;
+     fused_.fuse(m, ids, ctrls, diag);
+     Descriptor d;
+     d.ctrl_mask = ids_to_bits(ctrls, locals_);
+     d.k = static_cast<int>(ids.size());
+     if (d.k > 5) fail("Run(): cannot apply " + std::to_string(d.k) + " qubits gate");
+     for (int l = 0; l < d.k; ++l) d.slots[l] = static_cast<int>(find_sure(locals_, ids[l]));
+     if (d.k == 0) {
+          if (m.at(0, 0) != cplx(1.0)) {
+               d.kind = HIQ_DESC_SCALE;
+               d.payload = {m.at(0, 0)};
+               ++stats_.scale_passes;
+          }
+          else {
+               d.kind = HIQ_DESC_NONE;
+               ++stats_.skipped_passes;
+          }
+     }
+     else if (diag) {
+          d.kind = HIQ_DESC_DIAG;
+          d.payload.resize(m.dim);
+          for (int i = 0; i < m.dim; ++i) d.payload[i] = m.at(i, i);
+          ++stats_.diag_passes;
+     }
+     else {
+          d.kind = HIQ_DESC_DENSE;
+          d.payload = std::move(m.a);
+          ++stats_.dense_passes;
+     }
+     if (d.kind != HIQ_DESC_NONE) execute(d);
+     fused_.reset();
+     ++stats_.total_runs;
+     stats_.runs_s += seconds_since(t0);
+}
+
+// ------------------------------------------------------------------------------------ reductions
+void Engine::masks(const std::vector<Index>& ids, const std::vector<bool>& bits, const char* what, uint64_t& lm, uint64_t& lv,
+                   uint64_t& gm, uint64_t& gv) const
+{
+     if (ids.size() != bits.size()) fail(std::string(what) + ": ids.size() != bit_string.size()");
+     lm = lv = gm = gv = 0;
+     for (size_t i = 0; i < ids.size(); ++i) {
+          size_t pos = find(locals_, ids[i]);
+          if (pos != kNpos) {
+               lm |= 1ull << pos;
+               if (bits[i]) lv |= 1ull << pos;
+          }
+          else {
+               pos = find_sure(globals_, ids[i]);
+               gm |= 1ull << pos;
+               if (bits[i]) gv |= 1ull << pos;
+          }
+     }
+}
+
+double Engine::probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv)
+{
+     // reference: SimulatorMPI.cpp:841-870
+     double p = 0.0;
+     if ((static_cast<uint64_t>(rank_) & gm) == gv) {
+          cu(hiqk_prob_masked(slab_.data(), static_cast<int>(locals_.size()), lm, lv, d_vals_, workspace_, stream_));
+          cu(check_cuda(cudaMemcpyAsync(&p, d_vals_, sizeof(double), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+          synchronize();
+     }
+     cu(comm_.allreduce_sum(&p, 1, stream_));
+     return p;
+}
+
+void Engine::normalize(double norm, uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv)
+{
+     // reference: SimulatorMPI.cpp:872-895
+     const int L = static_cast<int>(locals_.size());
+     if ((static_cast<uint64_t>(rank_) & gm) != gv)
+          cu(check_cuda(cudaMemsetAsync(slab_.data(), 0, sizeof(double2) << L, stream_), "cudaMemsetAsync"));
+     else
+          cu(hiqk_collapse(slab_.data(), L, lm, lv, 1.0 / std::sqrt(norm), stream_));
+}
+
+double Engine::get_probability(const std::vector<bool>& bits, const std::vector<Index>& ids)
+{
+     uint64_t lm, lv, gm, gv;
+     masks(ids, bits, "GetProbability()", lm, lv, gm, gv);
+     need_device("GetProbability()");
+     return probability_internal(lm, lv, gm, gv);
+}
+
+cplx Engine::get_amplitude(const std::vector<bool>& bits, const std::vector<Index>& ids)
+{
+     // reference: SimulatorMPI.cpp:602-650
+     const size_t nq = locals_.size() + globals_.size() - std::count(globals_.begin(), globals_.end(), kNone);
+     if (bits.size() != nq || bits.size() != ids.size()) fail("GetAmplitude(): ids.size() != number of qubits");
+     uint64_t owner = 0, num = 0, check = 0;
+     for (size_t i = 0; i < ids.size(); ++i) {
+          size_t pos = find(locals_, ids[i]);
+          if (pos != kNpos) {
+               if (bits[i]) num |= 1ull << pos;
+               check |= 1ull << pos;
+          }
+          else {
+               pos = find_sure(globals_, ids[i]);
+               if (bits[i]) owner |= 1ull << pos;
+               check |= 1ull << (pos + locals_.size());
+          }
+     }
+     if ((1ull << nq) - 1 != check)
+          fail("GetAmplitude(): the second argument must be a permutation of all allocated qubits.");
+     need_device("GetAmplitude()");
+     cplx value(0.0);
+     if (static_cast<uint64_t>(rank_) == owner) {
+          cu(check_cuda(cudaMemcpyAsync(&value, slab_.data() + num, sizeof(cplx), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+          synchronize();
+     }
+     cu(comm_.broadcast_bytes(&value, sizeof(value), static_cast<int>(owner), stream_));
+     return value;
+}
+
+void Engine::collapse_wavefunction(const std::vector<Index>& ids, const std::vector<bool>& values)
+{
+     // reference: SimulatorMPI.cpp:1010-1058
+     if (ids.size() != values.size()) fail("collapseWaveFunction(): ids.size() != values.size()");
+     uint64_t lm, lv, gm, gv;
+     masks(ids, values, "collapseWaveFunction()", lm, lv, gm, gv);
+     need_device("collapseWaveFunction()");
+     const double norm = probability_internal(lm, lv, gm, gv);
+     if (norm < 1.e-12) fail("collapseWaveFunction(): Invalid collapse! Probability is ~0.");
+     normalize(norm, lm, lv, gm, gv);
+}
+
+std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
+{
+     // two-level inverse-CDF sampling of the reference (SimulatorMPI.cpp:897-1008)
+     need_device("MeasureQubits()");
+     const auto t0 = Clock::now();
+     const int L = static_cast<int>(locals_.size());
+     const uint64_t size = 1ull << L;
+     const uint64_t n = std::min(size, kMaxBlocks);
+     if (!d_blocks_) cu(check_cuda(cudaMalloc(&d_blocks_, sizeof(double) * kMaxBlocks * world_), "cudaMalloc blocks"));
+     cu(hiqk_block_norms(slab_.data(), L, n, d_blocks_ + n * rank_, stream_));
+     cu(comm_.allgather(d_blocks_ + n * rank_, d_blocks_, n, stream_));
+     std::vector<double> tot(n * world_);
+     cu(check_cuda(cudaMemcpyAsync(tot.data(), d_blocks_, sizeof(double) * tot.size(), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+     synchronize();
+     // per-rank inclusive prefix, then the running shift over ranks — same order as the reference
+     double shift = 0.0;
+     for (int r = 0; r < world_; ++r) {
+          double* blk = tot.data() + n * r;
+          for (uint64_t j = 1; j < n; ++j) blk[j] += blk[j - 1];
+          const double new_shift = blk[n - 1];
+          for (uint64_t j = 0; j < n; ++j) blk[j] += shift;
+          shift += new_shift;
+     }
+     const double rnd = rng_();
+     uint64_t i = 0;
+     for (; i < tot.size(); ++i)
+          if (rnd <= tot[i]) break;
+     const uint64_t src_rank = i / n, src_index = i % n;
+     if (static_cast<int>(src_rank) == world_) {
+          std::ostringstream o;
+          o << "MeasureQubits(): Random number " << rnd << " > norm partial sum " << tot.back();
+          fail(o.str());
+     }
+     const uint64_t block_size = size / n;
+     uint64_t k = 0;
+     if (rank_ == static_cast<int>(src_rank)) {
+          double acc = i > 0 ? tot[i - 1] : 0.0;
+          std::vector<cplx> blk(block_size);
+          k = src_index * block_size;
+          cu(check_cuda(cudaMemcpyAsync(blk.data(), slab_.data() + k, sizeof(cplx) * block_size, cudaMemcpyDeviceToHost, stream_),
+                        "cudaMemcpyAsync"));
+          synchronize();
+          for (uint64_t j = 0; j < block_size; ++j, ++k) {
+               acc += std::norm(blk[j]);
+               if (acc >= rnd) break;
+          }
+     }
+     uint64_t res_index = (src_rank << L) + k;
+     cu(comm_.broadcast_bytes(&res_index, sizeof(res_index), static_cast<int>(src_rank), stream_));
+
+     std::vector<bool> res(ids.size());
+     uint64_t lm = 0, lv = 0, gm = 0, gv = 0;
+     for (size_t q = 0; q < ids.size(); ++q) {
+          size_t pos = find(locals_, ids[q]);
+          if (pos != kNpos) {
+               lm |= 1ull << pos;
+               if (res_index & (1ull << pos)) {
+                    lv |= 1ull << pos;
+                    res[q] = true;
+               }
+          }
+          else {
+               pos = find_sure(globals_, ids[q]);
+               gm |= 1ull << pos;
+               if (src_rank & (1ull << pos)) {
+                    gv |= 1ull << pos;
+                    res[q] = true;
+               }
+          }
+     }
+     const double norm = probability_internal(lm, lv, gm, gv);
+     normalize(norm, lm, lv, gm, gv);
+     stats_.measures_s += seconds_since(t0);
+     return res;
+}
+
+double Engine::entropy()
+{
+     need_device("Entropy()");
+     double e = 0.0;
+     cu(hiqk_entropy(slab_.data(), static_cast<int>(locals_.size()), d_vals_, workspace_, stream_));
+     cu(check_cuda(cudaMemcpyAsync(&e, d_vals_, sizeof(double), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+     synchronize();
+     cu(comm_.allreduce_sum(&e, 1, stream_));
+     return -e;
+}
+
+// ------------------------------------------------------------------------------------ slot maps
+std::vector<Index> Engine::qubits_permutation() const
+{
+     std::vector<Index> res = locals_;
+     res.insert(res.end(), globals_.begin(), globals_.end());
+     return res;
+}
+
+void Engine::set_qubits_permutation(const std::vector<Index>& p)
+{
+     // relabel only, no data motion (reference: SimulatorMPI.cpp:661-667)
+     if (p.size() < locals_.size() || p.size() < globals_.size()) fail("SetQubitsPermutation(): permutation too short");
+     locals_.assign(p.begin(), p.begin() + locals_.size());
+     globals_.assign(p.end() - globals_.size(), p.end());
+}
+
+std::map<Index, int> Engine::id2pos() const
+{
+     std::map<Index, int> m;
+     for (size_t pos = 0; pos < locals_.size(); ++pos) m[locals_[pos]] = static_cast<int>(pos);
+     for (size_t pos = 0; pos < globals_.size(); ++pos)
+          if (globals_[pos] != kNone) m[globals_[pos]] = static_cast<int>(pos + locals_.size());
+     return m;
+}
+
+void Engine::copy_slab_to_host(void* dst, uint64_t cap_amps)
+{
+     need_device("cheat_local()");
+     const uint64_t n = 1ull << locals_.size();
+     if (cap_amps < n) fail("cheat_local(): destination buffer too small");
+     cu(check_cuda(cudaMemcpyAsync(dst, slab_.data(), n * sizeof(double2), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+     synchronize();
+}
+
+void Engine::copy_slab_from_host(const void* src, uint64_t n_amps)
+{
+     need_device("set_local_slab()");
+     if (n_amps != (1ull << locals_.size())) fail("set_local_slab(): size must equal 2^(local qubits)");
+     cu(check_cuda(cudaMemcpyAsync(slab_.data(), src, n_amps * sizeof(double2), cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync"));
+     synchronize();
+}
+
+// ------------------------------------------------------------------------------------ swaps
+void Engine::swap_qubits_stage(const std::vector<Index>& pairs)
+{
+     const auto t0 = Clock::now();
+     swap_qubits(pairs);
+     if (!dry_run_) synchronize();
+     stats_.swaps_s += seconds_since(t0);
+     ++stats_.total_swaps;
+     ++stats_.total_stages;
+}
+
+void Engine::swap_qubits(const std::vector<Index>& pairs)
+{
+     // pairs = [global id, local id, ...]; afterwards the ids trade places (reference: SimulatorMPI.cpp:1085-1138)
+     if (pairs.size() % 2) fail("SwapQubits(): odd number of ids");
+     std::map<Index, size_t> pos;
+     for (size_t i = 0; i < pairs.size(); i += 2) {
+          pos[pairs[i]] = find_sure(globals_, pairs[i]);
+          pos[pairs[i + 1]] = find_sure(locals_, pairs[i + 1]);
+     }
+     if (pos.size() != pairs.size()) fail("SwapQubits(): each qubit should be unique");
+     std::vector<int> gpos, slots;
+     for (size_t i = 0; i < pairs.size(); i += 2) {
+          gpos.push_back(static_cast<int>(pos[pairs[i]]));
+          slots.push_back(static_cast<int>(pos[pairs[i + 1]]));
+     }
+     if (tracing_) {
+          Descriptor d;
+          d.kind = HIQ_DESC_SWAP;
+          d.k = static_cast<int>(gpos.size());
+          for (size_t i = 0; i < gpos.size(); ++i) {
+               d.aux.push_back(gpos[i]);
+               d.aux.push_back(slots[i]);
+          }
+          trace_.push_back(d);
+     }
+     if (!dry_run_ && !gpos.empty()) exchange(gpos, slots);
+     for (size_t i = 0; i < gpos.size(); ++i) std::swap(locals_[slots[i]], globals_[gpos[i]]);
+}
+
+void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slots)
+{
+     // Net effect: transpose global-index bit (L + gpos_i) with bit slot_i.
+     // Peer p differs from this rank in a non-empty subset of the swapped global bits; the
+     // amplitudes whose swapped slots spell p's bits go to p and are replaced, in place, by p's
+     // amplitudes whose swapped slots spell this rank's bits.
+     const int L = static_cast<int>(locals_.size());
+     const int q = static_cast<int>(gpos.size());
+     std::vector<int> order(q);  // pair indices by ascending slot
+     for (int i = 0; i < q; ++i) order[i] = i;
+     std::sort(order.begin(), order.end(), [&](int a, int b) { return slots[a] < slots[b]; });
+     const uint64_t chunk = 1ull << (L - q);
+     const int n_peers = (1 << q) - 1;
+     const uint64_t piece = std::min(chunk, kSwapPieceAmps);
+     const size_t need = 2ull * n_peers * piece * sizeof(double2);
+     if (!swap_buf_ || swap_buf_bytes_ < need) {
+          if (swap_buf_) cudaFree(swap_buf_);
+          swap_buf_ = nullptr;
+          cu(check_cuda(cudaMalloc(&swap_buf_, need), "cudaMalloc swap staging"));
+          swap_buf_bytes_ = need;
+     }
+     double2* send = static_cast<double2*>(swap_buf_);
+     double2* recv = send + static_cast<uint64_t>(n_peers) * piece;
+     struct Peer {
+          int rank;
+          uint64_t pat;  // pattern over the sorted swapped slots
+     };
+     std::vector<Peer> peers;
+     for (int x = 1; x < (1 << q); ++x) {
+          int pr = rank_;
+          for (int i = 0; i < q; ++i)
+               if ((x >> i) & 1) pr ^= 1 << gpos[i];
+          uint64_t pat = 0;
+          for (int j = 0; j < q; ++j)
+               if ((pr >> gpos[order[j]]) & 1) pat |= 1ull << j;
+          peers.push_back({pr, pat});
+     }
+     for (uint64_t begin = 0; begin < chunk; begin += piece) {
+          const uint64_t cnt = std::min(piece, chunk - begin);
+          for (int i = 0; i < n_peers; ++i)
+               cu(hiqk_swap_pack(slab_.data(), L, q, slots.data(), peers[i].pat, begin, cnt, send + i * piece, stream_));
+          nccl().GroupStart();
+          for (int i = 0; i < n_peers; ++i) {
+               nccl().Send(send + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_.handle(), stream_);
+               nccl().Recv(recv + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_.handle(), stream_);
+          }
+          ncclResult_t r = nccl().GroupEnd();
+          if (r != ncclSuccess) throw EngineError(HIQ_ERR_CUDA, std::string("ncclGroupEnd: ") + nccl().GetErrorString(r));
+          for (int i = 0; i < n_peers; ++i)
+               cu(hiqk_swap_unpack(slab_.data(), L, q, slots.data(), peers[i].pat, begin, cnt, recv + i * piece, stream_));
+     }
+     stats_.swap_bytes_sent += static_cast<double>(n_peers) * chunk * sizeof(double2);
+}
+
+}  // namespace hiq

@@ -1,0 +1,135 @@
+// Host engine: one instance per rank/GPU.  Owns the amplitude slab (HBM), the qubit->slot maps,
+// the gate-fusion accumulator and the RNG, and turns the reference's operator API into fused-gate
+// descriptors, swap plans and reduction requests executed by the sm_100a kernels.
+//
+// Behavioural spec: the reference class SimulatorMPI
+// (reference: src/simulator-mpi/SimulatorMPI.hpp:43-308, SimulatorMPI.cpp).  Every rank-dependent
+// rule (global-control filter, diagonal slicing, allocation policy, measurement ordering, swap
+// colours) is evaluated exactly as the reference does for an MPI rank.
+#pragma once
+#include <chrono>
+#include <cstdint>
+#include <functional>
+#include <map>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "comm.hpp"
+#include "fusion.hpp"
+#include "slab.hpp"
+
+namespace hiq {
+
+struct EngineError : std::runtime_error {
+     int code;
+     EngineError(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+// What the host hands to the device layer; also the unit of the dry-run trace.
+struct Descriptor {
+     int kind = 0;  // HIQ_DESC_*
+     int k = 0;
+     int slots[5] = {0, 0, 0, 0, 0};
+     uint64_t ctrl_mask = 0;
+     std::vector<cplx> payload;   // dense: 4^k, diag: 2^k, scale: 1
+     std::vector<int64_t> aux;    // swap: gpos0, slot0, gpos1, slot1, ...
+};
+
+struct EngineStats {
+     uint64_t total_gates = 0, total_runs = 0, total_stages = 0, total_swaps = 0;
+     uint64_t dense_passes = 0, diag_passes = 0, scale_passes = 0, skipped_passes = 0;
+     double runs_s = 0, swaps_s = 0, measures_s = 0, allocs_s = 0, deallocs_s = 0;
+     double swap_bytes_sent = 0;
+};
+
+class Engine {
+public:
+     Engine(uint64_t seed, int max_local, int max_cluster, int rank, int world_size, const void* nccl_id, int device,
+            int flags);
+     ~Engine();
+     Engine(const Engine&) = delete;
+     Engine& operator=(const Engine&) = delete;
+
+     void allocate_qubit(Index id);
+     void allocate_qureg(const std::vector<Index>& ids, cplx init);
+     void deallocate_qubit(Index id);
+     void apply_gate(GateMatrix m, std::vector<Index> ids, std::vector<Index> ctrls);
+     void run();
+     void swap_qubits_stage(const std::vector<Index>& pairs);  // SwapQubitsWrapper
+     std::vector<bool> measure_qubits(const std::vector<Index>& ids);
+     double get_probability(const std::vector<bool>& bits, const std::vector<Index>& ids);
+     cplx get_amplitude(const std::vector<bool>& bits, const std::vector<Index>& ids);
+     void collapse_wavefunction(const std::vector<Index>& ids, const std::vector<bool>& values);
+     double entropy();
+     std::vector<Index> qubits_permutation() const;
+     const std::vector<Index>& locals() const { return locals_; }
+     const std::vector<Index>& globals() const { return globals_; }
+     void set_qubits_permutation(const std::vector<Index>& p);
+     std::map<Index, int> id2pos() const;
+     // copy the local slab to host memory (complex128, 2^L amplitudes)
+     void copy_slab_to_host(void* dst, uint64_t cap_amps);
+     void copy_slab_from_host(const void* src, uint64_t n_amps);
+     double2* slab_ptr() const { return slab_.data(); }
+     int local_qubits() const { return static_cast<int>(locals_.size()); }
+     void synchronize();
+
+     int rank() const { return rank_; }
+     int world_size() const { return world_; }
+     bool dry_run() const { return dry_run_; }
+     cudaStream_t stream() const { return stream_; }
+     const EngineStats& stats() const { return stats_; }
+     const std::vector<Descriptor>& trace() const { return trace_; }
+     void clear_trace() { trace_.clear(); }
+     void set_dense_variant(int v) { dense_variant_ = v; }
+
+private:
+     static constexpr Index kNone = -1;  // empty global slot (reference: kNotFound_ stored in an int64)
+     using Clock = std::chrono::steady_clock;
+
+     [[noreturn]] void fail(const std::string& msg) const;
+     void cu(int rc) const;
+     size_t find(const std::vector<Index>& v, Index val) const;       // npos when absent
+     size_t find_sure(const std::vector<Index>& v, Index val) const;  // throws when absent
+     uint64_t ids_to_bits(const std::vector<Index>& ids, const std::vector<Index>& perm) const;
+     void need_device(const char* what) const;
+
+     void allocate_local(Index id);
+     void allocate_global(Index id);
+     void deallocate_local(Index id);
+     void deallocate_global(Index id);
+     void swap_qubits(const std::vector<Index>& pairs);
+     void exchange(const std::vector<int>& gpos, const std::vector<int>& slots);
+     void masks(const std::vector<Index>& ids, const std::vector<bool>& bits, const char* what, uint64_t& lm, uint64_t& lv,
+                uint64_t& gm, uint64_t& gv) const;
+     double probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
+     void normalize(double norm, uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
+     void execute(const Descriptor& d);
+     void ensure_scratch();
+
+     const double max_float_error_ = 1e-12;
+     size_t min_local_, max_local_, max_global_, max_cluster_;
+     int rank_, world_, device_;
+     bool dry_run_, tracing_;
+     std::vector<Index> locals_, globals_;
+     FusionAccumulator fused_;
+     std::mt19937 rnd_eng_;
+     std::function<double()> rng_;
+
+     Slab slab_;
+     Comm comm_;
+     cudaStream_t stream_ = nullptr;
+     cudaStream_t comm_stream_ = nullptr;
+     void* workspace_ = nullptr;  // reduction partials
+     double* d_vals_ = nullptr;   // small device results
+     double* d_blocks_ = nullptr; // world * 2^15 block sums
+     void* swap_buf_ = nullptr;   // staging for the exchange (send | recv)
+     size_t swap_buf_bytes_ = 0;
+     int dense_variant_ = 0;
+
+     EngineStats stats_;
+     std::vector<Descriptor> trace_;
+};
+
+}  // namespace hiq

@@ -1,0 +1,261 @@
+// pybind11 module `_cppsim_mpi`: the operator API that the ProjectQ/HiQ `SimulatorMPI` backend
+// drives, re-hosted on the B200 engine through the C ABI in include/hiq_b200.h.
+//
+// Same class name, method names, argument order and error type as the reference binding
+// (reference: _cppsim_mpi.cpp:61-83).  Differences, all additive:
+//   * the MPI world is replaced by one process per GPU; `init_world(rank, world_size, nccl_id,
+//     device)` plays the role of MPI_Init (world size 1 needs no call);
+//   * `cheat_local()` returns the local slab as a numpy complex128 array instead of a Python list;
+//   * extra helpers: `synchronize`, `stats`, `local_slab_ptr`, descriptor trace accessors.
+#include <pybind11/complex.h>
+#include <pybind11/numpy.h>
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include <complex>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/hiq_b200.h"
+
+namespace py = pybind11;
+using cplx = std::complex<double>;
+
+namespace {
+
+struct World {
+     int rank = 0, size = 1, device = 0, flags = 0;
+     std::string nccl_id;  // 128 bytes when size > 1
+} g_world;
+
+void check(int rc)
+{
+     if (rc != HIQ_OK) throw std::runtime_error(hiq_last_error());
+}
+
+class SimulatorB200 {
+public:
+     SimulatorB200(uint64_t seed, int max_local, int max_cluster)
+     {
+          check(hiq_create(seed, max_local, max_cluster, g_world.rank, g_world.size,
+                           g_world.size > 1 ? g_world.nccl_id.data() : nullptr, g_world.device, g_world.flags, &e_));
+     }
+     ~SimulatorB200() { hiq_destroy(e_); }
+     SimulatorB200(const SimulatorB200&) = delete;
+
+     std::vector<int64_t> ids(int kind) const
+     {
+          int n = 0;
+          check(hiq_get_qubits_ids(e_, kind, nullptr, 0, &n));
+          std::vector<int64_t> v(n);
+          check(hiq_get_qubits_ids(e_, kind, v.data(), n, &n));
+          return v;
+     }
+     std::vector<int64_t> get_qubits_ids() const { return ids(0); }
+     std::vector<int64_t> get_local_qubits_ids() const { return ids(1); }
+     std::vector<int64_t> get_global_qubits_ids() const { return ids(2); }
+     void set_qubits_perm(const std::vector<int64_t>& p) { check(hiq_set_qubits_perm(e_, p.data(), static_cast<int>(p.size()))); }
+     void swap_qubits(const std::vector<int64_t>& pairs)
+     {
+          py::gil_scoped_release nogil;
+          check(hiq_swap_qubits(e_, pairs.data(), static_cast<int>(pairs.size())));
+     }
+     void allocate_qureg(const std::vector<int64_t>& q, cplx init)
+     {
+          check(hiq_allocate_qureg(e_, q.data(), static_cast<int>(q.size()), init.real(), init.imag()));
+     }
+     void allocate_qubit(int64_t id) { check(hiq_allocate_qubit(e_, id)); }
+     void deallocate_qubit(int64_t id) { check(hiq_deallocate_qubit(e_, id)); }
+     std::vector<bool> measure_qubits(const std::vector<int64_t>& q)
+     {
+          std::vector<uint8_t> out(q.size());
+          check(hiq_measure_qubits(e_, q.data(), static_cast<int>(q.size()), out.data()));
+          return std::vector<bool>(out.begin(), out.end());
+     }
+     void apply_controlled_gate(const std::vector<std::vector<cplx>>& m, const std::vector<int64_t>& q,
+                                const std::vector<int64_t>& ctrls)
+     {
+          const int dim = static_cast<int>(m.size());
+          std::vector<cplx> flat;
+          flat.reserve(static_cast<size_t>(dim) * dim);
+          for (auto& row: m) {
+               if (static_cast<int>(row.size()) != dim) throw std::runtime_error("apply_controlled_gate: matrix must be square");
+               flat.insert(flat.end(), row.begin(), row.end());
+          }
+          check(hiq_apply_controlled_gate(e_, reinterpret_cast<const double*>(flat.data()), dim, q.data(),
+                                          static_cast<int>(q.size()), ctrls.data(), static_cast<int>(ctrls.size())));
+     }
+     // fast path: numpy matrix, no list-of-lists conversion
+     void apply_controlled_matrix(py::array_t<cplx, py::array::c_style | py::array::forcecast> m, const std::vector<int64_t>& q,
+                                  const std::vector<int64_t>& ctrls)
+     {
+          if (m.ndim() != 2 || m.shape(0) != m.shape(1)) throw std::runtime_error("apply_controlled_matrix: matrix must be square");
+          check(hiq_apply_controlled_gate(e_, reinterpret_cast<const double*>(m.data()), static_cast<int>(m.shape(0)), q.data(),
+                                          static_cast<int>(q.size()), ctrls.data(), static_cast<int>(ctrls.size())));
+     }
+     void emulate_math(py::function, const std::vector<std::vector<unsigned>>&, const std::vector<int64_t>&)
+     {
+          throw std::runtime_error("SimulatorMPI::emulate_math() is not supported");
+     }
+     cplx get_amplitude(const std::vector<bool>& bits, const std::vector<int64_t>& q)
+     {
+          if (bits.size() != q.size()) throw std::runtime_error("GetAmplitude(): ids.size() != number of qubits");
+          std::vector<uint8_t> b(bits.begin(), bits.end());
+          double out[2];
+          check(hiq_get_amplitude(e_, b.data(), q.data(), static_cast<int>(q.size()), out));
+          return cplx(out[0], out[1]);
+     }
+     double get_probability(const std::vector<bool>& bits, const std::vector<int64_t>& q)
+     {
+          if (bits.size() != q.size()) throw std::runtime_error("GetProbability(): ids.size() != bit_string.size()");
+          std::vector<uint8_t> b(bits.begin(), bits.end());
+          double out = 0.0;
+          check(hiq_get_probability(e_, b.data(), q.data(), static_cast<int>(q.size()), &out));
+          return out;
+     }
+     void run() { check(hiq_run(e_)); }
+     double entropy()
+     {
+          double out = 0.0;
+          check(hiq_entropy(e_, &out));
+          return out;
+     }
+     py::tuple cheat_local()
+     {
+          int n_map = 0;
+          uint64_t n_amps = 0;
+          check(hiq_cheat_local(e_, nullptr, nullptr, 0, &n_map, nullptr, 0, &n_amps));
+          std::vector<int64_t> idv(n_map);
+          std::vector<int> posv(n_map);
+          py::array_t<cplx> vec(static_cast<py::ssize_t>(n_amps));
+          check(hiq_cheat_local(e_, idv.data(), posv.data(), n_map, &n_map, vec.mutable_data(), n_amps, &n_amps));
+          py::dict d;
+          for (int i = 0; i < n_map; ++i) d[py::int_(idv[i])] = posv[i];
+          return py::make_tuple(d, vec);
+     }
+     void collapse_wavefunction(const std::vector<int64_t>& q, const std::vector<bool>& values)
+     {
+          if (values.size() != q.size()) throw std::runtime_error("collapseWaveFunction(): ids.size() != values.size()");
+          std::vector<uint8_t> b(values.begin(), values.end());
+          check(hiq_collapse_wavefunction(e_, q.data(), b.data(), static_cast<int>(q.size())));
+     }
+
+     // ---- additions
+     void synchronize() { check(hiq_synchronize(e_)); }
+     void set_dense_variant(int v) { check(hiq_set_dense_variant(e_, v)); }
+     void set_local_slab(py::array_t<cplx, py::array::c_style | py::array::forcecast> a)
+     {
+          check(hiq_set_local_slab(e_, a.data(), static_cast<uint64_t>(a.size())));
+     }
+     py::tuple local_slab_ptr()
+     {
+          void* p = nullptr;
+          int L = 0;
+          check(hiq_local_slab(e_, &p, &L));
+          return py::make_tuple(reinterpret_cast<uintptr_t>(p), L);
+     }
+     py::dict stats()
+     {
+          hiq_stats s;
+          check(hiq_get_stats(e_, &s));
+          py::dict d;
+          d["total_gates"] = s.total_gates;
+          d["total_runs"] = s.total_runs;
+          d["total_stages"] = s.total_stages;
+          d["total_swaps"] = s.total_swaps;
+          d["dense_passes"] = s.dense_passes;
+          d["diag_passes"] = s.diag_passes;
+          d["scale_passes"] = s.scale_passes;
+          d["skipped_passes"] = s.skipped_passes;
+          d["runs_s"] = s.runs_s;
+          d["swaps_s"] = s.swaps_s;
+          d["measures_s"] = s.measures_s;
+          d["allocs_s"] = s.allocs_s;
+          d["deallocs_s"] = s.deallocs_s;
+          d["swap_bytes_sent"] = s.swap_bytes_sent;
+          return d;
+     }
+     py::list trace()
+     {
+          int n = 0;
+          check(hiq_trace_count(e_, &n));
+          py::list out;
+          for (int i = 0; i < n; ++i) {
+               hiq_descriptor d;
+               check(hiq_trace_get(e_, i, &d, nullptr, 0, nullptr, 0));
+               py::array_t<cplx> payload(d.n_payload);
+               std::vector<int64_t> aux(d.n_aux);
+               check(hiq_trace_get(e_, i, &d, reinterpret_cast<double*>(payload.mutable_data()), d.n_payload, aux.data(), d.n_aux));
+               py::dict r;
+               r["kind"] = d.kind;
+               r["k"] = d.k;
+               r["slots"] = std::vector<int>(d.slots, d.slots + (d.kind == HIQ_DESC_DENSE || d.kind == HIQ_DESC_DIAG ? d.k : 0));
+               r["ctrl_mask"] = d.ctrl_mask;
+               r["payload"] = payload;
+               r["aux"] = aux;
+               out.append(r);
+          }
+          return out;
+     }
+     void clear_trace() { check(hiq_trace_clear(e_)); }
+
+private:
+     hiq_engine* e_ = nullptr;
+};
+
+}  // namespace
+
+PYBIND11_MODULE(_cppsim_mpi, m)
+{
+     m.doc() = "B200-native drop-in for HiQsimulator's _cppsim_mpi (state-vector engine on sm_100a)";
+     m.def("unique_id", [] {
+          std::string id(128, '\0');
+          check(hiq_comm_unique_id(id.data()));
+          return py::bytes(id);
+     }, "NCCL unique id (call on rank 0, hand to every rank's init_world)");
+     m.def("init_world", [](int rank, int world_size, py::bytes nccl_id, int device, int flags) {
+          g_world.rank = rank;
+          g_world.size = world_size;
+          g_world.nccl_id = std::string(nccl_id);
+          g_world.device = device;
+          g_world.flags = flags;
+          if (world_size > 1 && !(flags & HIQ_FLAG_DRY_RUN) && g_world.nccl_id.size() != 128)
+               throw std::runtime_error("init_world: nccl_id must be the 128 bytes returned by unique_id() on rank 0");
+     }, py::arg("rank") = 0, py::arg("world_size") = 1, py::arg("nccl_id") = py::bytes(), py::arg("device") = 0, py::arg("flags") = 0);
+     m.def("world", [] { return py::make_tuple(g_world.rank, g_world.size, g_world.device, g_world.flags); });
+     m.def("device_count", &hiq_device_count);
+     m.def("version", [] { return std::string(hiq_version()); });
+     m.def("launch_count", &hiqk_launch_count);
+     m.attr("FLAG_DRY_RUN") = HIQ_FLAG_DRY_RUN;
+     m.attr("FLAG_TRACE") = HIQ_FLAG_TRACE;
+
+     py::class_<SimulatorB200>(m, "SimulatorMPI")
+         .def(py::init<uint64_t, int, int>())
+         .def("get_qubits_ids", &SimulatorB200::get_qubits_ids)
+         .def("get_local_qubits_ids", &SimulatorB200::get_local_qubits_ids)
+         .def("get_global_qubits_ids", &SimulatorB200::get_global_qubits_ids)
+         .def("set_qubits_perm", &SimulatorB200::set_qubits_perm)
+         .def("swap_qubits", &SimulatorB200::swap_qubits)
+         .def("allocate_qureg", &SimulatorB200::allocate_qureg, py::arg("ids"), py::arg("init") = cplx(0.0))
+         .def("allocate_qubit", &SimulatorB200::allocate_qubit)
+         .def("deallocate_qubit", &SimulatorB200::deallocate_qubit)
+         .def("measure_qubits", &SimulatorB200::measure_qubits)
+         .def("apply_controlled_gate", &SimulatorB200::apply_controlled_gate)
+         .def("apply_controlled_matrix", &SimulatorB200::apply_controlled_matrix)
+         .def("emulate_math", &SimulatorB200::emulate_math)
+         .def("get_amplitude", &SimulatorB200::get_amplitude)
+         .def("get_probability", &SimulatorB200::get_probability)
+         .def("run", &SimulatorB200::run)
+         .def("entropy", &SimulatorB200::entropy)
+         .def("cheat_local", &SimulatorB200::cheat_local)
+         .def("collapse_wavefunction", &SimulatorB200::collapse_wavefunction)
+         .def("synchronize", &SimulatorB200::synchronize)
+         .def("set_dense_variant", &SimulatorB200::set_dense_variant)
+         .def("set_local_slab", &SimulatorB200::set_local_slab)
+         .def("local_slab_ptr", &SimulatorB200::local_slab_ptr)
+         .def("stats", &SimulatorB200::stats)
+         .def("trace", &SimulatorB200::trace)
+         .def("clear_trace", &SimulatorB200::clear_trace);
+}

@@ -125,6 +125,87 @@ int hiqk_microbench(int what, int iters, double* out_value);
 /* Number of kernels launched by this library in the calling process (bench evidence). */
 uint64_t hiqk_launch_count(void);
 
+/* ------------------------------------------------------------------------- *
+ * Engine-level entry points (hiq_*): one handle per rank / GPU.
+ * They are the methods of the reference's pybind class, in the same order and with the
+ * same argument meaning (reference: _cppsim_mpi.cpp:63-82).  Qubit ids are int64; bit
+ * strings are one byte per bit (0/1); matrices are row-major interleaved complex128.
+ * ------------------------------------------------------------------------- */
+typedef struct hiq_engine hiq_engine;
+
+#define HIQ_FLAG_DRY_RUN 1 /* no device: host logic only, every device op is recorded as a descriptor */
+#define HIQ_FLAG_TRACE 2   /* also record descriptors while executing on the GPU */
+
+/* descriptor kinds (what the host hands to the device layer) */
+#define HIQ_DESC_NONE 0
+#define HIQ_DESC_DENSE 1
+#define HIQ_DESC_DIAG 2
+#define HIQ_DESC_SCALE 3
+#define HIQ_DESC_SWAP 4
+#define HIQ_DESC_GROW 5
+#define HIQ_DESC_FILL 6
+
+typedef struct hiq_descriptor {
+     int kind;           /* HIQ_DESC_* */
+     int k;              /* targets (dense/diag), swapped pairs (swap), new local count (grow) */
+     int slots[5];       /* matrix bit l <-> local slot slots[l] */
+     uint64_t ctrl_mask; /* over local slots */
+     int n_payload;      /* complex128 values in the payload: 4^k dense, 2^k diag, 1 scale/fill */
+     int n_aux;          /* swap: 2k ints gpos0, slot0, gpos1, slot1 ... */
+} hiq_descriptor;
+
+/* rank 0 obtains the 128-byte NCCL unique id; the launcher hands it to every rank's hiq_create */
+int hiq_comm_unique_id(void* out128);
+
+/* SimulatorMPI(seed, max_local, max_cluster_size) (reference: SimulatorMPI.cpp:66-104).
+ * rank/world_size replace the MPI communicator (one process per GPU); nccl_id may be NULL when
+ * world_size == 1; device is the CUDA ordinal. */
+int hiq_create(uint64_t seed, int max_local, int max_cluster_size, int rank, int world_size, const void* nccl_id,
+               int device, int flags, hiq_engine** out);
+int hiq_destroy(hiq_engine* e);
+
+int hiq_allocate_qubit(hiq_engine* e, int64_t id);                                   /* AllocateQubit  :184-216 */
+int hiq_allocate_qureg(hiq_engine* e, const int64_t* ids, int n, double init_re, double init_im); /* AllocateQureg :218-251 */
+int hiq_deallocate_qubit(hiq_engine* e, int64_t id);                                 /* DeallocateQubit :369-426 */
+int hiq_apply_controlled_gate(hiq_engine* e, const double* matrix, int dim, const int64_t* ids, int n_ids,
+                              const int64_t* ctrls, int n_ctrls);                    /* ApplyGate :710-815 */
+int hiq_run(hiq_engine* e);                                                          /* Run :441-541 */
+int hiq_swap_qubits(hiq_engine* e, const int64_t* pairs, int n);                     /* SwapQubitsWrapper :1060-1138 */
+int hiq_measure_qubits(hiq_engine* e, const int64_t* ids, int n, uint8_t* out_bits); /* MeasureQubits :897-1008 */
+int hiq_get_probability(hiq_engine* e, const uint8_t* bits, const int64_t* ids, int n, double* out); /* :561-600 */
+int hiq_get_amplitude(hiq_engine* e, const uint8_t* bits, const int64_t* ids, int n, double* out_re_im); /* :602-650 */
+int hiq_collapse_wavefunction(hiq_engine* e, const int64_t* ids, const uint8_t* values, int n); /* :1010-1058 */
+int hiq_entropy(hiq_engine* e, double* out);                                         /* Entropy :681-694 */
+/* kind 0: locals ++ globals (get_qubits_ids), 1: locals, 2: globals; empty global slots are -1 */
+int hiq_get_qubits_ids(hiq_engine* e, int kind, int64_t* out, int cap, int* n);      /* :652-679 */
+int hiq_set_qubits_perm(hiq_engine* e, const int64_t* p, int n);                     /* :661-667 */
+/* cheat_local (:543-559): id -> bit position map, and a host copy of the local slab
+ * (host_dst may be NULL to query sizes only; *n_amps = 2^L) */
+int hiq_cheat_local(hiq_engine* e, int64_t* ids, int* pos, int cap, int* n_map, void* host_dst, uint64_t cap_amps,
+                    uint64_t* n_amps);
+/* device pointer of the local slab and L (zero-copy views; valid until the next (de)allocation) */
+int hiq_local_slab(hiq_engine* e, void** dev_ptr, int* L);
+int hiq_set_local_slab(hiq_engine* e, const void* host_src, uint64_t n_amps);
+/* wait until every operation issued so far has completed on the device */
+int hiq_synchronize(hiq_engine* e);
+int hiq_rank(hiq_engine* e, int* rank, int* world_size);
+/* force a dense kernel variant (HIQK_DENSE_*) for every fused pass; 0 = automatic */
+int hiq_set_dense_variant(hiq_engine* e, int variant);
+
+/* counters and timers in the spirit of the reference's stage statistics (:106-134, :1148-1157) */
+typedef struct hiq_stats {
+     uint64_t total_gates, total_runs, total_stages, total_swaps;
+     uint64_t dense_passes, diag_passes, scale_passes, skipped_passes;
+     double runs_s, swaps_s, measures_s, allocs_s, deallocs_s;
+     double swap_bytes_sent;
+} hiq_stats;
+int hiq_get_stats(hiq_engine* e, hiq_stats* out);
+
+/* descriptor trace (HIQ_FLAG_DRY_RUN / HIQ_FLAG_TRACE) */
+int hiq_trace_count(hiq_engine* e, int* n);
+int hiq_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux);
+int hiq_trace_clear(hiq_engine* e);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,219 @@
+"""Parity of the CUDA engine (through the reference-facing `_cppsim_mpi.SimulatorMPI` surface,
+i.e. through the C ABI) with the reference: golden fixtures from oracle/_ref, live numpy oracle,
+and the reference's own known-answer tests.  Amplitudes 1e-12 absolute; slot maps and measurement
+outcomes bit-exact."""
+import math
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+import scripts
+from golden_util import golden_names, load_golden
+from hiqsimulator_b200 import gates as G
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _M():
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    M.init_world(0, 1, b"", 0, 0)
+    return M
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if n.startswith("r1_")])
+def test_engine_matches_golden_single_gpu(name):
+    M = _M()
+    R, script, exp = load_golden(name)
+    got = scripts.run_on_sim(M.SimulatorMPI, script)
+    scripts.assert_outputs_match(script, got, exp)
+
+
+@pytest.mark.parametrize("nq,seed,mc", [(6, 11, 4), (13, 12, 4), (16, 13, 5), (18, 14, 3), (20, 15, 4)])
+def test_engine_matches_oracle_random(nq, seed, mc):
+    M = _M()
+    script = scripts.random_script(nq, 1, seed, ngates=70, max_cluster=mc, queries=True, dealloc=(seed % 2 == 1))
+    exp = scripts.run_on_oracle(script, 1)
+    got = scripts.run_on_sim(M.SimulatorMPI, script)
+    scripts.assert_outputs_match(script, got, exp)
+
+
+@pytest.mark.parametrize("variant", [1, 2, 3])
+def test_engine_forced_kernel_variants(variant):
+    M = _M()
+    script = scripts.random_script(14, 1, 77, ngates=60, queries=False)
+    exp = scripts.run_on_oracle(script, 1)
+
+    def make(*a):
+        s = M.SimulatorMPI(*a)
+        s.set_dense_variant(variant)
+        return s
+    got = scripts.run_on_sim(make, script)
+    scripts.assert_outputs_match(script, got, exp)
+
+
+def _gpu_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("r1_")])
+def test_engine_matches_golden_multi_gpu(name):
+    R = int(name[1])
+    if _gpu_count() < R:
+        pytest.skip("needs %d GPUs" % R)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+# ---------------------------------------------------------------------------------------------
+# Known answers of the reference's own test-suite, restated without ProjectQ
+# (reference: hiq/projectq/backends/_sim/_simulator_mpi_test.py)
+# ---------------------------------------------------------------------------------------------
+def _apply(sim, m, ids, ctrls=()):
+    sim.apply_controlled_gate(np.asarray(m).tolist(), list(ids), list(ctrls))
+
+
+def test_ref_cheat_sizes():  # :161-187
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    d, v = sim.cheat_local()
+    assert len(d) == 0 and len(v) == 1
+    sim.allocate_qubit(0)
+    d, v = sim.cheat_local()
+    assert d == {0: 0} and len(v) == 2 and abs(v[0]) == pytest.approx(1.0)
+    sim.deallocate_qubit(0)
+    d, v = sim.cheat_local()
+    assert len(d) == 0 and len(v) == 1
+
+
+def test_ref_ghz_measurement():  # :190-201
+    M = _M()
+    for seed in range(6):
+        sim = M.SimulatorMPI(seed, 20, 4)
+        sim.allocate_qureg(list(range(5)), 0)
+        _apply(sim, G.H, [0])
+        for q in range(1, 5):
+            _apply(sim, G.X, [q], [0])
+        sim.run()
+        bits = sim.measure_qubits(list(range(5)))
+        assert sum(bits) in (0, 5)
+
+
+def test_ref_kqubit_gate():  # :247-283
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    m1, m2, m3 = G.Rx(0.3), G.Rx(0.8), G.Ry(0.1)
+    m4 = G.Rz(0.9) @ G.Ry(-0.1)
+    m = np.kron(m4, np.kron(m3, np.kron(m2, m1)))
+    sim.allocate_qureg([0, 1, 2, 3], 0)
+    sim.allocate_qubit(4)
+    _apply(sim, G.Rx(-0.3), [0]); _apply(sim, G.Rx(-0.8), [1]); _apply(sim, G.Ry(-0.1), [2])
+    _apply(sim, G.Rz(-0.9), [3]); _apply(sim, G.Ry(0.1), [3])
+    sim.run()
+    _apply(sim, G.X, [4]); sim.run()
+    _apply(sim, m, [0, 1, 2, 3], [4]); sim.run()
+    _apply(sim, G.X, [4]); sim.run()
+    _apply(sim, m.conj().T, [0, 1, 2, 3], [4]); sim.run()
+    assert sim.get_amplitude([False] * 5, [4, 0, 1, 2, 3]) == pytest.approx(1.0)
+    with pytest.raises(RuntimeError):
+        sim.apply_controlled_gate(np.eye(64).tolist(), [0, 1, 2, 3, 4, 5], [])
+
+
+def test_ref_probability():  # :308-339
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    q = list(range(6))
+    sim.allocate_qureg(q, 0)
+    for i in q:
+        _apply(sim, G.H, [i]); sim.run()
+    bits = [False, False, True, False, True, False]
+    for i in range(6):
+        assert sim.get_probability(bits[:i], q[:i]) == pytest.approx(0.5 ** i)
+    with pytest.raises(RuntimeError):
+        sim.get_probability([False], [6])  # unknown qubit
+    for i in q:
+        _apply(sim, G.H, [i]); sim.run()
+    _apply(sim, G.Ry(2 * math.acos(math.sqrt(0.3))), [0]); sim.run()
+    assert sim.get_probability([False], [0]) == pytest.approx(0.3)
+    _apply(sim, G.Ry(2 * math.acos(math.sqrt(0.4))), [2]); sim.run()
+    assert sim.get_probability([False], [2]) == pytest.approx(0.4)
+    assert sim.get_probability([False, False], [0, 2]) == pytest.approx(0.12)
+    assert sim.get_probability([False, True], [0, 2]) == pytest.approx(0.18)
+    assert sim.get_probability([True, False], [0, 2]) == pytest.approx(0.28)
+
+
+def test_ref_amplitude():  # :342-379
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    q = list(range(6))
+    sim.allocate_qureg(q, 0)
+    for i in q:
+        _apply(sim, G.X, [i]); sim.run()
+        _apply(sim, G.H, [i]); sim.run()
+    assert sim.get_amplitude([0, 0, 1, 0, 1, 0], q) == pytest.approx(1. / 8.)
+    assert sim.get_amplitude([0, 0, 0, 0, 1, 0], q) == pytest.approx(-1. / 8.)
+    assert sim.get_amplitude([0, 1, 1, 0, 1, 0], q) == pytest.approx(-1. / 8.)
+    for i in q:
+        _apply(sim, G.H, [i]); sim.run()
+        _apply(sim, G.X, [i]); sim.run()
+    _apply(sim, G.Ry(2 * math.acos(0.3)), [0]); sim.run()
+    assert sim.get_amplitude([0] * 6, q) == pytest.approx(0.3)
+    assert sim.get_amplitude([1, 0, 0, 0, 0, 0], q) == pytest.approx(math.sqrt(0.91))
+    with pytest.raises(RuntimeError):
+        sim.get_amplitude([0] * 5, q[:-1])
+    with pytest.raises(RuntimeError):
+        sim.get_amplitude([0] * 6, q[:-1] + [q[0]])
+    sim.allocate_qubit(6)
+    with pytest.raises(RuntimeError):
+        sim.get_amplitude([0] * 6, q)
+
+
+def test_ref_collapse():  # :569-603
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    q = list(range(4))
+    sim.allocate_qureg(q, 0)
+    for i in q:
+        _apply(sim, G.H, [i]); sim.run()
+    assert sim.get_probability([0, 0, 0, 0], q) == pytest.approx(.0625)
+    sim.collapse_wavefunction([0], [False])
+    assert sim.get_probability([0, 0, 0, 0], q) == pytest.approx(.125)
+    sim.collapse_wavefunction([1, 2], [False, False])
+    assert sim.get_probability([0, 0, 0, 0], q) == pytest.approx(.5)
+    with pytest.raises(RuntimeError):
+        sim.collapse_wavefunction([0], [True])  # impossible outcome
+    sim.collapse_wavefunction([3], [True])
+    assert sim.get_probability([0, 0, 0, 1], q) == pytest.approx(1.0)
+
+
+def test_ref_dealloc_superposed_raises():  # :606-614
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    sim.allocate_qubit(0)
+    _apply(sim, G.H, [0]); sim.run()
+    with pytest.raises(RuntimeError, match="entangled"):
+        sim.deallocate_qubit(0)
+
+
+def test_ref_multi_controlled_x():  # :652-706 (huge gate / ctrl-mask path)
+    M = _M()
+    for nctrl in (4, 3, 2):
+        sim = M.SimulatorMPI(1, 20, 4)
+        n = nctrl + 1
+        sim.allocate_qureg(list(range(n)), 0)
+        for c in range(nctrl):
+            _apply(sim, G.X, [c]); sim.run()
+        _apply(sim, G.X, [nctrl], list(range(nctrl))); sim.run()
+        d, v = sim.cheat_local()
+        assert abs(v[(1 << n) - 1]) == pytest.approx(1.0)

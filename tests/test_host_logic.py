@@ -1,0 +1,113 @@
+"""Host logic of the engine WITHOUT a GPU: slot maps, per-rank gate slicing, fusion, swap plans.
+
+The engine runs in dry-run mode (HIQ_FLAG_DRY_RUN: every device operation is recorded as a
+descriptor instead of being launched), one engine per rank; the descriptor streams are replayed
+with the oracle kernels and compared with the reference's final state from the golden fixtures.
+Slot maps must be bit-exact."""
+import numpy as np
+import pytest
+
+import scripts
+from golden_util import golden_names, load_golden
+
+
+def _dry_engines(script, R):
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    engines = []
+    for r in range(R):
+        M.init_world(r, R, b"", 0, M.FLAG_DRY_RUN)
+        engines.append(M.SimulatorMPI(*script[0][1:]))
+    M.init_world(0, 1, b"", 0, 0)
+    return engines
+
+
+def _gate_prefix(script):
+    """ops up to (and including) the first cheat_local: gates, runs, swaps, slot-map queries"""
+    out = []
+    for op in script:
+        out.append(op)
+        if op[0] == "cheat_local":
+            break
+    return out
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_dry_run_traces_reproduce_reference_state(name):
+    R, script, exp = load_golden(name)
+    prefix = _gate_prefix(script)
+    engines = _dry_engines(script, R)
+    for j, op in enumerate(prefix[1:], start=1):
+        if op[0] == "cheat_local":
+            break
+        for e in engines:
+            got = getattr(e, op[0])(*op[1:])
+            if op[0] == "get_qubits_ids":
+                assert list(got) == list(exp[j])  # slot maps are bit-exact
+    state = scripts.replay_traces([e.trace() for e in engines], R)
+    j = len(prefix) - 1
+    id2pos, vec = exp[j]
+    assert np.abs(state - vec).max() <= 1e-12
+    # id -> position map of cheat_local
+    for e in engines:
+        d, _ = ({}, None)
+        ids = e.get_qubits_ids()
+        nl = len(e.get_local_qubits_ids())
+        got = {q: p for p, q in enumerate(ids) if q != -1}
+        assert got == id2pos and nl == len(e.get_local_qubits_ids())
+
+
+def test_allocation_policy_matches_reference_example():
+    """R=8, max_cluster=4, allocate_qureg(range(35))."""
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    M.init_world(3, 8, b"", 0, M.FLAG_DRY_RUN)
+    e = M.SimulatorMPI(1, 32, 4)
+    M.init_world(0, 1, b"", 0, 0)
+    assert e.get_global_qubits_ids() == [-1, -1, -1]
+    e.allocate_qureg(list(range(35)), 0)
+    assert e.get_local_qubits_ids() == [0, 1, 2, 3] + list(range(7, 35))
+    assert e.get_global_qubits_ids() == [4, 5, 6]
+    with pytest.raises(RuntimeError):
+        e.allocate_qubit(99)
+
+
+def test_error_conventions_dry_run():
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    M.init_world(0, 2, b"", 0, M.FLAG_DRY_RUN)
+    e = M.SimulatorMPI(1, 8, 4)
+    M.init_world(0, 1, b"", 0, 0)
+    e.allocate_qureg(list(range(6)), 0)       # locals 0..3,5 ; global 4
+    assert e.get_global_qubits_ids() == [4]
+    X = [[0, 1], [1, 0]]
+    with pytest.raises(RuntimeError, match="non-diagonal"):
+        e.apply_controlled_gate(X, [4], [])
+    with pytest.raises(RuntimeError, match="unique"):
+        e.swap_qubits([4, 0, 4, 1])
+    with pytest.raises(RuntimeError, match="Can't find"):
+        e.swap_qubits([0, 1])
+    with pytest.raises(RuntimeError, match="not supported"):
+        e.emulate_math(lambda x: x, [[0]], [])
+    # six fused qubits cannot run (reference: "Run(): cannot apply 6 qubits gate")
+    e2 = _dry_engines([("ctor", 1, 8, 4)], 1)[0]
+    e2.allocate_qureg(list(range(7)), 0)
+    for q in range(6):
+        e2.apply_controlled_gate(X, [q], [])
+    with pytest.raises(RuntimeError, match="cannot apply 6"):
+        e2.run()
+    # data-dependent calls need the device
+    with pytest.raises(RuntimeError, match="dry-run"):
+        e.get_probability([True], [0])
+
+
+def test_set_qubits_perm_is_relabel_only():
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    M.init_world(1, 4, b"", 0, M.FLAG_DRY_RUN)
+    e = M.SimulatorMPI(1, 8, 2)
+    M.init_world(0, 1, b"", 0, 0)
+    e.allocate_qureg(list(range(6)), 0)
+    ids = e.get_qubits_ids()
+    assert ids == [0, 1, 4, 5, 2, 3]
+    n = len(e.trace())
+    ids[0], ids[4] = ids[4], ids[0]
+    e.set_qubits_perm(ids)
+    assert e.get_local_qubits_ids() == [2, 1, 4, 5] and e.get_global_qubits_ids() == [0, 3]
+    assert len(e.trace()) == n  # no data motion

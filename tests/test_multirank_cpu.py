@@ -1,0 +1,29 @@
+"""World-size-2 run of the N>1 plumbing on CPU (gloo): torchrun launches two ranks, each builds a
+dry-run engine for its rank, the descriptor traces are gathered on rank 0 and replayed against
+the reference's golden state."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _free_port():
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.parametrize("name,R", [("r2_q10_gates", 2), ("r2_q9", 2), ("r4_q12_gates", 4)])
+def test_dry_run_world(name, R):
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(HERE, "mp_worker.py"), name, "dry"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
