@@ -1,0 +1,104 @@
+"""SimulatorMPI: host-side mirror of the reference's ProjectQ backend engine, without ProjectQ.
+
+Same constructor keywords, query methods and command handling as
+reference hiq/projectq/backends/_sim/_simulator_mpi.py:47-513, driving the B200 engine through
+the `_cppsim_mpi` pybind module (and therefore through the C ABI).  `cheat()` gathers the rank
+slabs with torch.distributed instead of mpi4py.
+"""
+from __future__ import annotations
+
+import random
+
+import numpy as np
+
+from . import _cppsim_mpi as _M
+from . import ops
+
+
+class SimulatorMPI:
+    def __init__(self, gate_fusion=False, rnd_seed=None, num_local_qubits=33, max_fused_qubits=4, backend_class=None):
+        if rnd_seed is None:
+            rnd_seed = random.randint(0, 4294967295)
+        cls = backend_class or _M.SimulatorMPI
+        self._simulator = cls(rnd_seed, num_local_qubits, max_fused_qubits)
+        self._gate_fusion = gate_fusion
+        self.main_engine = None
+        self.h2d_bytes = 0  # gate-matrix bytes handed to the engine (bench accounting)
+
+    # -- queries (reference: _simulator_mpi.py:148-346) ------------------------------------------
+    def get_probability(self, bit_string, qureg):
+        bit_string = [bool(int(b)) for b in bit_string]
+        return self._simulator.get_probability(bit_string, list(qureg))
+
+    def get_amplitude(self, bit_string, qureg):
+        bit_string = [bool(int(b)) for b in bit_string]
+        return self._simulator.get_amplitude(bit_string, list(qureg))
+
+    def collapse_wavefunction(self, qureg, values):
+        return self._simulator.collapse_wavefunction(list(qureg), [bool(int(v)) for v in values])
+
+    def cheat_local(self):
+        return self._simulator.cheat_local()
+
+    def cheat(self):
+        """(id2pos, full state vector) — concatenation of the rank slabs (reference: :348-380)."""
+        id2pos, vec = self.cheat_local()
+        rank, world = _M.world()[:2]
+        if world == 1:
+            return id2pos, np.asarray(vec)
+        import torch
+        import torch.distributed as dist
+        t = torch.from_numpy(np.ascontiguousarray(vec)).view(torch.float64)
+        if dist.get_backend() == "nccl":
+            t = t.cuda()
+        parts = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(parts, t)
+        return id2pos, np.concatenate([p.cpu().numpy().view(np.complex128) for p in parts])
+
+    def get_qubits_ids(self):
+        return self._simulator.get_qubits_ids()
+
+    def get_local_qubits_ids(self):
+        return self._simulator.get_local_qubits_ids()
+
+    def get_global_qubits_ids(self):
+        return self._simulator.get_global_qubits_ids()
+
+    def set_qubits_perm(self, ids):
+        self._simulator.set_qubits_perm(list(ids))
+
+    # -- command handling (reference: _simulator_mpi.py:416-513) -----------------------------------
+    def _handle(self, cmd):
+        if cmd.kind == ops.FLUSH:
+            pass
+        elif cmd.kind == ops.METASWAP:
+            self._simulator.swap_qubits(list(cmd.qubits))
+        elif cmd.kind == ops.MEASURE:
+            assert len(cmd.controls) == 0
+            out = self._simulator.measure_qubits(list(cmd.qubits))
+            for q, b in zip(cmd.qubits, out):
+                if self.main_engine is not None:
+                    self.main_engine.set_measurement_result(q, b)
+            cmd.result = list(out)
+        elif cmd.kind == ops.ALLOCATE:
+            self._simulator.allocate_qubit(cmd.qubits[0])
+        elif cmd.kind == ops.ALLOCATE_QUREG:
+            self._simulator.allocate_qureg(list(cmd.qubits), cmd.init)
+        elif cmd.kind == ops.DEALLOCATE:
+            self._simulator.deallocate_qubit(cmd.qubits[0])
+        elif cmd.kind == ops.GATE and len(cmd.matrix) <= 2 ** 5:
+            if not 2 ** len(cmd.qubits) == len(cmd.matrix):
+                raise Exception("Simulator: Error applying {} gate: {}-qubit gate applied to {} qubits.".format(
+                    cmd.name, int(np.log2(len(cmd.matrix))), len(cmd.qubits)))
+            self.h2d_bytes += cmd.matrix.nbytes
+            self._simulator.apply_controlled_matrix(cmd.matrix, list(cmd.qubits), list(cmd.controls))
+            if not self._gate_fusion:
+                self._simulator.run()
+        else:
+            raise Exception("This simulator only supports controlled k-qubit gates with k < 6!")
+
+    def receive(self, command_list):
+        for cmd in command_list:
+            if cmd.kind == ops.FLUSH or cmd.fast_forwarding:
+                self._simulator.run()  # flush gate --> run all saved gates
+            self._handle(cmd)

@@ -1,0 +1,213 @@
+"""GreedyScheduler: the stage/cluster driver loop around `_sched_cpp`, restated without ProjectQ.
+
+Behavioural spec: reference hiq/projectq/cengines/_greedyscheduler.py:95-265.
+Gates are cached; Allocate / AllocateQureg / fast-forwarding commands force scheduling:
+  first time only, the SwapScheduler picks the initial local set and the backend is *relabelled*
+  (set_qubits_perm, no data motion); then ClusterScheduler is asked repeatedly which cached gates
+  form the next cluster (sent followed by one Flush); when nothing is schedulable a MetaSwap with
+  pairs [g->l id, l->g id, ...] starts the next stage.
+Every gate is reported to the schedulers as non-diagonal (reference: _greedyscheduler.py:28).
+"""
+from __future__ import annotations
+
+import time
+
+from . import ops
+
+
+class GreedyScheduler:
+    def __init__(self, supremacy_circuit=False, num_splits=10 ** 6, cluster_size=4, sched_module=None):
+        if sched_module is None:
+            from . import _sched_cpp as sched_module
+        self._sched = sched_module
+        self._cmd_list = []
+        self._was_scheduling = False
+        self._supremacy_circuit = supremacy_circuit
+        self.NUM_SPLITS = num_splits
+        self.CLUSTER_SIZE = cluster_size
+        self._deallocations_cache = []
+        self.backend = None
+        self.next_engine = None
+        # instrumentation (host seconds spent inside the C++ schedulers, emitted schedule shape)
+        self.cluster_seconds = 0.0
+        self.swap_seconds = 0.0
+        self.n_clusters = 0
+        self.n_swaps = 0
+        self.log = []  # ("cluster", [ids of gates...]) / ("swap", pairs) / ("perm", ids)
+
+    # -- wiring --------------------------------------------------------------------------------
+    def send(self, cmds):
+        self.next_engine.receive(cmds)
+
+    # -- reference: _greedyscheduler.py:95-112
+    def _prepare_ctrlz(self):
+        local_qubits = self.backend.get_local_qubits_ids()
+        global_qubits = self.backend.get_global_qubits_ids()
+        for cmd in self._cmd_list:
+            if cmd.is_z:
+                assert len(cmd.qubits) == 1
+                if cmd.qubits[0] in global_qubits:
+                    for i, c in enumerate(cmd.controls):
+                        if c in local_qubits:
+                            cmd.controls[i], cmd.qubits[0] = cmd.qubits[0], cmd.controls[i]
+                            break
+
+    def _get_commands(self):
+        return ([list(c.qubits) for c in self._cmd_list], [list(c.controls) for c in self._cmd_list],
+                [False] * len(self._cmd_list))
+
+    # -- reference: _greedyscheduler.py:119-137
+    def _call_cluster_scheduler(self):
+        self._prepare_ctrlz()
+        local_qubits = self.backend.get_local_qubits_ids()
+        global_qubits = self.backend.get_global_qubits_ids()
+        while True:
+            gate, gate_ctrl, gate_diag = self._get_commands()
+            t0 = time.perf_counter()
+            cs = self._sched.ClusterScheduler(gate, gate_ctrl, gate_diag, local_qubits, global_qubits, self.CLUSTER_SIZE)
+            avail = cs.ScheduleCluster()
+            self.cluster_seconds += time.perf_counter() - t0
+            if len(avail) == 0:
+                return
+            self.n_clusters += 1
+            self.log.append(("cluster", [self._cmd_list[i].uid for i in avail]))
+            for i in avail:
+                self.send([self._cmd_list[i]])
+            self.send([ops.Flush()])
+            for i in reversed(sorted(avail)):
+                del self._cmd_list[i]
+
+    # -- reference: _greedyscheduler.py:151-173
+    def _remove_ending_cz(self):
+        i = len(self._cmd_list) - 1
+        used = set()
+        while i >= 0:
+            cmd = self._cmd_list[i]
+            allq = list(cmd.controls) + list(cmd.qubits)
+            bad = True
+            if cmd.is_z:
+                if any(q in used for q in allq):
+                    bad = False
+            else:
+                bad = False
+            if bad:
+                self._cmd_list.pop(i)
+            else:
+                used.update(allq)
+            i -= 1
+
+    # -- reference: _greedyscheduler.py:175-193
+    def _call_swap_scheduler(self):
+        local_qubits = self.backend.get_local_qubits_ids()
+        gate, gate_ctrl, gate_diag = self._get_commands()
+        t0 = time.perf_counter()
+        new_locals = self._sched.SwapScheduler(gate, gate_ctrl, gate_diag, self.NUM_SPLITS, len(local_qubits), True).ScheduleSwap()
+        if len(new_locals) == 0:
+            new_locals = self._sched.SwapScheduler(gate, gate_ctrl, gate_diag, self.NUM_SPLITS, len(local_qubits), False).ScheduleSwap()
+        self.swap_seconds += time.perf_counter() - t0
+        g_to_l = sorted(set(new_locals) - set(local_qubits))
+        l_to_g = []
+        if len(g_to_l) > 0:
+            lst = sorted(set(local_qubits) - set(new_locals))
+            assert len(lst) >= len(g_to_l)
+            l_to_g = lst[:len(g_to_l)]
+        return g_to_l, l_to_g
+
+    # -- reference: _greedyscheduler.py:195-201
+    def _check_commands(self):
+        locals_size = len(self.backend.get_local_qubits_ids())
+        for gate in self._get_commands()[0]:
+            if locals_size < len(gate):
+                raise Exception("Can't apply {}-qubits gate (only {} local qubits)".format(len(gate), locals_size))
+            if len(gate) > 5:
+                raise Exception("Can't apply {}-qubits gate (no more that 5 qubits allowed)".format(len(gate)))
+
+    # -- reference: _greedyscheduler.py:203-242
+    def _force_scheduling(self):
+        if len(self._cmd_list) == 0:
+            return
+        self._check_commands()
+        if self._supremacy_circuit:
+            self._remove_ending_cz()
+        if not self._was_scheduling:
+            self._was_scheduling = True
+            ids_list = list(self.backend.get_qubits_ids())
+            g_to_l, l_to_g = self._call_swap_scheduler()
+            for i in range(len(l_to_g)):
+                p1 = ids_list.index(g_to_l[i])
+                p2 = ids_list.index(l_to_g[i])
+                ids_list[p1], ids_list[p2] = ids_list[p2], ids_list[p1]
+            self.backend.set_qubits_perm(ids_list)
+            self.log.append(("perm", list(ids_list)))
+        self._call_cluster_scheduler()
+        while len(self._cmd_list) > 0:
+            g_to_l, l_to_g = self._call_swap_scheduler()
+            assert len(g_to_l) > 0
+            pairs = []
+            for i in range(len(g_to_l)):
+                pairs += [g_to_l[i], l_to_g[i]]
+            self.n_swaps += 1
+            self.log.append(("swap", list(pairs)))
+            self.send([ops.MetaSwap(pairs)])
+            self._call_cluster_scheduler()
+        assert len(self._cmd_list) == 0
+
+    def _send_deallocations(self):
+        for c in sorted(self._deallocations_cache, key=lambda cmd: cmd.qubits[0], reverse=True):
+            self.send([c])
+        del self._deallocations_cache[:]
+
+    # -- reference: _greedyscheduler.py:250-265
+    def receive(self, command_list):
+        for cmd in command_list:
+            if not hasattr(cmd, "uid"):
+                cmd.uid = GreedyScheduler._next_uid
+                GreedyScheduler._next_uid += 1
+            if cmd.kind == ops.DEALLOCATE:
+                self._deallocations_cache.append(cmd)
+            elif cmd.kind in (ops.ALLOCATE, ops.ALLOCATE_QUREG) or cmd.fast_forwarding:
+                self._force_scheduling()
+                self._send_deallocations()
+                self.send([cmd])
+            else:
+                if len(self._deallocations_cache) > 0:
+                    self._force_scheduling()
+                    self._send_deallocations()
+                self._cmd_list.append(cmd)
+
+    _next_uid = 0
+
+
+class HiQMainEngine:
+    """Thin stand-in for the reference's HiQMainEngine(backend, [GreedyScheduler()]) wiring
+    (reference: hiq/projectq/cengines/_hiq_main_engine.py:22-81): scheduler -> backend."""
+
+    def __init__(self, backend, engine_list=None):
+        self.backend = backend
+        self.scheduler = (engine_list or [GreedyScheduler()])[-1]
+        self.scheduler.backend = backend
+        self.scheduler.next_engine = backend
+        backend.main_engine = self
+        self._next_id = 0
+        self.measurements = {}
+
+    def allocate_qubit(self):
+        q = self._next_id
+        self._next_id += 1
+        self.receive([ops.Allocate(q)])
+        return q
+
+    def allocate_qureg(self, n, init=0.0):
+        ids = list(range(self._next_id, self._next_id + n))
+        self._next_id += n
+        self.receive([ops.AllocateQureg(ids, init)])
+        return ids
+
+    def receive(self, cmds):
+        self.scheduler.receive(cmds)
+
+    def flush(self):
+        self.receive([ops.Flush()])
+
+    def set_measurement_result(self, qid, value):
+        self.measurements[qid] = bool(value)

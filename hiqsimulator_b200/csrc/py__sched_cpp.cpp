@@ -1,0 +1,23 @@
+// pybind11 module `_sched_cpp`: same two classes, constructor signatures and methods as the
+// reference binding (reference: _sched_cpp.cpp:28-39), backed by csrc/sched.cpp.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "sched.hpp"
+
+namespace py = pybind11;
+using namespace hiq::sched;
+
+PYBIND11_MODULE(_sched_cpp, m)
+{
+     m.doc() = "B200 engine host scheduler: drop-in for HiQsimulator's _sched_cpp";
+     py::class_<SwapScheduler>(m, "SwapScheduler")
+         .def(py::init<const std::vector<std::vector<Id>>&, const std::vector<std::vector<Id>>&, std::vector<bool>, int, int, bool>())
+         .def("ScheduleSwap", &SwapScheduler::ScheduleSwap, py::call_guard<py::gil_scoped_release>());
+     py::class_<ClusterScheduler>(m, "ClusterScheduler")
+         .def(py::init<const std::vector<std::vector<Id>>&, const std::vector<std::vector<Id>>&, std::vector<bool>,
+                       const std::vector<Id>&, const std::vector<Id>&, int>())
+         .def("ScheduleCluster", &ClusterScheduler::ScheduleCluster, py::call_guard<py::gil_scoped_release>())
+         .def("candidates", &ClusterScheduler::candidates);
+     m.def("set_threads", &ClusterScheduler::set_threads, "host threads used to score candidate clusters (0 = auto)");
+}

@@ -1,0 +1,343 @@
+#include "sched.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <stdexcept>
+#include <thread>
+#include <unordered_set>
+
+namespace hiq {
+namespace sched {
+
+static inline int popcount(Mask m) { return __builtin_popcountll(m); }
+static inline bool subset(Mask a, Mask b) { return (a & ~b) == 0; }
+
+// ------------------------------------------------------------------------------------ Universe
+void Universe::build(const std::vector<std::vector<Id>>& gate, const std::vector<std::vector<Id>>& gate_ctrl,
+                     const std::vector<Id>& extra_a, const std::vector<Id>& extra_b)
+{
+     // position = rank of the id among all distinct ids seen (ascending id == ascending position)
+     pos_to_id.clear();
+     for (auto& g: gate) pos_to_id.insert(pos_to_id.end(), g.begin(), g.end());
+     for (auto& g: gate_ctrl) pos_to_id.insert(pos_to_id.end(), g.begin(), g.end());
+     pos_to_id.insert(pos_to_id.end(), extra_a.begin(), extra_a.end());
+     pos_to_id.insert(pos_to_id.end(), extra_b.begin(), extra_b.end());
+     std::sort(pos_to_id.begin(), pos_to_id.end());
+     pos_to_id.erase(std::unique(pos_to_id.begin(), pos_to_id.end()), pos_to_id.end());
+     if (pos_to_id.size() >= 64) throw std::runtime_error("CalcPos(): scheduling with 64 or more qubits is not yet supported");
+     id_to_pos.clear();
+     for (size_t i = 0; i < pos_to_id.size(); ++i) id_to_pos[pos_to_id[i]] = static_cast<int>(i);
+}
+
+Mask Universe::mask_of(const std::vector<Id>& ids) const
+{
+     Mask m = 0;
+     for (Id q: ids) m |= Mask(1) << id_to_pos.at(q);
+     return m;
+}
+
+std::vector<Id> Universe::ids_of(Mask m) const
+{
+     std::vector<Id> out;
+     for (int p = 0; p < 64 && (Mask(1) << p) <= m; ++p)
+          if ((m >> p) & 1) out.push_back(pos_to_id[p]);
+     return out;
+}
+
+// ------------------------------------------------------------------------------------ SwapScheduler
+SwapScheduler::SwapScheduler(const std::vector<std::vector<Id>>& gate, const std::vector<std::vector<Id>>& gate_ctrl,
+                             std::vector<bool> gate_diag, int num_splits, int num_locals, bool fuse)
+    : num_splits_(num_splits), num_locals_(num_locals), diag_(std::move(gate_diag)), weight_(gate.size(), 1)
+{
+     if (gate.size() != gate_ctrl.size() || gate.size() != diag_.size()) throw std::runtime_error("SwapScheduler: ctor(): size mismatch");
+     u_.build(gate, gate_ctrl, {}, {});
+     gate_.resize(gate.size());
+     ctrl_.resize(gate.size());
+     for (size_t i = 0; i < gate.size(); ++i) {
+          gate_[i] = u_.mask_of(gate[i]);
+          ctrl_[i] = u_.mask_of(gate_ctrl[i]);
+     }
+     if (fuse) fuse_single_qubit_gates();
+}
+
+bool SwapScheduler::can_take(int pos, Mask locals, Mask bad) const
+{
+     if ((ctrl_[pos] | gate_[pos]) & bad) return false;
+     if (!diag_[pos]) return popcount(gate_[pos] | locals) <= num_locals_;
+     return true;
+}
+
+void SwapScheduler::merge_into(int from, int to)
+{
+     weight_[to] += weight_[from];
+     weight_[from] = 0;
+     if (!diag_[from]) diag_[to] = false;
+     if (ctrl_[to] & gate_[from]) {
+          ctrl_[to] ^= gate_[from];  // the qubit stops being a control of the neighbour ...
+          gate_[to] |= gate_[from];  // ... and becomes one of its targets
+     }
+}
+
+bool SwapScheduler::merge_prev(int i)
+{
+     for (int j = i - 1; j >= 0; --j)
+          if (gate_[i] & (gate_[j] | ctrl_[j])) {
+               merge_into(i, j);
+               return true;
+          }
+     return false;
+}
+
+bool SwapScheduler::merge_next(int i)
+{
+     for (int j = i + 1; j < static_cast<int>(gate_.size()); ++j)
+          if (gate_[i] & (gate_[j] | ctrl_[j])) {
+               merge_into(i, j);
+               return true;
+          }
+     return false;
+}
+
+void SwapScheduler::fuse_single_qubit_gates()
+{
+     // last gate to first: a gate touching exactly one qubit is absorbed by a neighbour on that qubit
+     for (int i = static_cast<int>(gate_.size()) - 1; i >= 0; --i) {
+          bool absorbed = false;
+          if (popcount(gate_[i] | ctrl_[i]) == 1) {
+               if (!diag_[i]) absorbed = merge_next(i) || merge_prev(i);
+               else absorbed = merge_prev(i) || merge_next(i);
+          }
+          if (absorbed) {
+               gate_.erase(gate_.begin() + i);
+               ctrl_.erase(ctrl_.begin() + i);
+               diag_.erase(diag_.begin() + i);
+               weight_.erase(weight_.begin() + i);
+          }
+     }
+}
+
+std::vector<Id> SwapScheduler::ScheduleSwap()
+{
+     if (gate_.empty()) return {};
+     best_score_ = 0;
+     best_locals_ = 0;
+     search(0, 0, 0, 0, num_splits_);
+     return u_.ids_of(best_locals_);
+}
+
+// Budgeted backtracking; returns the unused split budget.  Branch order: skip first, then take.
+int SwapScheduler::search(int pos, Mask locals, Mask bad, int score, int splits)
+{
+     if (score > best_score_) {
+          best_score_ = score;
+          best_locals_ = locals;
+     }
+     if (pos == static_cast<int>(gate_.size())) return splits;
+
+     const bool takeable = can_take(pos, locals, bad);
+     bool skip = true;
+     int branches = 1;
+     if (takeable) {
+          if (!diag_[pos]) {
+               if (subset(gate_[pos], locals)) skip = false;  // already local: always take
+               else branches = 2;
+          }
+          else {
+               skip = false;  // diagonal gates never constrain the local set
+          }
+     }
+     if (splits == 0 && takeable && skip) {  // out of budget: take only
+          skip = false;
+          branches = 1;
+     }
+     splits -= branches - 1;
+     if (skip) {
+          const int give = splits / branches;
+          splits += search(pos + 1, locals, bad | gate_[pos] | ctrl_[pos], score, give) - give;
+     }
+     if (takeable) {
+          const Mask next_locals = diag_[pos] ? locals : (locals | gate_[pos]);
+          splits = search(pos + 1, next_locals, bad, score + weight_[pos], splits);
+     }
+     return splits;
+}
+
+// ------------------------------------------------------------------------------------ ClusterScheduler
+static std::atomic<int> g_threads{0};
+void ClusterScheduler::set_threads(int n) { g_threads.store(n); }
+
+ClusterScheduler::ClusterScheduler(const std::vector<std::vector<Id>>& gate, const std::vector<std::vector<Id>>& gate_ctrl,
+                                   std::vector<bool> gate_diag, const std::vector<Id>& locals, const std::vector<Id>& globals,
+                                   int cluster_size)
+    : cluster_size_(cluster_size), diag_(std::move(gate_diag))
+{
+     if (gate.size() != gate_ctrl.size() || gate.size() != diag_.size()) throw std::runtime_error("ClusterScheduler: ctor(): size mismatch");
+     u_.build(gate, gate_ctrl, locals, globals);
+     gate_.resize(gate.size());
+     ctrl_.resize(gate.size());
+     all_.resize(gate.size());
+     locals_ = u_.mask_of(locals);
+     globals_ = u_.mask_of(globals);
+     for (size_t i = 0; i < gate.size(); ++i) {
+          gate_[i] = u_.mask_of(gate[i]);
+          ctrl_[i] = u_.mask_of(gate_ctrl[i]);
+          all_[i] = gate_[i] | ctrl_[i];
+          // A gate without any local qubit can only be taken if it is diagonal (or has no targets);
+          // if none exists, a walk may stop as soon as every cluster qubit is blocked.
+          if ((all_[i] & locals_) == 0 && (diag_[i] || gate_[i] == 0)) early_exit_ok_ = false;
+     }
+}
+
+bool ClusterScheduler::can_take(int i, Mask cluster, Mask bad) const
+{
+     if ((all_[i] & bad) || !subset(all_[i] & locals_, cluster)) return false;
+     if (!diag_[i]) return subset(gate_[i], locals_);
+     return true;
+}
+
+// gates admitted by `cluster` in program order; a gate that is not admitted blocks its qubits
+int ClusterScheduler::score(Mask cluster) const
+{
+     Mask bad = 0;
+     int taken = 0;
+     const int n = static_cast<int>(gate_.size());
+     for (int i = 0; i < n; ++i) {
+          if (can_take(i, cluster, bad)) ++taken;
+          else {
+               bad |= all_[i];
+               if (early_exit_ok_ && subset(cluster, bad)) break;
+          }
+     }
+     return taken;
+}
+
+std::vector<int> ClusterScheduler::gates_of(Mask cluster) const
+{
+     Mask bad = 0;
+     std::vector<int> out;
+     for (int i = 0; i < static_cast<int>(gate_.size()); ++i) {
+          if (can_take(i, cluster, bad)) out.push_back(i);
+          else bad |= all_[i];
+     }
+     return out;
+}
+
+// Replays the reference's enumeration and records each distinct cluster the first time it is met.
+//
+// Reference walk (cluster_scheduler.cpp:80-99): Rec(c, bit) scores c, then walks bit upwards; at
+// every position it stops if (c, bit) was expanded before, marks it, recurses into (c | bit,
+// bit << 1) when the bit is an unused local and the cluster is not full, and goes on with bit << 1
+// until bit exceeds the highest local.  Because every walk runs to the top or into an already
+// marked position, the marked positions of a cluster always form a range [lo, top]; remembering
+// `lo` per cluster is therefore equivalent to the reference's per-(cluster, bit) memo, and the
+// walk only needs to touch the addable bits in [b0, lo).
+void ClusterScheduler::visit(Mask cluster, int b0)
+{
+     size_t slot = (cluster * 0x9E3779B97F4A7C15ull) >> table_shift_;
+     while (table_[slot].used && table_[slot].key != cluster) slot = (slot + 1) & table_mask_;
+     Entry& e = table_[slot];
+     if (!e.used) {
+          e.used = 1;
+          e.key = cluster;
+          e.lo = static_cast<uint8_t>(top_ + 1);
+          order_.push_back(cluster);
+     }
+     if (b0 >= e.lo) return;
+     const int hi = e.lo;
+     e.lo = static_cast<uint8_t>(b0);
+     if (popcount(cluster) >= cluster_size_) return;
+     Mask range = (hi >= 64 ? ~Mask(0) : ((Mask(1) << hi) - 1)) & ~((Mask(1) << b0) - 1);
+     Mask addable = locals_ & ~cluster & range;
+     while (addable) {
+          const int b = __builtin_ctzll(addable);
+          addable &= addable - 1;
+          visit(cluster | (Mask(1) << b), b + 1);
+     }
+}
+
+std::vector<int> ClusterScheduler::ScheduleCluster()
+{
+     if (gate_.empty()) return {};
+     order_.clear();
+     top_ = locals_ ? 63 - __builtin_clzll(locals_) : -1;
+     {
+          // capacity: every subset of the locals with <= cluster_size qubits, plus the seeds
+          const int nl = popcount(locals_);
+          double bound = static_cast<double>(gate_.size()) + 1;
+          double binom = 1;
+          for (int s = 0; s <= std::min(cluster_size_, nl); ++s) {
+               bound += binom;
+               binom = binom * (nl - s) / (s + 1);
+          }
+          size_t cap = 1024;
+          int shift = 54;
+          while (static_cast<double>(cap) < 2.0 * bound && shift > 34) {
+               cap <<= 1;
+               --shift;
+          }
+          table_.assign(cap, Entry{});
+          table_mask_ = cap - 1;
+          table_shift_ = shift;
+     }
+     for (size_t i = 0; i < gate_.size(); ++i) {
+          const Mask seed = locals_ & all_[i];
+          if (popcount(seed) <= cluster_size_) visit(seed, 0);
+     }
+     n_candidates_ = order_.size();
+
+     // winner = more gates, then fewer qubits, then earlier visit; score 0 never displaces "nothing"
+     struct Best {
+          int score = 0;
+          int bits = 0;
+          size_t index = 0;
+          bool better_than(const Best& o) const
+          {
+               if (score != o.score) return score > o.score;
+               if (bits != o.bits) return bits < o.bits;
+               return index < o.index;
+          }
+     };
+     auto scan = [&](size_t lo, size_t hi) {
+          Best b;
+          b.index = static_cast<size_t>(-1);
+          for (size_t k = lo; k < hi; ++k) {
+               Best c;
+               c.score = score(order_[k]);
+               if (c.score == 0) continue;
+               c.bits = popcount(order_[k]);
+               c.index = k;
+               if (b.index == static_cast<size_t>(-1) || c.better_than(b)) b = c;
+          }
+          return b;
+     };
+     int threads = g_threads.load();
+     if (threads <= 0) threads = static_cast<int>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+     if (order_.size() * gate_.size() < (1u << 18)) threads = 1;  // not worth the thread start-up
+     Best best;
+     best.index = static_cast<size_t>(-1);
+     if (threads == 1) {
+          best = scan(0, order_.size());
+     }
+     else {
+          std::vector<Best> part(threads);
+          std::vector<std::thread> pool;
+          const size_t per = (order_.size() + threads - 1) / threads;
+          for (int t = 0; t < threads; ++t)
+               pool.emplace_back([&, t] { part[t] = scan(std::min(order_.size(), t * per), std::min(order_.size(), (t + 1) * per)); });
+          for (auto& th: pool) th.join();
+          for (auto& p: part)
+               if (p.index != static_cast<size_t>(-1) && (best.index == static_cast<size_t>(-1) || p.better_than(best))) best = p;
+     }
+     if (best.index != static_cast<size_t>(-1)) return gates_of(order_[best.index]);
+
+     // nothing fits a cluster: the first gate that can run when every local qubit is allowed ("huge gate")
+     Mask bad = 0;
+     for (int i = 0; i < static_cast<int>(gate_.size()); ++i) {
+          if (can_take(i, locals_, bad)) return {i};
+          bad |= all_[i];
+     }
+     return {};
+}
+
+}  // namespace sched
+}  // namespace hiq

@@ -1,0 +1,92 @@
+// Host-side stage / cluster scheduling (the `_sched_cpp` surface of the reference).
+//
+// Behavioural spec (must be reproduced bit-exactly):
+//   SwapScheduler    reference: src/scheduler/swap_scheduler.{h,cpp}
+//   ClusterScheduler reference: src/scheduler/cluster_scheduler.{h,cpp}
+//   id <-> bit-position conversion: src/scheduler/convertors.cpp:45-73
+// The algorithms are re-implemented, not transcribed: the cluster search replays the reference's
+// deterministic first-visit order of candidate qubit sets without scoring, then scores the
+// candidates with an early-exit walk (optionally on several host threads) and reduces
+// lexicographically (more gates, fewer qubits, earlier visit) — the same winner, much sooner.
+#pragma once
+#include <cstdint>
+#include <map>
+#include <vector>
+
+namespace hiq {
+namespace sched {
+
+using Id = int64_t;
+using Mask = uint64_t;
+
+struct Universe {
+     std::vector<Id> pos_to_id;  // ascending ids
+     std::map<Id, int> id_to_pos;
+     void build(const std::vector<std::vector<Id>>& gate, const std::vector<std::vector<Id>>& gate_ctrl,
+                const std::vector<Id>& extra_a, const std::vector<Id>& extra_b);
+     Mask mask_of(const std::vector<Id>& ids) const;
+     std::vector<Id> ids_of(Mask m) const;
+};
+
+class SwapScheduler {
+public:
+     SwapScheduler(const std::vector<std::vector<Id>>& gate, const std::vector<std::vector<Id>>& gate_ctrl,
+                   std::vector<bool> gate_diag, int num_splits, int num_locals, bool fuse);
+     // ids of the qubits that should be local during the next stage (ascending)
+     std::vector<Id> ScheduleSwap();
+
+private:
+     bool can_take(int pos, Mask locals, Mask bad) const;
+     void merge_into(int from, int to);
+     bool merge_prev(int i);
+     bool merge_next(int i);
+     void fuse_single_qubit_gates();
+     int search(int pos, Mask locals, Mask bad, int score, int splits);
+
+     int num_splits_, num_locals_;
+     Universe u_;
+     std::vector<Mask> gate_, ctrl_;
+     std::vector<bool> diag_;
+     std::vector<int> weight_;
+     int best_score_ = 0;
+     Mask best_locals_ = 0;
+};
+
+class ClusterScheduler {
+public:
+     ClusterScheduler(const std::vector<std::vector<Id>>& gate, const std::vector<std::vector<Id>>& gate_ctrl,
+                      std::vector<bool> gate_diag, const std::vector<Id>& locals, const std::vector<Id>& globals,
+                      int cluster_size);
+     // indices (program order) of the gates of the best next cluster; {} if nothing can run
+     std::vector<int> ScheduleCluster();
+     // number of candidate clusters scored by the last call (diagnostics)
+     size_t candidates() const { return n_candidates_; }
+     static void set_threads(int n);
+
+private:
+     bool can_take(int i, Mask cluster, Mask bad) const;
+     int score(Mask cluster) const;
+     std::vector<int> gates_of(Mask cluster) const;
+     void visit(Mask cluster, int b0);
+
+     int cluster_size_;
+     Universe u_;
+     Mask locals_ = 0, globals_ = 0;
+     std::vector<Mask> gate_, ctrl_, all_;
+     std::vector<bool> diag_;
+     bool early_exit_ok_ = true;
+     struct Entry {
+          Mask key = 0;
+          uint8_t used = 0;
+          uint8_t lo = 0;  // lowest bit position already expanded for this cluster
+     };
+     std::vector<Entry> table_;          // open-addressing memo: cluster -> expansion range
+     size_t table_mask_ = 0;
+     int table_shift_ = 0;
+     int top_ = -1;                      // position of the highest local qubit
+     std::vector<Mask> order_;           // candidates in first-visit order
+     size_t n_candidates_ = 0;
+};
+
+}  // namespace sched
+}  // namespace hiq

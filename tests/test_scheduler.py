@@ -1,0 +1,163 @@
+"""`_sched_cpp` re-implementation vs the reference scheduler: cluster choices, swap choices and the
+complete GreedyScheduler command stream must be bit-exact (BASELINE.json north_star).
+Live differential runs need oracle/_ref (the unmodified reference scheduler, compiled by
+oracle/Makefile; it travels to the GPU box); golden schedules in tests/golden pin the same thing
+where it is absent."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ref
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+needs_ref = pytest.mark.skipif(not ref.have_ref(), reason="oracle/_ref not built")
+
+
+def _mine():
+    from hiqsimulator_b200 import _sched_cpp
+    return _sched_cpp
+
+
+def _random_gates(rng, n_qubits, n_gates, max_targets=3, max_ctrls=2, diag_prob=0.0):
+    gate, ctrl, diag = [], [], []
+    for _ in range(n_gates):
+        k = int(rng.integers(1, max_targets + 1))
+        c = int(rng.integers(0, max_ctrls + 1))
+        qs = [int(x) for x in rng.choice(n_qubits, size=min(k + c, n_qubits), replace=False)]
+        gate.append(qs[:k])
+        ctrl.append(qs[k:])
+        diag.append(bool(rng.random() < diag_prob))
+    return gate, ctrl, diag
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(40))
+def test_cluster_scheduler_fuzz(seed):
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(4, 24))
+    g = int(rng.integers(0, 4))
+    ids = [int(x) for x in rng.permutation(n + 3)[:n]]  # non-contiguous ids
+    n_glob = min(g, n - 2)
+    locals_, globals_ = ids[: n - n_glob], ids[n - n_glob:]
+    if seed % 5 == 0:
+        globals_ = globals_ + [-1]  # an unallocated global slot flows into the scheduler
+    gate, ctrl, diag = _random_gates(rng, n, int(rng.integers(1, 120)), diag_prob=0.0 if seed % 3 else 0.3)
+    gate = [[ids[q] for q in t] for t in gate]
+    ctrl = [[ids[q] for q in t] for t in ctrl]
+    size = int(rng.integers(2, 6))
+    R = ref.load_ref_sched()
+    exp = R.ClusterScheduler(gate, ctrl, diag, locals_, globals_, size).ScheduleCluster()
+    got = _mine().ClusterScheduler(gate, ctrl, diag, locals_, globals_, size).ScheduleCluster()
+    assert list(got) == list(exp)
+
+
+@needs_ref
+@pytest.mark.parametrize("seed", range(40))
+def test_swap_scheduler_fuzz(seed):
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(4, 26))
+    gate, ctrl, diag = _random_gates(rng, n, int(rng.integers(1, 150)), diag_prob=0.0 if seed % 3 else 0.3)
+    num_locals = int(rng.integers(3, n + 1))
+    # every gate must fit the local set
+    gate = [t[:num_locals] for t in gate]
+    splits = int(rng.choice([0, 1, 7, 100, 10 ** 4, 10 ** 6]))
+    R = ref.load_ref_sched()
+    for fuse in (True, False):
+        exp = R.SwapScheduler(gate, ctrl, diag, splits, num_locals, fuse).ScheduleSwap()
+        got = _mine().SwapScheduler(gate, ctrl, diag, splits, num_locals, fuse).ScheduleSwap()
+        assert list(got) == list(exp)
+
+
+def greedy_log(n, cmds, R, max_local, sched_module, cluster=4, supremacy=False):
+    """Full GreedyScheduler run against a dry-run engine; returns the emitted schedule."""
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    from hiqsimulator_b200 import backends, cengines
+    M.init_world(0, R, b"", 0, M.FLAG_DRY_RUN)
+    be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=max_local, max_fused_qubits=cluster)
+    M.init_world(0, 1, b"", 0, 0)
+    gs = cengines.GreedyScheduler(cluster_size=cluster, sched_module=sched_module, supremacy_circuit=supremacy)
+    eng = cengines.HiQMainEngine(be, [gs])
+    eng.allocate_qureg(n)
+    cmds = copy.deepcopy(cmds)
+    for i, c in enumerate(cmds):
+        c.uid = i
+    eng.receive(cmds)
+    eng.flush()
+    return [[k, [int(x) for x in v]] for k, v in gs.log], be
+
+
+def _circuit(name):
+    from hiqsimulator_b200 import circuits
+    if name == "qft18":
+        return circuits.qft_circuit(18) + (1, 18)
+    if name == "qft20_r4":
+        return circuits.qft_circuit(20) + (4, 18)
+    if name == "rand20_r8":
+        return circuits.random_circuit(20, 12) + (8, 17)
+    if name == "rand16":
+        return circuits.random_circuit(16, 20) + (1, 16)
+    if name == "grover9":
+        return circuits.grover_circuit(9, 3) + (1, 12)
+    if name == "grover9_r2":
+        return circuits.grover_circuit(9, 3) + (2, 9)
+    raise KeyError(name)
+
+
+CIRCUITS = ["qft18", "qft20_r4", "rand20_r8", "rand16", "grover9", "grover9_r2"]
+
+
+@needs_ref
+@pytest.mark.parametrize("name", CIRCUITS)
+def test_greedy_schedule_matches_reference_scheduler(name):
+    n, cmds, R, ml = _circuit(name)
+    mine, _ = greedy_log(n, cmds, R, ml, _mine())
+    theirs, _ = greedy_log(n, cmds, R, ml, ref.load_ref_sched())
+    assert mine == theirs
+
+
+@pytest.mark.parametrize("name", CIRCUITS)
+def test_greedy_schedule_matches_golden(name):
+    path = os.path.join(HERE, "golden", "sched_%s.json" % name)
+    n, cmds, R, ml = _circuit(name)
+    mine, _ = greedy_log(n, cmds, R, ml, _mine())
+    with open(path) as f:
+        assert mine == json.load(f)
+
+
+def test_scheduled_circuit_is_executable_and_correct():
+    """Dry-run descriptors of a scheduled multi-rank circuit, replayed with the oracle kernels,
+    equal the unscheduled circuit applied gate by gate (the scheduler only reorders commuting work)."""
+    import scripts
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    from hiqsimulator_b200 import backends, cengines, circuits
+    from oracle import statevec
+    n, cmds = circuits.random_circuit(10, 6, seed=5)
+    R = 4
+    traces = []
+    for r in range(R):
+        M.init_world(r, R, b"", 0, M.FLAG_DRY_RUN)
+        be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=8, max_fused_qubits=4)
+        eng = cengines.HiQMainEngine(be, [cengines.GreedyScheduler()])
+        eng.allocate_qureg(n)
+        eng.receive(copy.deepcopy(cmds))
+        eng.flush()
+        traces.append(be._simulator.trace())
+        perm = be.get_qubits_ids()
+    M.init_world(0, 1, b"", 0, 0)
+    state = scripts.replay_traces(traces, R)
+    # plain application on a single-rank oracle, qubit q at bit q
+    o = statevec.SimulatorMPI(1, n, 5, 1)
+    o.allocate_qureg(list(range(n)), 0)
+    for c in cmds:
+        o.apply_controlled_gate(c.matrix, c.qubits, c.controls)
+        o.run()
+    ref_state = o.vec[0]
+    # re-index: scheduled bit position p holds qubit perm[p]
+    idx = np.arange(1 << n)
+    src = np.zeros_like(idx)
+    for p, q in enumerate(perm):
+        src |= ((idx >> p) & 1) << q
+    assert np.abs(state - ref_state[src]).max() <= 1e-12
