@@ -32,6 +32,7 @@ _SIGNATURES = {
     "hiq_version": (C.c_char_p, []),
     "hiq_device_count": (C.c_int, []),
     "hiqk_apply_dense": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _dp, _u64, C.c_int, _vp]),
+    "hiqk_dense_pick_variant": (C.c_int, [C.c_int, C.c_int, _ip]),
     "hiqk_apply_diag": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _dp, _u64, _vp]),
     "hiqk_scale": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp]),
     "hiqk_workspace_bytes": (C.c_size_t, []),

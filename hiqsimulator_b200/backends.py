@@ -91,7 +91,10 @@ class SimulatorMPI:
                 raise Exception("Simulator: Error applying {} gate: {}-qubit gate applied to {} qubits.".format(
                     cmd.name, int(np.log2(len(cmd.matrix))), len(cmd.qubits)))
             self.h2d_bytes += cmd.matrix.nbytes
-            self._simulator.apply_controlled_matrix(cmd.matrix, list(cmd.qubits), list(cmd.controls))
+            if hasattr(self._simulator, "apply_controlled_matrix"):
+                self._simulator.apply_controlled_matrix(cmd.matrix, list(cmd.qubits), list(cmd.controls))
+            else:  # the reference binding only takes nested lists (reference: _simulator_mpi.py:485-488)
+                self._simulator.apply_controlled_gate(cmd.matrix.tolist(), list(cmd.qubits), list(cmd.controls))
             if not self._gate_fusion:
                 self._simulator.run()
         else:

@@ -402,16 +402,24 @@ static int launch_dmma(double2* psi, int L, const int* slots, const double* matr
      return check_launch("dense_dmma_kernel");
 }
 
+// Kernel choice measured on B200 (profiles/r01_sweep_a_L30.jsonl): the 32x32 product is FP64-bound and
+// fastest on the tensor cores; k <= 4 is HBM-bound and fastest with one tuple per thread unless a
+// target sits in the lowest slots, where the shared-memory tile keeps the accesses coalesced.
+static int pick_variant(int L, int k, const int* slots)
+{
+     int min_slot = 64;
+     for (int l = 0; l < k; ++l) min_slot = std::min(min_slot, slots[l]);
+     const bool can_tile = tile_bits_for(k, L) >= k + 3 && L >= 10;
+     if (k == 5) return (L - k >= 3) ? HIQK_DENSE_DMMA : HIQK_DENSE_DIRECT;
+     if (k == 4) return (min_slot < 1 && can_tile) ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT;
+     return (min_slot < 2 && can_tile) ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT;
+}
+
 template <int K>
 static int dispatch_k(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask, int variant,
                       cudaStream_t stream)
 {
-     int min_slot = 64;
-     for (int l = 0; l < K; ++l) min_slot = std::min(min_slot, slots[l]);
-     if (variant == HIQK_DENSE_AUTO) {
-          const bool can_tile = tile_bits_for(K, L) >= K + 3 && L >= 10;
-          variant = (min_slot < 2 && can_tile) ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT;
-     }
+     if (variant == HIQK_DENSE_AUTO) variant = pick_variant(L, K, slots);
      switch (variant) {
           case HIQK_DENSE_DIRECT: return launch_direct<K>(psi, L, slots, matrix, ctrl_mask, stream);
           case HIQK_DENSE_TILED: return launch_tiled<K>(psi, L, slots, matrix, ctrl_mask, stream);
@@ -423,6 +431,12 @@ static int dispatch_k(double2* psi, int L, const int* slots, const double* matri
 }
 
 }  // namespace hiq
+
+extern "C" int hiqk_dense_pick_variant(int L, int k, const int* slots)
+{
+     if (!slots || k < 1 || k > hiq::kMaxTargets) return HIQK_DENSE_DIRECT;
+     return hiq::pick_variant(L, k, slots);
+}
 
 extern "C" int hiqk_apply_dense(void* slab, int L, int k, const int* slots, const double* matrix,
                                 uint64_t ctrl_mask, int variant, void* stream)

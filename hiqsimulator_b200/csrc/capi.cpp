@@ -228,6 +228,31 @@ int hiq_get_stats(hiq_engine* e, hiq_stats* out)
      out->allocs_s = s.allocs_s;
      out->deallocs_s = s.deallocs_s;
      out->swap_bytes_sent = s.swap_bytes_sent;
+     out->h2d_bytes = s.h2d_bytes;
+     out->d2h_bytes = s.d2h_bytes;
+     return HIQ_OK;
+}
+
+int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* variant, int cap, int* n)
+{
+     NEED(e);
+     return guarded([&] {
+          auto t = e->impl.collect_timings();
+          *n = static_cast<int>(t.size());
+          if (cap < *n) throw EngineError(HIQ_ERR_ARG, "hiq_collect_timings: buffer too small");
+          for (int i = 0; i < *n; ++i) {
+               ms[i] = t[i].ms;
+               kind[i] = t[i].kind;
+               k[i] = t[i].k;
+               variant[i] = t[i].variant;
+          }
+     });
+}
+
+int hiq_stream(hiq_engine* e, void** stream)
+{
+     NEED(e);
+     *stream = e->impl.stream();
      return HIQ_OK;
 }
 

@@ -51,7 +51,8 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
       world_(world_size),
       device_(device),
       dry_run_(flags & HIQ_FLAG_DRY_RUN),
-      tracing_(flags & (HIQ_FLAG_TRACE | HIQ_FLAG_DRY_RUN))
+      tracing_(flags & (HIQ_FLAG_TRACE | HIQ_FLAG_DRY_RUN)),
+      timing_((flags & HIQ_FLAG_TIMING) && !(flags & HIQ_FLAG_DRY_RUN))
 {
      if (world_size < 1 || (world_size & (world_size - 1)) || rank < 0 || rank >= world_size)
           fail("ctor(): world size must be a power of two and 0 <= rank < world size");
@@ -87,6 +88,11 @@ Engine::~Engine()
           if (d_blocks_) cudaFree(d_blocks_);
           if (swap_buf_) cudaFree(swap_buf_);
           slab_.release();
+          for (auto& t: timed_) {
+               cudaEventDestroy(t.start);
+               cudaEventDestroy(t.stop);
+          }
+          for (auto ev: event_pool_) cudaEventDestroy(ev);
           if (stream_) cudaStreamDestroy(stream_);
           if (comm_stream_) cudaStreamDestroy(comm_stream_);
      }
@@ -188,8 +194,7 @@ void Engine::deallocate_local(Index id)
      const int L = static_cast<int>(locals_.size());
      double sums[2];
      cu(hiqk_bit_norms(slab_.data(), L, static_cast<int>(pos), d_vals_, workspace_, stream_));
-     cu(check_cuda(cudaMemcpyAsync(sums, d_vals_, sizeof(sums), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
-     synchronize();
+     d2h(sums, d_vals_, sizeof(sums));
      cu(comm_.allreduce_sum(sums, 2, stream_));
      if (!((sums[0] > max_float_error_) ^ (sums[1] > max_float_error_)))
           fail("DeallocateLocalQubit(): qubit " + std::to_string(id) + " is entangled");
@@ -206,8 +211,7 @@ void Engine::deallocate_global(Index id)
      const int L = static_cast<int>(locals_.size());
      double local_norm = 0.0;
      cu(hiqk_prob_masked(slab_.data(), L, 0, 0, d_vals_, workspace_, stream_));
-     cu(check_cuda(cudaMemcpyAsync(&local_norm, d_vals_, sizeof(double), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
-     synchronize();
+     d2h(&local_norm, d_vals_, sizeof(double));
      double sums[2] = {0.0, 0.0};
      sums[(rank_ >> pos) & 1] = local_norm;
      cu(comm_.allreduce_sum(sums, 2, stream_));
@@ -299,15 +303,59 @@ void Engine::apply_gate(GateMatrix m, std::vector<Index> ids, std::vector<Index>
      fused_.insert(std::move(sub), diag, std::move(ids), {});
 }
 
+cudaEvent_t Engine::take_event()
+{
+     if (!event_pool_.empty()) {
+          cudaEvent_t ev = event_pool_.back();
+          event_pool_.pop_back();
+          return ev;
+     }
+     cudaEvent_t ev;
+     cu(check_cuda(cudaEventCreate(&ev), "cudaEventCreate"));
+     return ev;
+}
+
+std::vector<Engine::PassTime> Engine::collect_timings()
+{
+     std::vector<PassTime> out;
+     if (dry_run_) return out;
+     synchronize();
+     for (auto& t: timed_) {
+          float ms = 0.f;
+          cudaEventElapsedTime(&ms, t.start, t.stop);
+          out.push_back({t.kind, t.k, t.variant, static_cast<double>(ms)});
+          event_pool_.push_back(t.start);
+          event_pool_.push_back(t.stop);
+     }
+     timed_.clear();
+     return out;
+}
+
+void Engine::d2h(void* dst, const void* src, size_t bytes)
+{
+     cu(check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
+     synchronize();
+     stats_.d2h_bytes += static_cast<double>(bytes);
+}
+
 void Engine::execute(const Descriptor& d)
 {
      if (tracing_) trace_.push_back(d);
      if (dry_run_) return;
      const int L = static_cast<int>(locals_.size());
+     int variant = 0;
+     if (d.kind == HIQ_DESC_DENSE) variant = dense_variant_ ? dense_variant_ : hiqk_dense_pick_variant(L, d.k, d.slots);
+     TimedPass tp{d.kind, d.k, variant, nullptr, nullptr};
+     if (timing_) {
+          tp.start = take_event();
+          tp.stop = take_event();
+          cudaEventRecord(tp.start, stream_);
+     }
+     stats_.h2d_bytes += static_cast<double>(d.payload.size() * sizeof(cplx));
      switch (d.kind) {
           case HIQ_DESC_DENSE:
                cu(hiqk_apply_dense(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()), d.ctrl_mask,
-                                   dense_variant_, stream_));
+                                   variant, stream_));
                break;
           case HIQ_DESC_DIAG:
                cu(hiqk_apply_diag(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()), d.ctrl_mask,
@@ -315,6 +363,10 @@ void Engine::execute(const Descriptor& d)
                break;
           case HIQ_DESC_SCALE: cu(hiqk_scale(slab_.data(), L, d.payload[0].real(), d.payload[0].imag(), stream_)); break;
           default: break;
+     }
+     if (timing_) {
+          cudaEventRecord(tp.stop, stream_);
+          timed_.push_back(tp);
      }
 }
 
@@ -385,8 +437,7 @@ double Engine::probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint6
      double p = 0.0;
      if ((static_cast<uint64_t>(rank_) & gm) == gv) {
           cu(hiqk_prob_masked(slab_.data(), static_cast<int>(locals_.size()), lm, lv, d_vals_, workspace_, stream_));
-          cu(check_cuda(cudaMemcpyAsync(&p, d_vals_, sizeof(double), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
-          synchronize();
+          d2h(&p, d_vals_, sizeof(double));
      }
      cu(comm_.allreduce_sum(&p, 1, stream_));
      return p;
@@ -433,8 +484,7 @@ cplx Engine::get_amplitude(const std::vector<bool>& bits, const std::vector<Inde
      need_device("GetAmplitude()");
      cplx value(0.0);
      if (static_cast<uint64_t>(rank_) == owner) {
-          cu(check_cuda(cudaMemcpyAsync(&value, slab_.data() + num, sizeof(cplx), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
-          synchronize();
+          d2h(&value, slab_.data() + num, sizeof(cplx));
      }
      cu(comm_.broadcast_bytes(&value, sizeof(value), static_cast<int>(owner), stream_));
      return value;
@@ -464,8 +514,7 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
      cu(hiqk_block_norms(slab_.data(), L, n, d_blocks_ + n * rank_, stream_));
      cu(comm_.allgather(d_blocks_ + n * rank_, d_blocks_, n, stream_));
      std::vector<double> tot(n * world_);
-     cu(check_cuda(cudaMemcpyAsync(tot.data(), d_blocks_, sizeof(double) * tot.size(), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
-     synchronize();
+     d2h(tot.data(), d_blocks_, sizeof(double) * tot.size());
      // per-rank inclusive prefix, then the running shift over ranks — same order as the reference
      double shift = 0.0;
      for (int r = 0; r < world_; ++r) {
@@ -491,9 +540,7 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
           double acc = i > 0 ? tot[i - 1] : 0.0;
           std::vector<cplx> blk(block_size);
           k = src_index * block_size;
-          cu(check_cuda(cudaMemcpyAsync(blk.data(), slab_.data() + k, sizeof(cplx) * block_size, cudaMemcpyDeviceToHost, stream_),
-                        "cudaMemcpyAsync"));
-          synchronize();
+          d2h(blk.data(), slab_.data() + k, sizeof(cplx) * block_size);
           for (uint64_t j = 0; j < block_size; ++j, ++k) {
                acc += std::norm(blk[j]);
                if (acc >= rnd) break;
@@ -533,8 +580,7 @@ double Engine::entropy()
      need_device("Entropy()");
      double e = 0.0;
      cu(hiqk_entropy(slab_.data(), static_cast<int>(locals_.size()), d_vals_, workspace_, stream_));
-     cu(check_cuda(cudaMemcpyAsync(&e, d_vals_, sizeof(double), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
-     synchronize();
+     d2h(&e, d_vals_, sizeof(double));
      cu(comm_.allreduce_sum(&e, 1, stream_));
      return -e;
 }
@@ -569,8 +615,7 @@ void Engine::copy_slab_to_host(void* dst, uint64_t cap_amps)
      need_device("cheat_local()");
      const uint64_t n = 1ull << locals_.size();
      if (cap_amps < n) fail("cheat_local(): destination buffer too small");
-     cu(check_cuda(cudaMemcpyAsync(dst, slab_.data(), n * sizeof(double2), cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
-     synchronize();
+     d2h(dst, slab_.data(), n * sizeof(double2));
 }
 
 void Engine::copy_slab_from_host(const void* src, uint64_t n_amps)
@@ -579,6 +624,7 @@ void Engine::copy_slab_from_host(const void* src, uint64_t n_amps)
      if (n_amps != (1ull << locals_.size())) fail("set_local_slab(): size must equal 2^(local qubits)");
      cu(check_cuda(cudaMemcpyAsync(slab_.data(), src, n_amps * sizeof(double2), cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync"));
      synchronize();
+     stats_.h2d_bytes += static_cast<double>(n_amps * sizeof(double2));
 }
 
 // ------------------------------------------------------------------------------------ swaps
@@ -617,7 +663,19 @@ void Engine::swap_qubits(const std::vector<Index>& pairs)
           }
           trace_.push_back(d);
      }
-     if (!dry_run_ && !gpos.empty()) exchange(gpos, slots);
+     if (!dry_run_ && !gpos.empty()) {
+          TimedPass tp{HIQ_DESC_SWAP, static_cast<int>(gpos.size()), 0, nullptr, nullptr};
+          if (timing_) {
+               tp.start = take_event();
+               tp.stop = take_event();
+               cudaEventRecord(tp.start, stream_);
+          }
+          exchange(gpos, slots);
+          if (timing_) {
+               cudaEventRecord(tp.stop, stream_);
+               timed_.push_back(tp);
+          }
+     }
      for (size_t i = 0; i < gpos.size(); ++i) std::swap(locals_[slots[i]], globals_[gpos[i]]);
 }
 

@@ -42,6 +42,7 @@ struct EngineStats {
      uint64_t dense_passes = 0, diag_passes = 0, scale_passes = 0, skipped_passes = 0;
      double runs_s = 0, swaps_s = 0, measures_s = 0, allocs_s = 0, deallocs_s = 0;
      double swap_bytes_sent = 0;
+     double h2d_bytes = 0, d2h_bytes = 0;
 };
 
 class Engine {
@@ -80,6 +81,11 @@ public:
      bool dry_run() const { return dry_run_; }
      cudaStream_t stream() const { return stream_; }
      const EngineStats& stats() const { return stats_; }
+     struct PassTime {
+          int kind, k, variant;
+          double ms;
+     };
+     std::vector<PassTime> collect_timings();
      const std::vector<Descriptor>& trace() const { return trace_; }
      void clear_trace() { trace_.clear(); }
      void set_dense_variant(int v) { dense_variant_ = v; }
@@ -111,7 +117,7 @@ private:
      const double max_float_error_ = 1e-12;
      size_t min_local_, max_local_, max_global_, max_cluster_;
      int rank_, world_, device_;
-     bool dry_run_, tracing_;
+     bool dry_run_, tracing_, timing_;
      std::vector<Index> locals_, globals_;
      FusionAccumulator fused_;
      std::mt19937 rnd_eng_;
@@ -130,6 +136,14 @@ private:
 
      EngineStats stats_;
      std::vector<Descriptor> trace_;
+     struct TimedPass {
+          int kind, k, variant;
+          cudaEvent_t start, stop;
+     };
+     std::vector<TimedPass> timed_;
+     std::vector<cudaEvent_t> event_pool_;
+     cudaEvent_t take_event();
+     void d2h(void* dst, const void* src, size_t bytes);
 };
 
 }  // namespace hiq

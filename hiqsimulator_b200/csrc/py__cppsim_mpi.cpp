@@ -42,6 +42,14 @@ public:
           check(hiq_create(seed, max_local, max_cluster, g_world.rank, g_world.size,
                            g_world.size > 1 ? g_world.nccl_id.data() : nullptr, g_world.device, g_world.flags, &e_));
      }
+     // explicit world: used for dry-run (descriptor trace) engines of any rank without touching the
+     // process-wide world set by init_world
+     SimulatorB200(uint64_t seed, int max_local, int max_cluster, int rank, int world_size, int flags)
+     {
+          if (!(flags & HIQ_FLAG_DRY_RUN) && world_size > 1)
+               throw std::runtime_error("SimulatorMPI(rank, world_size, flags): only dry-run engines may name their own world");
+          check(hiq_create(seed, max_local, max_cluster, rank, world_size, nullptr, g_world.device, flags, &e_));
+     }
      ~SimulatorB200() { hiq_destroy(e_); }
      SimulatorB200(const SimulatorB200&) = delete;
 
@@ -175,6 +183,8 @@ public:
           d["allocs_s"] = s.allocs_s;
           d["deallocs_s"] = s.deallocs_s;
           d["swap_bytes_sent"] = s.swap_bytes_sent;
+          d["h2d_bytes"] = s.h2d_bytes;
+          d["d2h_bytes"] = s.d2h_bytes;
           return d;
      }
      py::list trace()
@@ -200,6 +210,23 @@ public:
           return out;
      }
      void clear_trace() { check(hiq_trace_clear(e_)); }
+     py::list collect_timings()
+     {
+          const int cap = 1 << 16;
+          std::vector<double> ms(cap);
+          std::vector<int> kind(cap), k(cap), variant(cap);
+          int n = 0;
+          check(hiq_collect_timings(e_, ms.data(), kind.data(), k.data(), variant.data(), cap, &n));
+          py::list out;
+          for (int i = 0; i < n; ++i) out.append(py::make_tuple(kind[i], k[i], variant[i], ms[i]));
+          return out;
+     }
+     uintptr_t stream_ptr()
+     {
+          void* s = nullptr;
+          check(hiq_stream(e_, &s));
+          return reinterpret_cast<uintptr_t>(s);
+     }
 
 private:
      hiq_engine* e_ = nullptr;
@@ -230,9 +257,12 @@ PYBIND11_MODULE(_cppsim_mpi, m)
      m.def("launch_count", &hiqk_launch_count);
      m.attr("FLAG_DRY_RUN") = HIQ_FLAG_DRY_RUN;
      m.attr("FLAG_TRACE") = HIQ_FLAG_TRACE;
+     m.attr("FLAG_TIMING") = HIQ_FLAG_TIMING;
 
      py::class_<SimulatorB200>(m, "SimulatorMPI")
          .def(py::init<uint64_t, int, int>())
+         .def(py::init<uint64_t, int, int, int, int, int>(), py::arg("seed"), py::arg("max_local"), py::arg("max_cluster_size"),
+              py::arg("rank"), py::arg("world_size"), py::arg("flags"))
          .def("get_qubits_ids", &SimulatorB200::get_qubits_ids)
          .def("get_local_qubits_ids", &SimulatorB200::get_local_qubits_ids)
          .def("get_global_qubits_ids", &SimulatorB200::get_global_qubits_ids)
@@ -257,5 +287,7 @@ PYBIND11_MODULE(_cppsim_mpi, m)
          .def("local_slab_ptr", &SimulatorB200::local_slab_ptr)
          .def("stats", &SimulatorB200::stats)
          .def("trace", &SimulatorB200::trace)
-         .def("clear_trace", &SimulatorB200::clear_trace);
+         .def("clear_trace", &SimulatorB200::clear_trace)
+         .def("collect_timings", &SimulatorB200::collect_timings)
+         .def("stream_ptr", &SimulatorB200::stream_ptr);
 }

@@ -61,6 +61,9 @@ int hiq_device_count(void);
 int hiqk_apply_dense(void* slab, int L, int k, const int* slots, const double* matrix,
                      uint64_t ctrl_mask, int variant, void* stream);
 
+/* The variant HIQK_DENSE_AUTO resolves to for these targets (so callers can label timings). */
+int hiqk_dense_pick_variant(int L, int k, const int* slots);
+
 /* Diagonal k-qubit gate: psi[i] *= diag[d], d = target bits of i gathered in
  * matrix-bit order, where (i & ctrl_mask) == ctrl_mask. `diag` is HOST memory, 2^k complex128.
  * Replaces kernel_core_diag (reference: kernels/intrin/kernels_diag.hpp:35-144). */
@@ -135,6 +138,7 @@ typedef struct hiq_engine hiq_engine;
 
 #define HIQ_FLAG_DRY_RUN 1 /* no device: host logic only, every device op is recorded as a descriptor */
 #define HIQ_FLAG_TRACE 2   /* also record descriptors while executing on the GPU */
+#define HIQ_FLAG_TIMING 4  /* bracket every fused pass / swap with CUDA events on the engine stream */
 
 /* descriptor kinds (what the host hands to the device layer) */
 #define HIQ_DESC_NONE 0
@@ -198,8 +202,15 @@ typedef struct hiq_stats {
      uint64_t dense_passes, diag_passes, scale_passes, skipped_passes;
      double runs_s, swaps_s, measures_s, allocs_s, deallocs_s;
      double swap_bytes_sent;
+     double h2d_bytes, d2h_bytes; /* host<->device traffic issued by the engine (descriptor payloads, results) */
 } hiq_stats;
 int hiq_get_stats(hiq_engine* e, hiq_stats* out);
+
+/* per-pass device times (HIQ_FLAG_TIMING): waits for the stream, then returns and clears the
+ * records since the last call.  kind = HIQ_DESC_*, variant = HIQK_DENSE_* (dense only). */
+int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* variant, int cap, int* n);
+/* cudaStream_t of the engine (for event timing by the caller) */
+int hiq_stream(hiq_engine* e, void** stream);
 
 /* descriptor trace (HIQ_FLAG_DRY_RUN / HIQ_FLAG_TRACE) */
 int hiq_trace_count(hiq_engine* e, int* n);
