@@ -28,6 +28,7 @@ from __future__ import annotations
 
 import argparse
 import copy
+import gc
 import json
 import os
 import statistics
@@ -352,7 +353,8 @@ def main():
     swap_ms = sum(ms for (kind_id, k, variant, ms) in timings if kind_id == 4)
     if swap_ms > 0:
         swap_gbs = (stats1["swap_bytes_sent"] - stats0["swap_bytes_sent"]) / (swap_ms * 1e-3) / 1e9
-    del be, sim
+    del be, sim, ext
+    gc.collect()
     torch.cuda.empty_cache()
 
     # ---- e2e: the full reference-facing pipeline, every step from host inputs to measured bits
@@ -379,7 +381,9 @@ def main():
                 h2d += be2.h2d_bytes
                 d2h += st["d2h_bytes"] + n  # + the measured bits returned to the caller
             e2e_passes = st["dense_passes"] + st["diag_passes"] + st["scale_passes"]
+            be2.main_engine = None  # break the engine<->backend cycle: the 128 GiB slab must go before the next step
             del eng, be2
+            gc.collect()
         tt = torch.tensor([sum(per_step)], dtype=torch.float64, device="cuda")
         ww = torch.tensor([32.0 * (1 << L) * e2e_passes * len(per_step)], dtype=torch.float64, device="cuda")
         if size > 1:

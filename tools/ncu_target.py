@@ -1,0 +1,31 @@
+"""Target for `ncu --set full`: a few launches of the dominant gate kernels over a 2^L slab
+(L=30 by default: 16 GiB, so ncu's save/restore between replay passes stays cheap).
+    ncu --set full --clock-control none --import-source on -k regex:'diag_kernel|dense_direct' \
+        --launch-skip 2 -c 2 -o gpurun_out/r01_full python tools/ncu_target.py
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from hiqsimulator_b200 import kernels as K  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--L", type=int, default=30)
+ap.add_argument("--reps", type=int, default=2)
+args = ap.parse_args()
+L = args.L
+state = torch.full((1 << L,), 2.0 ** (-L / 2), dtype=torch.complex128, device="cuda")
+rng = np.random.default_rng(0)
+z = rng.normal(size=(16, 16)) + 1j * rng.normal(size=(16, 16))
+u4, _ = np.linalg.qr(z)
+d4 = np.exp(1j * rng.uniform(0, 6.28, size=16))
+for _ in range(args.reps):
+    K.apply_diag(state, [3, 9, 17, 25], d4, 0)
+    K.apply_dense(state, [3, 9, 17, 25], u4, 0, K.DIRECT)
+    K.apply_dense(state, [0, 9, 17, 25], u4, 0, K.TILED)
+torch.cuda.synchronize()
+print("ok", K.prob_masked(state))
