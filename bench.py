@@ -253,6 +253,8 @@ def main():
     ap.add_argument("--cpu-qubits", type=int, default=None, help="size of the CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-batch", action="store_true",
+                    help="one launch per fused gate of the plan (HIQ_FLAG_NO_BATCH): no folding of diagonal passes")
     args = ap.parse_args()
 
     os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count() or 1))
@@ -267,7 +269,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device (this engine has no CPU path)")
 
-    rank, size = world.init_world(M.FLAG_TIMING)
+    rank, size = world.init_world(M.FLAG_TIMING | (M.FLAG_NO_BATCH if args.no_batch else 0))
     assert size == args.gpus, "launch with torchrun --nproc-per-node %d (WORLD_SIZE=%d)" % (args.gpus, size)
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
@@ -327,30 +329,41 @@ def main():
     ms_per_step = ms_total / args.steps
 
     # ---- roofline of the dominant kernel (this rank's launches; rank 0 reports)
+    # timings: (kind, k, variant, ms, n_ref) per launch; n_ref = passes of the reference's plan the launch carried
     groups = {}
-    for kind_id, k, variant, ms in timings:
-        groups.setdefault((kind_id, k, variant), []).append(ms)
-    names = {1: "dense", 2: "diag", 3: "scale", 4: "swap"}
+    for kind_id, k, variant, ms, n_ref in timings:
+        folded = kind_id == 1 and n_ref > 1
+        groups.setdefault((kind_id, k if kind_id != 2 else 0, variant, folded), []).append((ms, n_ref))
+    names = {1: "dense", 2: "diag_batch", 3: "scale", 4: "swap"}
     vnames = {0: "", 1: "direct", 2: "tiled", 3: "dmma"}
+
+    def gname(g):
+        if g[0] == 2:
+            return "diag_batch" if not args.no_batch else "diag"
+        return "%s_k%d_%s%s" % (names.get(g[0], "?"), g[1], vnames.get(g[2], ""), "+prediag" if g[3] else "")
     peak, peak_src = measured_peaks()
     gate_groups = {g: v for g, v in groups.items() if g[0] in (1, 2, 3)}
     roofline = None
     breakdown = []
     if gate_groups:
-        dom = max(gate_groups, key=lambda g: sum(gate_groups[g]))
-        mean_ms = statistics.mean(gate_groups[dom])
-        achieved = 32.0 * (1 << L) / (mean_ms * 1e-3) / 1e9
+        tot = lambda v: sum(ms for ms, _ in v)  # noqa: E731
+        dom = max(gate_groups, key=lambda g: tot(gate_groups[g]))
+        mean_ms = tot(gate_groups[dom]) / len(gate_groups[dom])
+        mean_ref = sum(r for _, r in gate_groups[dom]) / len(gate_groups[dom])
+        achieved = 32.0 * (1 << L) / (mean_ms * 1e-3) / 1e9  # bytes one launch moves: ONE pass over the slab
         roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                    "kernel": "%s_k%d_%s" % (names[dom[0]], dom[1], vnames[dom[2]]), "launches": len(gate_groups[dom]),
-                    "mean_launch_ms": mean_ms, "peak_source": peak_src,
-                    "share_of_step": sum(gate_groups[dom]) / max(1e-9, sum(sum(v) for v in groups.values()))}
-        for g, v in sorted(groups.items(), key=lambda kv: -sum(kv[1])):
+                    "kernel": gname(dom), "launches": len(gate_groups[dom]), "mean_launch_ms": mean_ms, "peak_source": peak_src,
+                    "share_of_step": tot(gate_groups[dom]) / max(1e-9, sum(tot(v) for v in groups.values())),
+                    "reference_passes_per_launch": mean_ref, "effective_gbs_per_launch": achieved * mean_ref,
+                    "note": "achieved counts the bytes a launch really moves (32 B x 2^L); a launch that also carries folded "
+                            "diagonal passes of the plan does their work in the same pass (effective = achieved x passes per launch)"}
+        for g, v in sorted(groups.items(), key=lambda kv: -tot(kv[1])):
             per = 32.0 * (1 << L) if g[0] != 4 else 16.0 * (1 << L) * (1 - 2.0 ** -g[1])
-            breakdown.append({"kernel": "%s_k%d_%s" % (names.get(g[0], "?"), g[1], vnames.get(g[2], "")), "launches": len(v),
-                              "total_ms": round(sum(v), 3), "mean_ms": round(statistics.mean(v), 4),
-                              "gbs": round(per / (statistics.mean(v) * 1e-3) / 1e9, 1)})
+            m = tot(v) / len(v)
+            breakdown.append({"kernel": gname(g), "launches": len(v), "reference_passes": sum(r for _, r in v),
+                              "total_ms": round(tot(v), 3), "mean_ms": round(m, 4), "gbs": round(per / (m * 1e-3) / 1e9, 1)})
     swap_gbs = None
-    swap_ms = sum(ms for (kind_id, k, variant, ms) in timings if kind_id == 4)
+    swap_ms = sum(t[3] for t in timings if t[0] == 4)
     if swap_ms > 0:
         swap_gbs = (stats1["swap_bytes_sent"] - stats0["swap_bytes_sent"]) / (swap_ms * 1e-3) / 1e9
     del be, sim, ext
@@ -413,7 +426,11 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": name, "qubits": n, "local_qubits": L, "slab_gib_per_gpu": 16.0 * (1 << L) / 2 ** 30,
-                       "cluster_size": 4, "gates": shape["gates"], "fused_passes": passes, "swaps": shape["swaps"],
+                       "cluster_size": 4, "gates": shape["gates"], "fused_passes": passes,
+                       "hbm_passes_per_step": int(stats1["gate_launches"] - stats0["gate_launches"]) // args.steps,
+                       "batching": "off (one launch per fused gate)" if args.no_batch else
+                                   "diagonal fused gates folded into the next dense launch / batched per pass",
+                       "swaps": shape["swaps"],
                        "swap_qubits": shape["swap_qubits"], "l2_policy": "inputs larger than L2 (slab >> 126 MB), no flush",
                        "timing": "CUDA events on the engine stream, max over ranks"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,

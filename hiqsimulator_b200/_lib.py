@@ -27,6 +27,11 @@ _vp = C.c_void_p
 _ip = C.POINTER(C.c_int)
 _dp = C.POINTER(C.c_double)
 
+class DiagOp(C.Structure):
+    """hiqk_diag_op of include/hiq_b200.h"""
+    _fields_ = [("k", C.c_int), ("slots", C.c_int * 5), ("lut", C.c_double * 64)]
+
+
 _SIGNATURES = {
     "hiq_last_error": (C.c_char_p, []),
     "hiq_version": (C.c_char_p, []),
@@ -34,6 +39,9 @@ _SIGNATURES = {
     "hiqk_apply_dense": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _dp, _u64, C.c_int, _vp]),
     "hiqk_dense_pick_variant": (C.c_int, [C.c_int, C.c_int, _ip]),
     "hiqk_apply_diag": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _dp, _u64, _vp]),
+    "hiqk_apply_diag_batch": (C.c_int, [_vp, C.c_int, C.POINTER(DiagOp), C.c_int, _vp]),
+    "hiqk_apply_dense_prediag": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _dp, C.POINTER(DiagOp), C.c_int, _vp]),
+    "hiqk_dense_prediag_supported": (C.c_int, [C.c_int, C.c_int, _ip]),
     "hiqk_scale": (C.c_int, [_vp, C.c_int, C.c_double, C.c_double, _vp]),
     "hiqk_workspace_bytes": (C.c_size_t, []),
     "hiqk_prob_masked": (C.c_int, [_vp, C.c_int, _u64, _u64, _vp, _vp, _vp]),

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <mutex>
 #include <vector>
 
 #include "hiq_device.cuh"
@@ -88,6 +89,59 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_kernel(const __gri
           double2 in[1 << K];
           load_tuple<K>(in, base, p.off);
           apply_rows<K>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
+     }
+}
+
+// DIRECT with pre-diagonals: psi <- M * (prod_j D_j) * psi in one pass.  Tuples are processed in chunks
+// of THREADS * T consecutive free indices (one CTA iteration): diagonal ops whose slots cannot change
+// inside a chunk collapse into one factor per chunk (diag_hoist); an op with chunk-varying slots costs
+// one lookup + multiply per tuple; an op that overlaps the dense targets costs one per tuple element,
+// selected by (chunk bits | tuple bits | dsel[j][c]).
+constexpr int kPreTuplesPerThread = 8;
+
+template <int K>
+struct DirectPreParams {
+     DirectParams<K> d;
+     uint32_t overlap_mask;                  // bit j: op j touches a dense target
+     uint8_t dsel[kMaxDiagOps][1 << K];      // selector bits of op j contributed by tuple element c
+     DiagBatch pre;
+};
+
+template <int K, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const __grid_constant__ DirectPreParams<K> p)
+{
+     __shared__ double2 lut[kMaxDiagOps][1 << kMaxTargets];
+     __shared__ DiagHoist h;
+     for (int i = threadIdx.x; i < p.pre.n * (1 << kMaxTargets); i += THREADS)
+          lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)] = p.pre.lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)];
+     constexpr uint64_t CH = static_cast<uint64_t>(THREADS) * kPreTuplesPerThread;
+     const uint64_t n_chunks = (p.d.n_free + CH - 1) / CH;
+     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+          diag_hoist(p.pre, lut, insert_zero_bits(chunk * CH, p.d.ins), h);
+          const double2 s_hi = h.s_hi;
+#pragma unroll 1
+          for (int t = 0; t < kPreTuplesPerThread; ++t) {
+               const uint64_t f = chunk * CH + static_cast<uint64_t>(t) * THREADS + threadIdx.x;
+               if (f >= p.d.n_free) break;
+               const uint64_t bidx = insert_zero_bits(f, p.d.ins);
+               double2* base = p.d.psi + bidx;
+               double2 in[1 << K];
+               load_tuple<K>(in, base, p.d.off);
+               double2 s = s_hi;
+               for (int j = 0; j < p.pre.n_lo; ++j) {
+                    const uint32_t sb = h.selh[j] | diag_select_lo(p.pre.slots[j], p.pre.n_lo_slots[j], bidx);
+                    if ((p.overlap_mask >> j) & 1u) {
+#pragma unroll
+                         for (int c = 0; c < (1 << K); ++c) in[c] = cmul(in[c], lut[j][sb | p.dsel[j][c]]);
+                    }
+                    else {
+                         s = cmul(s, lut[j][sb]);
+                    }
+               }
+#pragma unroll
+               for (int c = 0; c < (1 << K); ++c) in[c] = cmul(in[c], s);
+               apply_rows<K>(in, p.d.m, [&](int b, double2 v) { base[p.d.off[b]] = v; });
+          }
      }
 }
 
@@ -297,6 +351,49 @@ static int launch_direct(double2* psi, int L, const int* slots, const double* ma
 }
 
 template <int K>
+static int launch_direct_pre(double2* psi, int L, const int* slots, const double* matrix, const hiqk_diag_op* pre, int n_pre,
+                             cudaStream_t stream)
+{
+     static DirectPreParams<K> p;  // 10+ KB: keep it off the stack; launches are issued from one host thread per engine
+     static std::mutex mu;
+     std::lock_guard<std::mutex> lock(mu);
+     constexpr int THREADS = (K >= 3) ? 128 : 256;
+     constexpr int MINB = 4;
+     constexpr uint64_t CH = static_cast<uint64_t>(THREADS) * kPreTuplesPerThread;
+     p.d.psi = psi;
+     p.d.n_free = 1ull << (L - K);
+     p.d.ctrl_mask = 0;
+     p.d.ins = make_insert_bits(slots, K, 0);
+     fill_common<K>(p.d.off, p.d.m, slots, matrix);
+     uint64_t tmask = 0;
+     for (int t = 0; t < K; ++t) tmask |= 1ull << slots[t];
+     // index bits that change inside one chunk of consecutive free indices
+     const uint64_t varying = insert_zero_bits(CH - 1, p.d.ins);
+     const int rc = make_diag_batch(p.pre, L, pre, n_pre, varying, tmask, "hiqk_apply_dense_prediag");
+     if (rc != HIQ_OK) return rc;
+     p.overlap_mask = 0;
+     std::memset(p.dsel, 0, sizeof(p.dsel));
+     for (int j = 0; j < n_pre; ++j) {
+          bool overlap = false;
+          for (int c = 0; c < (1 << K); ++c) {
+               uint32_t sel = 0;
+               for (int l = 0; l < kMaxTargets; ++l)
+                    for (int t = 0; t < K; ++t)
+                         if (p.pre.slots[j][l] == slots[t] && ((c >> t) & 1)) sel |= 1u << l;
+               p.dsel[j][c] = static_cast<uint8_t>(sel);
+               overlap |= sel != 0;
+          }
+          if (overlap) p.overlap_mask |= 1u << j;
+     }
+     const uint64_t n_chunks = (p.d.n_free + CH - 1) / CH;
+     const uint64_t cap = static_cast<uint64_t>(kNumSMs) * MINB * 4;
+     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap));
+     dense_direct_pre_kernel<K, THREADS, MINB><<<grid, THREADS, 0, stream>>>(p);
+     count_launch();
+     return check_launch("dense_direct_pre_kernel");
+}
+
+template <int K>
 static int launch_tiled(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
                         cudaStream_t stream)
 {
@@ -436,6 +533,36 @@ extern "C" int hiqk_dense_pick_variant(int L, int k, const int* slots)
 {
      if (!slots || k < 1 || k > hiq::kMaxTargets) return HIQK_DENSE_DIRECT;
      return hiq::pick_variant(L, k, slots);
+}
+
+extern "C" int hiqk_dense_prediag_supported(int L, int k, const int* slots)
+{
+     if (!slots || k < 1 || k > 4 || L < k) return 0;
+     return hiq::pick_variant(L, k, slots) == HIQK_DENSE_DIRECT ? 1 : 0;
+}
+
+extern "C" int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slots, const double* matrix,
+                                        const hiqk_diag_op* pre, int n_pre, void* stream)
+{
+     using namespace hiq;
+     if (!slab || !slots || !matrix) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: null argument");
+     if (n_pre == 0) return hiqk_apply_dense(slab, L, k, slots, matrix, 0, HIQK_DENSE_DIRECT, stream);
+     if (!hiqk_dense_prediag_supported(L, k, slots))
+          return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: needs k <= 4 and targets the DIRECT kernel takes");
+     uint64_t tmask = 0;
+     for (int l = 0; l < k; ++l) {
+          if (slots[l] < 0 || slots[l] >= L || ((tmask >> slots[l]) & 1))
+               return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: target slots must be distinct and < L");
+          tmask |= 1ull << slots[l];
+     }
+     double2* psi = static_cast<double2*>(slab);
+     cudaStream_t st = static_cast<cudaStream_t>(stream);
+     switch (k) {
+          case 1: return launch_direct_pre<1>(psi, L, slots, matrix, pre, n_pre, st);
+          case 2: return launch_direct_pre<2>(psi, L, slots, matrix, pre, n_pre, st);
+          case 3: return launch_direct_pre<3>(psi, L, slots, matrix, pre, n_pre, st);
+          default: return launch_direct_pre<4>(psi, L, slots, matrix, pre, n_pre, st);
+     }
 }
 
 extern "C" int hiqk_apply_dense(void* slab, int L, int k, const int* slots, const double* matrix,

@@ -230,10 +230,11 @@ int hiq_get_stats(hiq_engine* e, hiq_stats* out)
      out->swap_bytes_sent = s.swap_bytes_sent;
      out->h2d_bytes = s.h2d_bytes;
      out->d2h_bytes = s.d2h_bytes;
+     out->gate_launches = s.gate_launches;
      return HIQ_OK;
 }
 
-int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* variant, int cap, int* n)
+int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* variant, int* n_ref, int cap, int* n)
 {
      NEED(e);
      return guarded([&] {
@@ -245,6 +246,7 @@ int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* varia
                kind[i] = t[i].kind;
                k[i] = t[i].k;
                variant[i] = t[i].variant;
+               if (n_ref) n_ref[i] = t[i].n_ref;
           }
      });
 }

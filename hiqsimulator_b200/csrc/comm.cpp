@@ -1,6 +1,8 @@
 #include "comm.hpp"
 
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 
 #include "hiq_host.hpp"
@@ -46,6 +48,24 @@ int Comm::init(int rank, int world_size, const void* unique_id, int device)
      HIQ_NCCL(nccl().CommInitRank(&comm_, world_size, id, rank));
      HIQ_CUDA(cudaMalloc(&stage_, kStageBytes));
      return HIQ_OK;
+}
+
+Comm* Comm::shared(int rank, int world_size, const void* unique_id, int device)
+{
+     static std::mutex mu;
+     static auto* cache = new std::map<std::string, Comm*>();  // intentionally leaked: outlives CUDA teardown order issues
+     std::lock_guard<std::mutex> lock(mu);
+     std::string key = world_size > 1 && unique_id ? std::string(static_cast<const char*>(unique_id), 128) : std::string("single");
+     key += ":" + std::to_string(rank) + ":" + std::to_string(world_size) + ":" + std::to_string(device);
+     auto it = cache->find(key);
+     if (it != cache->end()) return it->second;
+     Comm* c = new Comm();
+     if (c->init(rank, world_size, unique_id, device) != HIQ_OK) {
+          delete c;
+          return nullptr;
+     }
+     (*cache)[key] = c;
+     return c;
 }
 
 int Comm::allreduce_sum(double* vals, int n, cudaStream_t stream)

@@ -23,6 +23,12 @@ public:
      // rank 0 obtained from hiq_comm_unique_id() (the launcher distributes it).
      int init(int rank, int world_size, const void* unique_id, int device);
 
+     // One communicator per process and unique id: an NCCL id can bootstrap exactly one communicator,
+     // while a process may create many engines over its lifetime (every SimulatorMPI(...) of the
+     // caller).  Returns the cached communicator of (id, rank) or creates it; never destroyed before
+     // process exit (the reference's MPI world has the same lifetime).  Null + error on failure.
+     static Comm* shared(int rank, int world_size, const void* unique_id, int device);
+
      int rank() const { return rank_; }
      int size() const { return size_; }
      ncclComm_t handle() const { return comm_; }

@@ -52,7 +52,8 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
       device_(device),
       dry_run_(flags & HIQ_FLAG_DRY_RUN),
       tracing_(flags & (HIQ_FLAG_TRACE | HIQ_FLAG_DRY_RUN)),
-      timing_((flags & HIQ_FLAG_TIMING) && !(flags & HIQ_FLAG_DRY_RUN))
+      timing_((flags & HIQ_FLAG_TIMING) && !(flags & HIQ_FLAG_DRY_RUN)),
+      batching_(!(flags & HIQ_FLAG_NO_BATCH))
 {
      if (world_size < 1 || (world_size & (world_size - 1)) || rank < 0 || rank >= world_size)
           fail("ctor(): world size must be a power of two and 0 <= rank < world size");
@@ -69,7 +70,8 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
           cu(slab_.init(device_, 1ull << max_local_));
           cu(check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           cu(check_cuda(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
-          cu(comm_.init(rank, world_size, nccl_id, device_));
+          comm_p_ = Comm::shared(rank, world_size, nccl_id, device_);
+          if (!comm_p_) throw EngineError(HIQ_ERR_CUDA, hiq_last_error());
           cu(check_cuda(cudaMalloc(&workspace_, hiqk_workspace_bytes()), "cudaMalloc workspace"));
           cu(check_cuda(cudaMalloc(&d_vals_, 64 * sizeof(double)), "cudaMalloc"));
           cu(slab_.ensure(1));
@@ -100,7 +102,9 @@ Engine::~Engine()
 
 void Engine::synchronize()
 {
-     if (!dry_run_) cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
+     if (dry_run_) return;
+     flush_pending();
+     cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
 }
 
 size_t Engine::find(const std::vector<Index>& v, Index val) const
@@ -138,6 +142,7 @@ void Engine::allocate_local(Index id)
           trace_.push_back(d);
      }
      if (dry_run_) return;
+     flush_pending();
      cu(slab_.ensure(2 * old));
      cu(check_cuda(cudaMemsetAsync(slab_.data() + old, 0, old * sizeof(double2), stream_), "cudaMemsetAsync"));
 }
@@ -190,12 +195,13 @@ void Engine::ensure_scratch()
 void Engine::deallocate_local(Index id)
 {
      need_device("DeallocateLocalQubit()");
+     flush_pending();
      const size_t pos = find_sure(locals_, id);
      const int L = static_cast<int>(locals_.size());
      double sums[2];
      cu(hiqk_bit_norms(slab_.data(), L, static_cast<int>(pos), d_vals_, workspace_, stream_));
      d2h(sums, d_vals_, sizeof(sums));
-     cu(comm_.allreduce_sum(sums, 2, stream_));
+     cu(comm_p_->allreduce_sum(sums, 2, stream_));
      if (!((sums[0] > max_float_error_) ^ (sums[1] > max_float_error_)))
           fail("DeallocateLocalQubit(): qubit " + std::to_string(id) + " is entangled");
      const int keep = sums[0] > max_float_error_ ? 0 : 1;
@@ -207,6 +213,7 @@ void Engine::deallocate_local(Index id)
 void Engine::deallocate_global(Index id)
 {
      need_device("DeallocateGlobalQubit()");
+     flush_pending();
      const size_t pos = find_sure(globals_, id);
      const int L = static_cast<int>(locals_.size());
      double local_norm = 0.0;
@@ -214,7 +221,7 @@ void Engine::deallocate_global(Index id)
      d2h(&local_norm, d_vals_, sizeof(double));
      double sums[2] = {0.0, 0.0};
      sums[(rank_ >> pos) & 1] = local_norm;
-     cu(comm_.allreduce_sum(sums, 2, stream_));
+     cu(comm_p_->allreduce_sum(sums, 2, stream_));
      if (!((sums[0] > max_float_error_) ^ (sums[1] > max_float_error_)))
           fail("DeallocateGlobalQubit(): qubit " + std::to_string(id) + " is entangled");
      if (sums[1] > max_float_error_) {
@@ -323,7 +330,7 @@ std::vector<Engine::PassTime> Engine::collect_timings()
      for (auto& t: timed_) {
           float ms = 0.f;
           cudaEventElapsedTime(&ms, t.start, t.stop);
-          out.push_back({t.kind, t.k, t.variant, static_cast<double>(ms)});
+          out.push_back({t.kind, t.k, t.variant, t.n_ref, static_cast<double>(ms)});
           event_pool_.push_back(t.start);
           event_pool_.push_back(t.stop);
      }
@@ -333,6 +340,7 @@ std::vector<Engine::PassTime> Engine::collect_timings()
 
 void Engine::d2h(void* dst, const void* src, size_t bytes)
 {
+     flush_pending();
      cu(check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
      synchronize();
      stats_.d2h_bytes += static_cast<double>(bytes);
@@ -343,19 +351,106 @@ void Engine::execute(const Descriptor& d)
      if (tracing_) trace_.push_back(d);
      if (dry_run_) return;
      const int L = static_cast<int>(locals_.size());
+     stats_.h2d_bytes += static_cast<double>(d.payload.size() * sizeof(cplx));
      int variant = 0;
      if (d.kind == HIQ_DESC_DENSE) variant = dense_variant_ ? dense_variant_ : hiqk_dense_pick_variant(L, d.k, d.slots);
-     TimedPass tp{d.kind, d.k, variant, nullptr, nullptr};
+     if (batching_) {
+          // diagonal passes of the plan are deferred: they ride along the next dense launch or go out
+          // as one batched pass at the next observation of the slab
+          if ((d.kind == HIQ_DESC_DIAG || d.kind == HIQ_DESC_SCALE) && d.ctrl_mask == 0) {
+               queue_diagonal(d);
+               return;
+          }
+          if (d.kind == HIQ_DESC_DENSE && d.ctrl_mask == 0 && !pending_.empty() && variant == HIQK_DENSE_DIRECT &&
+              hiqk_dense_prediag_supported(L, d.k, d.slots)) {
+               flush_pending(HIQK_MAX_DIAG_OPS);
+               launch(d, variant, static_cast<int>(pending_.size()));
+               return;
+          }
+     }
+     flush_pending();
+     launch(d, variant, 0);
+}
+
+void Engine::queue_diagonal(const Descriptor& d)
+{
+     hiqk_diag_op op;
+     std::memset(&op, 0, sizeof(op));
+     op.k = d.kind == HIQ_DESC_SCALE ? 0 : d.k;
+     for (int l = 0; l < op.k; ++l) op.slots[l] = d.slots[l];
+     std::memcpy(op.lut, d.payload.data(), sizeof(cplx) << op.k);
+     // host-side merge: an op over the same slot set as a pending one (or a global scalar) is folded
+     // into that op's table instead of costing another lookup per amplitude
+     for (size_t i = 0; i < pending_.size(); ++i) {
+          hiqk_diag_op& q = pending_[i];
+          uint64_t mq = 0, mo = 0;
+          for (int l = 0; l < q.k; ++l) mq |= 1ull << q.slots[l];
+          for (int l = 0; l < op.k; ++l) mo |= 1ull << op.slots[l];
+          if ((mo & ~mq) != 0) continue;  // op's slots must be a subset of q's
+          cplx* ql = reinterpret_cast<cplx*>(q.lut);
+          const cplx* ol = reinterpret_cast<const cplx*>(op.lut);
+          for (int e = 0; e < (1 << q.k); ++e) {
+               int sel = 0;
+               for (int l = 0; l < op.k; ++l)
+                    for (int m = 0; m < q.k; ++m)
+                         if (q.slots[m] == op.slots[l] && ((e >> m) & 1)) sel |= 1 << l;
+               ql[e] *= ol[sel];
+          }
+          ++pending_ref_[i];
+          return;
+     }
+     pending_.push_back(op);
+     pending_ref_.push_back(1);
+}
+
+void Engine::flush_pending(size_t keep)
+{
+     // batched diagonal launches (full batches first) until at most `keep` ops remain queued
+     if (dry_run_) return;
+     while (pending_.size() > keep) {
+          const size_t take = std::min<size_t>(pending_.size(), HIQK_MAX_DIAG_OPS);
+          int n_ref = 0;
+          for (size_t i = 0; i < take; ++i) n_ref += pending_ref_[i];
+          TimedPass tp{HIQ_DESC_DIAG, static_cast<int>(take), 0, n_ref, nullptr, nullptr};
+          if (timing_) {
+               tp.start = take_event();
+               tp.stop = take_event();
+               cudaEventRecord(tp.start, stream_);
+          }
+          cu(hiqk_apply_diag_batch(slab_.data(), static_cast<int>(locals_.size()), pending_.data(), static_cast<int>(take), stream_));
+          ++stats_.gate_launches;
+          if (timing_) {
+               cudaEventRecord(tp.stop, stream_);
+               timed_.push_back(tp);
+          }
+          pending_.erase(pending_.begin(), pending_.begin() + take);
+          pending_ref_.erase(pending_ref_.begin(), pending_ref_.begin() + take);
+     }
+}
+
+void Engine::launch(const Descriptor& d, int variant, int n_pre)
+{
+     const int L = static_cast<int>(locals_.size());
+     int n_ref = 1;
+     for (int i = 0; i < n_pre; ++i) n_ref += pending_ref_[i];
+     TimedPass tp{d.kind, d.k, variant, n_ref, nullptr, nullptr};
      if (timing_) {
           tp.start = take_event();
           tp.stop = take_event();
           cudaEventRecord(tp.start, stream_);
      }
-     stats_.h2d_bytes += static_cast<double>(d.payload.size() * sizeof(cplx));
      switch (d.kind) {
           case HIQ_DESC_DENSE:
-               cu(hiqk_apply_dense(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()), d.ctrl_mask,
-                                   variant, stream_));
+               if (n_pre > 0) {
+                    cu(hiqk_apply_dense_prediag(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()),
+                                                pending_.data(), n_pre, stream_));
+                    pending_.clear();
+                    pending_ref_.clear();
+               }
+               else {
+                    cu(hiqk_apply_dense(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()),
+                                        d.ctrl_mask, variant, stream_));
+               }
                break;
           case HIQ_DESC_DIAG:
                cu(hiqk_apply_diag(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()), d.ctrl_mask,
@@ -364,6 +459,7 @@ void Engine::execute(const Descriptor& d)
           case HIQ_DESC_SCALE: cu(hiqk_scale(slab_.data(), L, d.payload[0].real(), d.payload[0].imag(), stream_)); break;
           default: break;
      }
+     ++stats_.gate_launches;
      if (timing_) {
           cudaEventRecord(tp.stop, stream_);
           timed_.push_back(tp);
@@ -435,11 +531,12 @@ double Engine::probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint6
 {
      // reference: SimulatorMPI.cpp:841-870
      double p = 0.0;
+     flush_pending();
      if ((static_cast<uint64_t>(rank_) & gm) == gv) {
           cu(hiqk_prob_masked(slab_.data(), static_cast<int>(locals_.size()), lm, lv, d_vals_, workspace_, stream_));
           d2h(&p, d_vals_, sizeof(double));
      }
-     cu(comm_.allreduce_sum(&p, 1, stream_));
+     cu(comm_p_->allreduce_sum(&p, 1, stream_));
      return p;
 }
 
@@ -447,6 +544,7 @@ void Engine::normalize(double norm, uint64_t lm, uint64_t lv, uint64_t gm, uint6
 {
      // reference: SimulatorMPI.cpp:872-895
      const int L = static_cast<int>(locals_.size());
+     flush_pending();
      if ((static_cast<uint64_t>(rank_) & gm) != gv)
           cu(check_cuda(cudaMemsetAsync(slab_.data(), 0, sizeof(double2) << L, stream_), "cudaMemsetAsync"));
      else
@@ -486,7 +584,7 @@ cplx Engine::get_amplitude(const std::vector<bool>& bits, const std::vector<Inde
      if (static_cast<uint64_t>(rank_) == owner) {
           d2h(&value, slab_.data() + num, sizeof(cplx));
      }
-     cu(comm_.broadcast_bytes(&value, sizeof(value), static_cast<int>(owner), stream_));
+     cu(comm_p_->broadcast_bytes(&value, sizeof(value), static_cast<int>(owner), stream_));
      return value;
 }
 
@@ -506,13 +604,14 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
 {
      // two-level inverse-CDF sampling of the reference (SimulatorMPI.cpp:897-1008)
      need_device("MeasureQubits()");
+     flush_pending();
      const auto t0 = Clock::now();
      const int L = static_cast<int>(locals_.size());
      const uint64_t size = 1ull << L;
      const uint64_t n = std::min(size, kMaxBlocks);
      if (!d_blocks_) cu(check_cuda(cudaMalloc(&d_blocks_, sizeof(double) * kMaxBlocks * world_), "cudaMalloc blocks"));
      cu(hiqk_block_norms(slab_.data(), L, n, d_blocks_ + n * rank_, stream_));
-     cu(comm_.allgather(d_blocks_ + n * rank_, d_blocks_, n, stream_));
+     cu(comm_p_->allgather(d_blocks_ + n * rank_, d_blocks_, n, stream_));
      std::vector<double> tot(n * world_);
      d2h(tot.data(), d_blocks_, sizeof(double) * tot.size());
      // per-rank inclusive prefix, then the running shift over ranks — same order as the reference
@@ -547,7 +646,7 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
           }
      }
      uint64_t res_index = (src_rank << L) + k;
-     cu(comm_.broadcast_bytes(&res_index, sizeof(res_index), static_cast<int>(src_rank), stream_));
+     cu(comm_p_->broadcast_bytes(&res_index, sizeof(res_index), static_cast<int>(src_rank), stream_));
 
      std::vector<bool> res(ids.size());
      uint64_t lm = 0, lv = 0, gm = 0, gv = 0;
@@ -578,10 +677,11 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
 double Engine::entropy()
 {
      need_device("Entropy()");
+     flush_pending();
      double e = 0.0;
      cu(hiqk_entropy(slab_.data(), static_cast<int>(locals_.size()), d_vals_, workspace_, stream_));
      d2h(&e, d_vals_, sizeof(double));
-     cu(comm_.allreduce_sum(&e, 1, stream_));
+     cu(comm_p_->allreduce_sum(&e, 1, stream_));
      return -e;
 }
 
@@ -622,6 +722,8 @@ void Engine::copy_slab_from_host(const void* src, uint64_t n_amps)
 {
      need_device("set_local_slab()");
      if (n_amps != (1ull << locals_.size())) fail("set_local_slab(): size must equal 2^(local qubits)");
+     pending_.clear();  // the whole slab is overwritten
+     pending_ref_.clear();
      cu(check_cuda(cudaMemcpyAsync(slab_.data(), src, n_amps * sizeof(double2), cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync"));
      synchronize();
      stats_.h2d_bytes += static_cast<double>(n_amps * sizeof(double2));
@@ -664,7 +766,8 @@ void Engine::swap_qubits(const std::vector<Index>& pairs)
           trace_.push_back(d);
      }
      if (!dry_run_ && !gpos.empty()) {
-          TimedPass tp{HIQ_DESC_SWAP, static_cast<int>(gpos.size()), 0, nullptr, nullptr};
+          flush_pending();
+          TimedPass tp{HIQ_DESC_SWAP, static_cast<int>(gpos.size()), 0, 0, nullptr, nullptr};
           if (timing_) {
                tp.start = take_event();
                tp.stop = take_event();
@@ -722,8 +825,8 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
                cu(hiqk_swap_pack(slab_.data(), L, q, slots.data(), peers[i].pat, begin, cnt, send + i * piece, stream_));
           nccl().GroupStart();
           for (int i = 0; i < n_peers; ++i) {
-               nccl().Send(send + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_.handle(), stream_);
-               nccl().Recv(recv + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_.handle(), stream_);
+               nccl().Send(send + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_p_->handle(), stream_);
+               nccl().Recv(recv + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_p_->handle(), stream_);
           }
           ncclResult_t r = nccl().GroupEnd();
           if (r != ncclSuccess) throw EngineError(HIQ_ERR_CUDA, std::string("ncclGroupEnd: ") + nccl().GetErrorString(r));

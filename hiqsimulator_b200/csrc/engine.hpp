@@ -16,6 +16,7 @@
 #include <string>
 #include <vector>
 
+#include "../../include/hiq_b200.h"
 #include "comm.hpp"
 #include "fusion.hpp"
 #include "slab.hpp"
@@ -43,6 +44,7 @@ struct EngineStats {
      double runs_s = 0, swaps_s = 0, measures_s = 0, allocs_s = 0, deallocs_s = 0;
      double swap_bytes_sent = 0;
      double h2d_bytes = 0, d2h_bytes = 0;
+     uint64_t gate_launches = 0;  // device launches that carried the dense/diag/scale passes above
 };
 
 class Engine {
@@ -72,7 +74,11 @@ public:
      // copy the local slab to host memory (complex128, 2^L amplitudes)
      void copy_slab_to_host(void* dst, uint64_t cap_amps);
      void copy_slab_from_host(const void* src, uint64_t n_amps);
-     double2* slab_ptr() const { return slab_.data(); }
+     double2* slab_ptr()
+     {
+          flush_pending();  // the caller is about to look at the amplitudes
+          return slab_.data();
+     }
      int local_qubits() const { return static_cast<int>(locals_.size()); }
      void synchronize();
 
@@ -83,6 +89,7 @@ public:
      const EngineStats& stats() const { return stats_; }
      struct PassTime {
           int kind, k, variant;
+          int n_ref;  // fused-gate passes of the reference's plan carried by this launch
           double ms;
      };
      std::vector<PassTime> collect_timings();
@@ -112,19 +119,22 @@ private:
      double probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
      void normalize(double norm, uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
      void execute(const Descriptor& d);
+     void launch(const Descriptor& d, int variant, int n_pre);
+     void queue_diagonal(const Descriptor& d);
+     void flush_pending(size_t keep = 0);
      void ensure_scratch();
 
      const double max_float_error_ = 1e-12;
      size_t min_local_, max_local_, max_global_, max_cluster_;
      int rank_, world_, device_;
-     bool dry_run_, tracing_, timing_;
+     bool dry_run_, tracing_, timing_, batching_;
      std::vector<Index> locals_, globals_;
      FusionAccumulator fused_;
      std::mt19937 rnd_eng_;
      std::function<double()> rng_;
 
      Slab slab_;
-     Comm comm_;
+     Comm* comm_p_ = nullptr;  // process-wide communicator (Comm::shared), not owned
      cudaStream_t stream_ = nullptr;
      cudaStream_t comm_stream_ = nullptr;
      void* workspace_ = nullptr;  // reduction partials
@@ -137,9 +147,14 @@ private:
      EngineStats stats_;
      std::vector<Descriptor> trace_;
      struct TimedPass {
-          int kind, k, variant;
+          int kind, k, variant, n_ref;
           cudaEvent_t start, stop;
      };
+     // Diagonal fused gates wait here until the next dense launch (which applies them to the tuples
+     // it loads) or the next observation of the slab (one batched pass).  ref_passes[i] = how many
+     // passes of the reference's plan op i stands for (ops over the same slots are multiplied on the host).
+     std::vector<hiqk_diag_op> pending_;
+     std::vector<int> pending_ref_;
      std::vector<TimedPass> timed_;
      std::vector<cudaEvent_t> event_pool_;
      cudaEvent_t take_event();

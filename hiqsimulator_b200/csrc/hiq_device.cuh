@@ -41,6 +41,74 @@ __device__ __forceinline__ double2 cmul(const double2 a, const double2 b)
 
 __device__ __forceinline__ double norm2(const double2 a) { return fma(a.x, a.x, a.y * a.y); }
 
+// ---------------------------------------------------------------------------------------------
+// Batched diagonal factors.  Consecutive diagonal fused gates of the reference's plan (each one
+// would be a full pass of kernel_core_diag, reference: kernels/intrin/kernels_diag.hpp:35-144)
+// commute with every index permutation and compose by multiplication, so a launch can apply up
+// to kMaxDiagOps of them in ONE pass over HBM: psi[i] *= prod_j lut_j[bits of i at slots_j].
+// The same structure rides along a dense launch as "pre-diagonals" applied to the loaded tuple.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxDiagOps = 16;
+
+// Work is cut into *chunks* of consecutive indices (one CTA iteration each).  A slot whose index
+// bit cannot change inside a chunk is "chunk-constant": its selector bits are computed once per
+// chunk by one warp; an op made only of such slots collapses into a single per-chunk factor.
+struct DiagBatch {
+     int n;                               // ops in use
+     int n_lo;                            // ops [0, n_lo) need per-element work, ops [n_lo, n) are chunk-constant
+     uint8_t n_lo_slots[kMaxDiagOps];     // leading entries of slots[j] that vary inside a chunk
+     uint8_t slots[kMaxDiagOps][8];       // reordered: chunk-varying slots first; unused entries = 63 (always-0 bit)
+     double2 lut[kMaxDiagOps][1 << kMaxTargets];  // permuted to the reordered slots
+};
+
+// selector of an op for index idx (bit l of the selector = bit slots[l] of idx)
+__device__ __forceinline__ uint32_t diag_select(const uint8_t (&slots)[8], uint64_t idx)
+{
+     uint32_t sel = 0;
+#pragma unroll
+     for (int l = 0; l < kMaxTargets; ++l) sel |= static_cast<uint32_t>((idx >> slots[l]) & 1ull) << l;
+     return sel;
+}
+
+// selector bits contributed by the n_lo leading (chunk-varying) slots
+__device__ __forceinline__ uint32_t diag_select_lo(const uint8_t (&slots)[8], int n_lo, uint64_t idx)
+{
+     uint32_t sel = 0;
+     for (int l = 0; l < n_lo; ++l) sel |= static_cast<uint32_t>((idx >> slots[l]) & 1ull) << l;
+     return sel;
+}
+
+struct DiagHoist {
+     double2 s_hi;                  // product of the chunk-constant ops
+     uint32_t selh[kMaxDiagOps];    // chunk-constant selector bits of every op
+};
+
+// Once per chunk (all threads of the CTA call it): selectors at the chunk's base index, then the
+// product of the chunk-constant factors by a shuffle tree in warp 0.
+__device__ __forceinline__ void diag_hoist(const DiagBatch& b, const double2 (*lut)[1 << kMaxTargets], uint64_t chunk_base_idx,
+                                           DiagHoist& h)
+{
+     __syncthreads();  // readers of the previous chunk's values are done
+     if (threadIdx.x < 32) {
+          const int j = threadIdx.x;
+          double2 f = make_double2(1.0, 0.0);
+          if (j < b.n) {
+               const uint32_t sel = diag_select(b.slots[j], chunk_base_idx);
+               h.selh[j] = sel;
+               if (j >= b.n_lo) f = lut[j][sel];
+          }
+#pragma unroll
+          for (int o = kMaxDiagOps / 2; o > 0; o >>= 1) {
+               double2 g;
+               g.x = __shfl_xor_sync(0xffffffffu, f.x, o);
+               g.y = __shfl_xor_sync(0xffffffffu, f.y, o);
+               f = cmul(f, g);
+          }
+          if (j == 0) h.s_hi = f;
+     }
+     __syncthreads();
+}
+
 // 128-bit global accesses. Slabs are streamed once per pass: the loads skip L1
 // allocation, the stores are plain (L2 merges the sectors before eviction).
 __device__ __forceinline__ double2 ldg_stream(const double2* p)

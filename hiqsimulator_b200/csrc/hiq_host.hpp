@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <cstdint>
 #include <string>
 
 #include "../../include/hiq_b200.h"
@@ -14,6 +15,11 @@ int set_error(int code, const std::string& msg);
 int check_launch(const char* what);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch(unsigned n = 1);
+
+struct DiagBatch;
+// hiqk_diag_op[] (host, validated) -> kernel-side batch; defined in stream_kernels.cu
+int make_diag_batch(DiagBatch& b, int L, const hiqk_diag_op* ops, int n_ops, uint64_t varying_mask, uint64_t force_lo_mask,
+                    const char* who);
 
 #define HIQ_CUDA(call)                                          \
      do {                                                       \

@@ -185,6 +185,7 @@ public:
           d["swap_bytes_sent"] = s.swap_bytes_sent;
           d["h2d_bytes"] = s.h2d_bytes;
           d["d2h_bytes"] = s.d2h_bytes;
+          d["gate_launches"] = s.gate_launches;
           return d;
      }
      py::list trace()
@@ -214,11 +215,11 @@ public:
      {
           const int cap = 1 << 16;
           std::vector<double> ms(cap);
-          std::vector<int> kind(cap), k(cap), variant(cap);
+          std::vector<int> kind(cap), k(cap), variant(cap), n_ref(cap);
           int n = 0;
-          check(hiq_collect_timings(e_, ms.data(), kind.data(), k.data(), variant.data(), cap, &n));
+          check(hiq_collect_timings(e_, ms.data(), kind.data(), k.data(), variant.data(), n_ref.data(), cap, &n));
           py::list out;
-          for (int i = 0; i < n; ++i) out.append(py::make_tuple(kind[i], k[i], variant[i], ms[i]));
+          for (int i = 0; i < n; ++i) out.append(py::make_tuple(kind[i], k[i], variant[i], ms[i], n_ref[i]));
           return out;
      }
      uintptr_t stream_ptr()
@@ -258,6 +259,7 @@ PYBIND11_MODULE(_cppsim_mpi, m)
      m.attr("FLAG_DRY_RUN") = HIQ_FLAG_DRY_RUN;
      m.attr("FLAG_TRACE") = HIQ_FLAG_TRACE;
      m.attr("FLAG_TIMING") = HIQ_FLAG_TIMING;
+     m.attr("FLAG_NO_BATCH") = HIQ_FLAG_NO_BATCH;
 
      py::class_<SimulatorB200>(m, "SimulatorMPI")
          .def(py::init<uint64_t, int, int>())

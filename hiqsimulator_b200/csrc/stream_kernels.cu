@@ -3,7 +3,9 @@
 // pack/unpack halves of the global<->local qubit swap.  Each launcher cites the reference code it
 // replaces; all of them are one pass over (part of) the local slab with 128-bit accesses.
 #include <algorithm>
+#include <complex>
 #include <cstring>
+#include <string>
 #include <vector>
 
 #include "hiq_device.cuh"
@@ -11,6 +13,7 @@
 
 namespace hiq {
 
+using cplx = std::complex<double>;
 constexpr int kStreamThreads = 256;
 constexpr int kMaxPartials = 8192;  // per-CTA partial sums (x2 for bit_norms)
 
@@ -63,6 +66,47 @@ __global__ void __launch_bounds__(kStreamThreads) diag_kernel(const __grid_const
           int sel = 0;
           for (int l = 0; l < p.k; ++l) sel |= static_cast<int>((idx >> p.slots[l]) & 1ull) << l;
           p.psi[idx] = cmul(p.psi[idx], lut[sel]);
+     }
+}
+
+// ----------------------------------------------------------------------------- batched diagonal gates
+// One HBM pass for up to kMaxDiagOps diagonal fused gates (see DiagBatch in hiq_device.cuh).
+// A CTA iteration covers kDiagChunk consecutive amplitudes; ops whose slots all lie above the chunk
+// cost one factor per chunk, the others one lookup + one complex multiply per amplitude.
+constexpr int kDiagPerThread = 16;
+constexpr uint64_t kDiagChunk = static_cast<uint64_t>(kStreamThreads) * kDiagPerThread;
+
+__global__ void __launch_bounds__(kStreamThreads, 4) diag_batch_kernel(const __grid_constant__ DiagBatch b, double2* psi, uint64_t n)
+{
+     __shared__ double2 lut[kMaxDiagOps][1 << kMaxTargets];
+     __shared__ DiagHoist h;
+     for (int i = threadIdx.x; i < b.n * (1 << kMaxTargets); i += kStreamThreads)
+          lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)] = b.lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)];
+     const uint64_t n_chunks = (n + kDiagChunk - 1) / kDiagChunk;
+     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+          const uint64_t base = chunk * kDiagChunk;
+          diag_hoist(b, lut, base, h);  // also orders the LUT fill before its first use
+          const double2 s_hi = h.s_hi;
+#pragma unroll 1
+          for (int u0 = 0; u0 < kDiagPerThread; u0 += 4) {
+               uint64_t idx[4];
+               double2 v[4], f[4];
+#pragma unroll
+               for (int u = 0; u < 4; ++u) {
+                    idx[u] = base + static_cast<uint64_t>(u0 + u) * kStreamThreads + threadIdx.x;
+                    if (idx[u] < n) v[u] = ldg_stream(psi + idx[u]);
+                    f[u] = s_hi;
+               }
+               for (int j = 0; j < b.n_lo; ++j) {
+                    const uint32_t sh = h.selh[j];
+                    const int nl = b.n_lo_slots[j];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) f[u] = cmul(f[u], lut[j][sh | diag_select_lo(b.slots[j], nl, idx[u])]);
+               }
+#pragma unroll
+               for (int u = 0; u < 4; ++u)
+                    if (idx[u] < n) psi[idx[u]] = cmul(v[u], f[u]);
+          }
      }
 }
 
@@ -282,6 +326,83 @@ extern "C" int hiqk_apply_diag(void* slab, int L, int k, const int* slots, const
      diag_kernel<<<stream_grid(p.n_free), kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
      count_launch();
      return check_launch("diag_kernel");
+}
+
+// Validates `ops` and builds the kernel-side batch (shared with the dense pre-diagonal launcher).
+// varying_mask: index bits that change inside one chunk of the calling kernel; force_lo_mask: slots
+// that must be treated per element regardless (the dense targets).
+int hiq::make_diag_batch(DiagBatch& b, int L, const hiqk_diag_op* ops, int n_ops, uint64_t varying_mask, uint64_t force_lo_mask,
+                         const char* who)
+{
+     if (!ops || n_ops < 1 || n_ops > kMaxDiagOps)
+          return set_error(HIQ_ERR_ARG, std::string(who) + ": need 1.." + std::to_string(kMaxDiagOps) + " diagonal ops");
+     std::memset(&b, 0, sizeof(b));
+     b.n = n_ops;
+     struct Tmp {
+          int k, n_lo;
+          int slots[kMaxTargets];
+          cplx lut[1 << kMaxTargets];
+          bool per_element;
+     };
+     std::vector<Tmp> tmp(n_ops);
+     for (int j = 0; j < n_ops; ++j) {
+          const hiqk_diag_op& o = ops[j];
+          if (o.k < 0 || o.k > kMaxTargets) return set_error(HIQ_ERR_ARG, std::string(who) + ": diagonal op with k outside 0..5");
+          uint64_t seen = 0;
+          for (int l = 0; l < o.k; ++l) {
+               if (o.slots[l] < 0 || o.slots[l] >= L || ((seen >> o.slots[l]) & 1))
+                    return set_error(HIQ_ERR_ARG, std::string(who) + ": diagonal op slots must be distinct and < L");
+               seen |= 1ull << o.slots[l];
+          }
+          // new slot order: chunk-varying slots (ascending) first, then the rest (ascending)
+          Tmp& t = tmp[j];
+          t.k = o.k;
+          std::vector<int> order(o.k);
+          for (int l = 0; l < o.k; ++l) order[l] = l;
+          auto is_lo = [&](int l) { return ((varying_mask >> o.slots[l]) & 1ull) != 0; };
+          std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
+               if (is_lo(a) != is_lo(c)) return is_lo(a);
+               return o.slots[a] < o.slots[c];
+          });
+          t.n_lo = 0;
+          for (int l = 0; l < o.k; ++l) {
+               t.slots[l] = o.slots[order[l]];
+               t.n_lo += is_lo(order[l]) ? 1 : 0;
+          }
+          const cplx* src = reinterpret_cast<const cplx*>(o.lut);
+          for (int e = 0; e < (1 << o.k); ++e) {
+               int old = 0;
+               for (int l = 0; l < o.k; ++l)
+                    if ((e >> l) & 1) old |= 1 << order[l];
+               t.lut[e] = src[old];
+          }
+          t.per_element = t.n_lo > 0 || (seen & force_lo_mask) != 0;
+     }
+     // per-element ops first
+     std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp& a, const Tmp& c) { return a.per_element && !c.per_element; });
+     for (int j = 0; j < n_ops; ++j) {
+          const Tmp& t = tmp[j];
+          if (t.per_element) b.n_lo = j + 1;
+          b.n_lo_slots[j] = static_cast<uint8_t>(t.n_lo);
+          for (int l = 0; l < 8; ++l) b.slots[j][l] = l < t.k ? static_cast<uint8_t>(t.slots[l]) : 63;  // bit 63 is always 0
+          // entries beyond 2^k are never selected (their selector bits read as 0)
+          std::memcpy(b.lut[j], t.lut, sizeof(cplx) << t.k);
+     }
+     return HIQ_OK;
+}
+
+extern "C" int hiqk_apply_diag_batch(void* slab, int L, const hiqk_diag_op* ops, int n_ops, void* stream)
+{
+     if (!slab || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag_batch: bad argument");
+     DiagBatch b;
+     const int rc = make_diag_batch(b, L, ops, n_ops, kDiagChunk - 1, 0, "hiqk_apply_diag_batch");
+     if (rc != HIQ_OK) return rc;
+     const uint64_t n = 1ull << L;
+     const uint64_t n_chunks = (n + kDiagChunk - 1) / kDiagChunk;
+     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_chunks, static_cast<uint64_t>(kNumSMs) * 4 * 8));
+     diag_batch_kernel<<<grid, kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(b, static_cast<double2*>(slab), n);
+     count_launch();
+     return check_launch("diag_batch_kernel");
 }
 
 extern "C" int hiqk_scale(void* slab, int L, double re, double im, void* stream)

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from ._lib import check, lib
+from ._lib import DiagOp, check, lib
 
 AUTO, DIRECT, TILED, DMMA = 0, 1, 2, 3
 
@@ -48,6 +48,39 @@ def apply_diag(state, slots, diag, ctrl_mask=0):
     p, L = _slab(state)
     keep, dp = _cplx(diag)
     check(lib().hiqk_apply_diag(p, L, len(slots), _ints(slots), dp, ctrl_mask, _stream()))
+
+
+def _diag_ops(ops):
+    """ops: iterable of (slots, diag) -> ctypes array of hiqk_diag_op"""
+    arr = (DiagOp * len(ops))()
+    for o, (slots, diag) in zip(arr, ops):
+        d = np.ascontiguousarray(np.asarray(diag, dtype=np.complex128)).view(np.float64)
+        o.k = len(slots)
+        assert d.size == 2 << o.k
+        for l, sl in enumerate(slots):
+            o.slots[l] = int(sl)
+        for i, v in enumerate(d):
+            o.lut[i] = float(v)
+    return arr
+
+
+def apply_diag_batch(state, ops):
+    """One pass: psi[i] *= prod_j diag_j[bits of i at slots_j]; ops = [(slots, diag), ...]"""
+    p, L = _slab(state)
+    arr = _diag_ops(ops)
+    check(lib().hiqk_apply_diag_batch(p, L, arr, len(ops), _stream()))
+
+
+def apply_dense_prediag(state, slots, matrix, pre):
+    """One pass: psi <- M * prod_j D_j * psi (DIRECT kernel; pre = [(slots, diag), ...])"""
+    p, L = _slab(state)
+    keep, mp = _cplx(matrix)
+    arr = _diag_ops(pre)
+    check(lib().hiqk_apply_dense_prediag(p, L, len(slots), _ints(slots), mp, arr, len(pre), _stream()))
+
+
+def dense_prediag_supported(L, slots) -> bool:
+    return bool(lib().hiqk_dense_prediag_supported(L, len(slots), _ints(slots)))
 
 
 def scale(state, factor):

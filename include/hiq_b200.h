@@ -70,6 +70,30 @@ int hiqk_dense_pick_variant(int L, int k, const int* slots);
 int hiqk_apply_diag(void* slab, int L, int k, const int* slots, const double* diag,
                     uint64_t ctrl_mask, void* stream);
 
+/* One diagonal factor of a batched launch: psi[i] *= lut[d], d = bits of i at `slots`
+ * (bit l of d <-> slots[l]); lut holds 2^k interleaved complex128 values. */
+typedef struct hiqk_diag_op {
+     int k;          /* 0..5 (k = 0: a global scalar, lut[0..1]) */
+     int slots[5];
+     double lut[64];
+} hiqk_diag_op;
+#define HIQK_MAX_DIAG_OPS 16
+
+/* Several diagonal gates in ONE pass over the slab: psi[i] *= prod_j lut_j[bits_j(i)], n_ops <=
+ * HIQK_MAX_DIAG_OPS, no control masks.  Each op is what one launch of kernel_core_diag does in the
+ * reference (kernels/intrin/kernels_diag.hpp:35-144); diagonal factors compose by multiplication,
+ * so consecutive diagonal passes of the reference's plan cost one HBM pass here. */
+int hiqk_apply_diag_batch(void* slab, int L, const hiqk_diag_op* ops, int n_ops, void* stream);
+
+/* Dense k-qubit gate (k <= 4, no control mask, lowest target slot >= 2 — the DIRECT kernel) preceded by
+ * n_pre <= HIQK_MAX_DIAG_OPS diagonal factors applied to the loaded tuple in the same pass:
+ * psi <- M * (prod_j D_j) * psi.  Replaces n_pre launches of kernel_core_diag + one of kernelK. */
+int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slots, const double* matrix,
+                             const hiqk_diag_op* pre, int n_pre, void* stream);
+/* 1 if hiqk_apply_dense_prediag accepts these targets (otherwise apply the diagonals with
+ * hiqk_apply_diag_batch first). */
+int hiqk_dense_prediag_supported(int L, int k, const int* slots);
+
 /* psi[i] *= (re + i*im) for the whole slab.
  * Replaces kernelK_diag1 (reference: kernels/intrin/kernels_diag.hpp:21-32). */
 int hiqk_scale(void* slab, int L, double re, double im, void* stream);
@@ -139,6 +163,7 @@ typedef struct hiq_engine hiq_engine;
 #define HIQ_FLAG_DRY_RUN 1 /* no device: host logic only, every device op is recorded as a descriptor */
 #define HIQ_FLAG_TRACE 2   /* also record descriptors while executing on the GPU */
 #define HIQ_FLAG_TIMING 4  /* bracket every fused pass / swap with CUDA events on the engine stream */
+#define HIQ_FLAG_NO_BATCH 8 /* one launch per fused gate of the plan: do not fold diagonal passes into neighbours */
 
 /* descriptor kinds (what the host hands to the device layer) */
 #define HIQ_DESC_NONE 0
@@ -203,12 +228,15 @@ typedef struct hiq_stats {
      double runs_s, swaps_s, measures_s, allocs_s, deallocs_s;
      double swap_bytes_sent;
      double h2d_bytes, d2h_bytes; /* host<->device traffic issued by the engine (descriptor payloads, results) */
+     uint64_t gate_launches;      /* device launches that carried the dense/diag/scale passes (<= their sum) */
 } hiq_stats;
 int hiq_get_stats(hiq_engine* e, hiq_stats* out);
 
-/* per-pass device times (HIQ_FLAG_TIMING): waits for the stream, then returns and clears the
- * records since the last call.  kind = HIQ_DESC_*, variant = HIQK_DENSE_* (dense only). */
-int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* variant, int cap, int* n);
+/* per-launch device times (HIQ_FLAG_TIMING): waits for the stream, then returns and clears the
+ * records since the last call.  kind = HIQ_DESC_*, variant = HIQK_DENSE_* (dense only), k = targets
+ * (dense), ops in the batch (diag) or swapped pairs (swap); n_ref = fused-gate passes of the
+ * reference's plan that the launch carried (1 + folded diagonal passes). */
+int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* variant, int* n_ref, int cap, int* n);
 /* cudaStream_t of the engine (for event timing by the caller) */
 int hiq_stream(hiq_engine* e, void** stream);
 

@@ -55,6 +55,58 @@ def test_engine_forced_kernel_variants(variant):
     scripts.assert_outputs_match(script, got, exp)
 
 
+def _qft_like_script(nq, seed):
+    """H + controlled-phase ladders flushed in clusters of <= 4 qubits (long runs of diagonal passes
+    between dense ones, as the scheduled QFT produces) + queries"""
+    rng = np.random.default_rng(seed)
+    script = [("ctor", 5, nq, 4), ("allocate_qureg", list(range(nq)), 0)]
+    for q in reversed(range(nq)):
+        script.append(("apply_controlled_gate", G.H.tolist(), [q], []))
+        if rng.random() < 0.5:
+            script.append(("apply_controlled_gate", G.Ry(0.4).tolist(), [int(rng.integers(nq))], []))
+        script.append(("run",))
+        js = list(range(q))
+        for g in range(0, len(js), 3):
+            for j in js[g:g + 3]:
+                script.append(("apply_controlled_gate", G.R(math.pi / (1 << (q - j))).tolist(), [q], [j]))
+            if rng.random() < 0.3:  # a global phase (1x1 "gate") folded into the fusion factor
+                script.append(("apply_controlled_gate", G.Ph(0.2).tolist(), [q], []))
+            script.append(("run",))
+        if q % 5 == 0:
+            script.append(("get_probability", [True], [q]))
+    script.append(("get_probability", [True, False], [0, nq - 1]))
+    script.append(("cheat_local",))
+    script.append(("measure_qubits", list(range(nq))))
+    script.append(("cheat_local",))
+    return script
+
+
+@pytest.mark.parametrize("nq,seed", [(12, 1), (15, 2), (17, 3)])
+@pytest.mark.parametrize("flags", [0, 8])
+def test_engine_batched_diagonals_match_oracle(nq, seed, flags):
+    """the deferred / batched diagonal passes (and HIQ_FLAG_NO_BATCH = one launch per pass) give the reference's state"""
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    M.init_world(0, 1, b"", 0, flags)
+    try:
+        script = _qft_like_script(nq, seed)
+        exp = scripts.run_on_oracle(script, 1)
+        sims = []
+
+        def make(*a):
+            sims.append(M.SimulatorMPI(*a))
+            return sims[-1]
+        got = scripts.run_on_sim(make, script)
+        scripts.assert_outputs_match(script, got, exp)
+        st = sims[0].stats()
+        passes = st["dense_passes"] + st["diag_passes"] + st["scale_passes"]
+        if flags == 0:
+            assert st["gate_launches"] < passes, (st["gate_launches"], passes)
+        else:
+            assert st["gate_launches"] == passes
+    finally:
+        M.init_world(0, 1, b"", 0, 0)
+
+
 def _gpu_count():
     import torch
     return torch.cuda.device_count()

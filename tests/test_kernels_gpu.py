@@ -129,6 +129,68 @@ def test_apply_diag(k, slots, ctrl):
     assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
 
 
+def _rand_diag_ops(L, n_ops, seed, avoid=()):
+    rng = np.random.default_rng(seed)
+    ops = []
+    for j in range(n_ops):
+        k = int(rng.integers(0, 6))
+        slots = [int(x) for x in rng.choice(np.arange(L), size=k, replace=False)]
+        d = np.exp(1j * rng.uniform(0, 2 * np.pi, size=1 << k)) * rng.uniform(0.5, 1.5)
+        ops.append((slots, d))
+    return ops
+
+
+@pytest.mark.parametrize("L,n_ops,seed", [(14, 1, 0), (14, 5, 1), (15, 16, 2), (9, 7, 3), (5, 3, 4), (13, 12, 5)])
+def test_apply_diag_batch(L, n_ops, seed):
+    """one pass == the reference's n_ops successive kernel_core_diag passes"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    ref = rand_state(L, 40 + seed)
+    ops = _rand_diag_ops(L, n_ops, seed)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_diag_batch(dev, ops)
+    for slots, d in ops:
+        if slots:
+            statevec.apply_diag(ref, slots, d, 0)
+        else:
+            ref *= d[0]
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("k,slots", [(1, (2,)), (1, (13,)), (2, (3, 9)), (2, (12, 2)), (3, (4, 5, 6)), (3, (13, 6, 2)),
+                                     (4, (5, 2, 9, 12)), (4, (10, 11, 12, 13)), (4, (4, 8, 6, 10))])
+@pytest.mark.parametrize("n_pre", [1, 4, 16])
+def test_apply_dense_prediag(k, slots, n_pre):
+    """one pass == n_pre diagonal passes followed by the dense pass (overlapping and disjoint slots)"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    assert K.dense_prediag_supported(L, slots)
+    ref = rand_state(L, 70 + k)
+    m = rand_matrix(k, 3 * k + n_pre)
+    ops = _rand_diag_ops(L, n_pre, 100 * k + n_pre)
+    # make sure one op lies entirely inside the targets and one entirely outside
+    ops[0] = (list(slots[:max(1, k - 1)]), np.exp(1j * np.linspace(0.1, 2.0, 1 << max(1, k - 1))))
+    if n_pre > 1:
+        outside = [s for s in range(L) if s not in slots][:3]
+        ops[1] = (outside, np.exp(1j * np.linspace(0.3, 3.0, 8)))
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_dense_prediag(dev, list(slots), m, ops)
+    for sl, d in ops:
+        if sl:
+            statevec.apply_diag(ref, sl, d, 0)
+        else:
+            ref *= d[0]
+    statevec.apply_dense(ref, list(slots), m, 0)
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+def test_dense_prediag_rejects_low_slots():
+    from hiqsimulator_b200 import kernels as K
+    assert not K.dense_prediag_supported(14, (0, 5, 6, 7))
+    assert not K.dense_prediag_supported(14, (1, 2, 3, 4, 5))
+
+
 def test_scale_fill_collapse():
     torch = _torch()
     from hiqsimulator_b200 import kernels as K
