@@ -55,6 +55,7 @@ _SIGNATURES = {
     "hiqk_swap_unpack": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _u64, _u64, _u64, _vp, _vp]),
     "hiqk_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
     "hiqk_launch_count": (_u64, []),
+    "hiqk_debug_set_max_grid": (C.c_int, [C.c_int]),
 }
 
 

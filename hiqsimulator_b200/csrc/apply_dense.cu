@@ -92,56 +92,119 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_kernel(const __gri
      }
 }
 
-// DIRECT with pre-diagonals: psi <- M * (prod_j D_j) * psi in one pass.  Tuples are processed in chunks
-// of THREADS * T consecutive free indices (one CTA iteration): diagonal ops whose slots cannot change
-// inside a chunk collapse into one factor per chunk (diag_hoist); an op with chunk-varying slots costs
-// one lookup + multiply per tuple; an op that overlaps the dense targets costs one per tuple element,
-// selected by (chunk bits | tuple bits | dsel[j][c]).
-constexpr int kPreTuplesPerThread = 8;
+// DIRECT, staged: same arithmetic as dense_direct_kernel, but every thread's NEXT tuple is copied into
+// its shared-memory column by cp.async while the current tuple is multiplied, so the HBM latency of a
+// tuple hides behind 2^(2K) complex MACs instead of stalling the (register-limited, 4 warps/scheduler) CTA.
+template <int K, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) dense_direct_staged_kernel(const __grid_constant__ DirectParams<K> p)
+{
+     extern __shared__ double2 dyn_smem[];
+     double2 (*stage)[THREADS] = reinterpret_cast<double2 (*)[THREADS]>(dyn_smem);
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * THREADS;
+     auto tuple_base = [&](uint64_t f) { return p.psi + (insert_zero_bits(f, p.ins) | p.ctrl_mask); };
+     auto prefetch = [&](const double2* base) {
+#pragma unroll
+          for (int c = 0; c < (1 << K); ++c) cp_async16(&stage[c][threadIdx.x], base + p.off[c]);
+     };
+     uint64_t f = static_cast<uint64_t>(blockIdx.x) * THREADS + threadIdx.x;
+     if (f < p.n_free) prefetch(tuple_base(f));
+     for (; f < p.n_free; f += stride) {
+          double2* base = tuple_base(f);
+          cp_async_wait_all();  // this thread's own copies; nobody else reads its column
+          double2 in[1 << K];
+#pragma unroll
+          for (int c = 0; c < (1 << K); ++c) in[c] = stage[c][threadIdx.x];
+          if (f + stride < p.n_free) prefetch(tuple_base(f + stride));
+          apply_rows<K>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
+     }
+}
+
+// DIRECT with diagonals folded in: psi <- M * (prod_j D_j) * psi in one pass (DiagProg, hiq_device.cuh).
+// Free index = (chunk bits | t bits | tid bits): a CTA iteration covers THREADS consecutive free indices
+// (tid) times 2^n_t tuples per thread (t) whose index positions are the free bits the ops touch least.
+// Ops that avoid the dense targets are per-tuple scalars — S0: one factor per thread per chunk, S1: one
+// lookup per tuple — and are multiplied into ONE scalar s.  An op that overlaps the targets (class E)
+// needs a factor per tuple element: the first one is combined with s into the 2^m distinct values
+// s * lut[...] (m = overlapping target bits) staged in this thread's shared-memory column, so the whole
+// diagonal program costs 2^K complex multiplies per tuple on top of the matrix product.
+constexpr int kMaxTBits = 3;
 
 template <int K>
 struct DirectPreParams {
-     DirectParams<K> d;
-     uint32_t overlap_mask;                  // bit j: op j touches a dense target
-     uint8_t dsel[kMaxDiagOps][1 << K];      // selector bits of op j contributed by tuple element c
-     DiagBatch pre;
+     DirectParams<K> d;                      // d.ins = targets U t positions; d.n_free = 2^(L - K - n_t)
+     int n_t;
+     int fast;                               // no op depends on t: every factor is fixed per thread per chunk
+     uint64_t toff[1 << kMaxTBits];          // index offset of tuple t of a thread
+     int e_npat;                             // distinct joint patterns of the class-E ops over the tuple elements
+     uint8_t e_pat[kMaxDiagOps][1 << K];     // selector bits of class-E op j for joint pattern e
+     uint8_t e_cmap[1 << K];                 // joint pattern of tuple element c
+     DiagProg prog;
 };
 
 template <int K, int THREADS, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const __grid_constant__ DirectPreParams<K> p)
 {
-     __shared__ double2 lut[kMaxDiagOps][1 << kMaxTargets];
-     __shared__ DiagHoist h;
-     for (int i = threadIdx.x; i < p.pre.n * (1 << kMaxTargets); i += THREADS)
-          lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)] = p.pre.lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)];
-     constexpr uint64_t CH = static_cast<uint64_t>(THREADS) * kPreTuplesPerThread;
-     const uint64_t n_chunks = (p.d.n_free + CH - 1) / CH;
-     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-          diag_hoist(p.pre, lut, insert_zero_bits(chunk * CH, p.d.ins), h);
-          const double2 s_hi = h.s_hi;
+     // dynamic shared memory: stage[2^K][THREADS] (this thread's NEXT tuple, filled by cp.async while the
+     // current one is being multiplied) followed by sT[e_npat][THREADS] (this thread's class-E factors)
+     extern __shared__ double2 dyn_smem[];
+     double2 (*stage)[THREADS] = reinterpret_cast<double2 (*)[THREADS]>(dyn_smem);
+     double2 (*sT)[THREADS] = reinterpret_cast<double2 (*)[THREADS]>(dyn_smem + (1 << K) * THREADS);
+     __shared__ DiagShared sh;
+     uint32_t selt[kMaxDiagOps / 4];
+     diag_prog_init<THREADS>(p.prog, sh, insert_zero_bits(threadIdx.x, p.d.ins), selt);
+     const uint64_t n_chunks = (p.d.n_free + THREADS - 1) / THREADS;
+     const int nt = 1 << p.n_t;
+     const int je = p.prog.n_s0 + p.prog.n_s1;  // first class-E op
+     const bool valid = threadIdx.x < p.d.n_free;  // only a slab smaller than one chunk leaves threads idle
+     // factors of the joint patterns for tuple t of this thread, scalar part s folded in
+     auto build_patterns = [&](double2 s, int t) {
+          for (int e = 0; e < p.e_npat; ++e) {
+               double2 f = s;
+               for (int j = je; j < p.prog.n; ++j)
+                    f = cmul(f, sh.lut[j][sh.selh[j] | diag_selt(selt, j) | p.prog.usel[j][t] | p.e_pat[j][e]]);
+               sT[e][threadIdx.x] = f;
+          }
+     };
+     // index of this thread's tuple 0 in a chunk (bit deposit, once per chunk); tuple t adds toff[t]
+     auto chunk_index = [&](uint64_t chunk) { return insert_zero_bits(chunk * THREADS + threadIdx.x, p.d.ins); };
+     auto prefetch = [&](const double2* base) {
+#pragma unroll
+          for (int c = 0; c < (1 << K); ++c) cp_async16(&stage[c][threadIdx.x], base + p.d.off[c]);
+     };
+     uint64_t chunk = blockIdx.x;
+     uint64_t bidx = chunk < n_chunks ? chunk_index(chunk) : 0;
+     if (chunk < n_chunks && valid) prefetch(p.d.psi + bidx);
+     for (; chunk < n_chunks; chunk += gridDim.x) {
+          diag_prog_chunk(p.prog, sh, insert_zero_bits(chunk * THREADS, p.d.ins));
+          if (!valid) continue;
+          const double2 s0 = diag_prog_s0(p.prog, sh, selt);
+          if (p.fast && p.prog.n_e) build_patterns(s0, 0);
+          const uint64_t bidx_next = chunk + gridDim.x < n_chunks ? chunk_index(chunk + gridDim.x) : 0;
 #pragma unroll 1
-          for (int t = 0; t < kPreTuplesPerThread; ++t) {
-               const uint64_t f = chunk * CH + static_cast<uint64_t>(t) * THREADS + threadIdx.x;
-               if (f >= p.d.n_free) break;
-               const uint64_t bidx = insert_zero_bits(f, p.d.ins);
-               double2* base = p.d.psi + bidx;
-               double2 in[1 << K];
-               load_tuple<K>(in, base, p.d.off);
-               double2 s = s_hi;
-               for (int j = 0; j < p.pre.n_lo; ++j) {
-                    const uint32_t sb = h.selh[j] | diag_select_lo(p.pre.slots[j], p.pre.n_lo_slots[j], bidx);
-                    if ((p.overlap_mask >> j) & 1u) {
-#pragma unroll
-                         for (int c = 0; c < (1 << K); ++c) in[c] = cmul(in[c], lut[j][sb | p.dsel[j][c]]);
-                    }
-                    else {
-                         s = cmul(s, lut[j][sb]);
-                    }
+          for (int t = 0; t < nt; ++t) {
+               double2* base = p.d.psi + (bidx | p.toff[t]);
+               double2 s = s0;
+               if (!p.fast) {
+                    s = diag_prog_s1(p.prog, sh, selt, t, s0);
+                    if (p.prog.n_e) build_patterns(s, t);
                }
+               cp_async_wait_all();  // this thread's own copies: no CTA barrier needed, nobody else reads them
+               double2 in[1 << K];
+               if (p.prog.n_e == 0) {
 #pragma unroll
-               for (int c = 0; c < (1 << K); ++c) in[c] = cmul(in[c], s);
+                    for (int c = 0; c < (1 << K); ++c) in[c] = cmul(stage[c][threadIdx.x], s);
+               }
+               else {
+#pragma unroll
+                    for (int c = 0; c < (1 << K); ++c) in[c] = cmul(stage[c][threadIdx.x], sT[p.e_cmap[c]][threadIdx.x]);
+               }
+               // the staged tuple now lives in registers (the multiplies above consumed it): refill the stage
+               // with this thread's next tuple so its HBM latency hides behind the matrix product
+               if (t + 1 < nt) prefetch(p.d.psi + (bidx | p.toff[t + 1]));
+               else if (chunk + gridDim.x < n_chunks) prefetch(p.d.psi + bidx_next);
                apply_rows<K>(in, p.d.m, [&](int b, double2 v) { base[p.d.off[b]] = v; });
           }
+          bidx = bidx_next;
      }
 }
 
@@ -343,8 +406,23 @@ static int launch_direct(double2* psi, int L, const int* slots, const double* ma
      constexpr int THREADS = (K >= 4) ? 128 : 256;
      constexpr int MINB = (K >= 5) ? 2 : (K == 4 ? 4 : 4);
      const uint64_t need = (p.n_free + THREADS - 1) / THREADS;
-     const uint64_t cap = static_cast<uint64_t>(kNumSMs) * MINB * 8;
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(need, cap));
+     if constexpr (K >= 3 && K <= 4) {
+          // register-limited shapes: stage the next tuple through shared memory (cp.async)
+          if (need > cap) {
+               static bool attr_set = false;
+               if (!attr_set) {
+                    cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         64 * 1024);
+                    cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+                    attr_set = true;
+               }
+               dense_direct_staged_kernel<K, THREADS, MINB><<<grid, THREADS, sizeof(double2) * THREADS << K, stream>>>(p);
+               count_launch();
+               return check_launch("dense_direct_staged_kernel");
+          }
+     }
      dense_direct_kernel<K, THREADS, MINB><<<grid, THREADS, 0, stream>>>(p);
      count_launch();
      return check_launch("dense_direct_kernel");
@@ -358,37 +436,76 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
      static std::mutex mu;
      std::lock_guard<std::mutex> lock(mu);
      constexpr int THREADS = (K >= 3) ? 128 : 256;
+     constexpr int TID_BITS = (K >= 3) ? 7 : 8;
      constexpr int MINB = 4;
-     constexpr uint64_t CH = static_cast<uint64_t>(THREADS) * kPreTuplesPerThread;
-     p.d.psi = psi;
-     p.d.n_free = 1ull << (L - K);
-     p.d.ctrl_mask = 0;
-     p.d.ins = make_insert_bits(slots, K, 0);
-     fill_common<K>(p.d.off, p.d.m, slots, matrix);
      uint64_t tmask = 0;
      for (int t = 0; t < K; ++t) tmask |= 1ull << slots[t];
-     // index bits that change inside one chunk of consecutive free indices
-     const uint64_t varying = insert_zero_bits(CH - 1, p.d.ins);
-     const int rc = make_diag_batch(p.pre, L, pre, n_pre, varying, tmask, "hiqk_apply_dense_prediag");
+     // tid occupies the TID_BITS lowest free index positions; t positions are picked among the rest
+     uint64_t tid_mask = 0;
+     for (int pos = 0, got = 0; pos < L && got < TID_BITS; ++pos)
+          if (!((tmask >> pos) & 1ull)) {
+               tid_mask |= 1ull << pos;
+               ++got;
+          }
+     int tpos[kMaxTBits];
+     const int n_t = choose_u_positions(L, pre, n_pre, tmask | tid_mask, kMaxTBits, tpos);
+     int order[kMaxDiagOps];
+     const int rc = build_diag_prog(p.prog, L, pre, n_pre, tpos, n_t, tmask, tid_mask, order, "hiqk_apply_dense_prediag");
      if (rc != HIQ_OK) return rc;
-     p.overlap_mask = 0;
-     std::memset(p.dsel, 0, sizeof(p.dsel));
-     for (int j = 0; j < n_pre; ++j) {
-          bool overlap = false;
-          for (int c = 0; c < (1 << K); ++c) {
-               uint32_t sel = 0;
+     p.n_t = n_t;
+     for (int t = 0; t < (1 << kMaxTBits); ++t) {
+          uint64_t o = 0;
+          for (int b = 0; b < n_t; ++b)
+               if ((t >> b) & 1) o |= 1ull << tpos[b];
+          p.toff[t] = o;
+     }
+     // free-index deposit skips the targets and the t positions
+     {
+          std::vector<int> skip(slots, slots + K);
+          skip.insert(skip.end(), tpos, tpos + n_t);
+          p.d.ins = make_insert_bits(skip.data(), static_cast<int>(skip.size()), 0);
+     }
+     p.d.psi = psi;
+     p.d.n_free = 1ull << (L - K - n_t);
+     p.d.ctrl_mask = 0;
+     fill_common<K>(p.d.off, p.d.m, slots, matrix);
+     // class-E tables: the selector bits every tuple element contributes to each op, grouped into the
+     // distinct joint patterns (elements with the same bits for all class-E ops share one factor)
+     std::memset(p.e_pat, 0, sizeof(p.e_pat));
+     std::memset(p.e_cmap, 0, sizeof(p.e_cmap));
+     const int je = p.prog.n_s0 + p.prog.n_s1;
+     std::vector<std::vector<uint32_t>> pats;  // pats[e][j - je]
+     for (int c = 0; c < (1 << K); ++c) {
+          std::vector<uint32_t> sel(p.prog.n - je, 0);
+          for (int j = je; j < p.prog.n; ++j)
                for (int l = 0; l < kMaxTargets; ++l)
                     for (int t = 0; t < K; ++t)
-                         if (p.pre.slots[j][l] == slots[t] && ((c >> t) & 1)) sel |= 1u << l;
-               p.dsel[j][c] = static_cast<uint8_t>(sel);
-               overlap |= sel != 0;
+                         if (p.prog.slots[j][l] == slots[t] && ((c >> t) & 1)) sel[j - je] |= 1u << l;
+          auto it = std::find(pats.begin(), pats.end(), sel);
+          if (it == pats.end()) {
+               pats.push_back(sel);
+               it = pats.end() - 1;
           }
-          if (overlap) p.overlap_mask |= 1u << j;
+          p.e_cmap[c] = static_cast<uint8_t>(it - pats.begin());
      }
-     const uint64_t n_chunks = (p.d.n_free + CH - 1) / CH;
-     const uint64_t cap = static_cast<uint64_t>(kNumSMs) * MINB * 4;
+     p.e_npat = p.prog.n_e ? static_cast<int>(pats.size()) : 0;
+     for (size_t e = 0; e < pats.size(); ++e)
+          for (int j = je; j < p.prog.n; ++j) p.e_pat[j][e] = static_cast<uint8_t>(pats[e][j - je]);
+     p.fast = p.prog.n_s1 == 0 ? 1 : 0;
+     for (int j = je; j < p.prog.n; ++j)
+          for (int t = 0; t < (1 << n_t); ++t)
+               if (p.prog.usel[j][t]) p.fast = 0;
+     static bool attr_set = false;
+     if (!attr_set) {
+          cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+          cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+          attr_set = true;
+     }
+     const size_t smem = sizeof(double2) * THREADS * ((1u << K) + std::max(p.e_npat, 1));
+     const uint64_t n_chunks = (p.d.n_free + THREADS - 1) / THREADS;
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap));
-     dense_direct_pre_kernel<K, THREADS, MINB><<<grid, THREADS, 0, stream>>>(p);
+     dense_direct_pre_kernel<K, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p);
      count_launch();
      return check_launch("dense_direct_pre_kernel");
 }
@@ -460,7 +577,7 @@ static int launch_tiled(double2* psi, int L, const int* slots, const double* mat
           cudaFuncSetAttribute(dense_tiled_kernel<K, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
           attr_set = true;
      }
-     const uint64_t cap = static_cast<uint64_t>(kNumSMs) * MINB * 4;
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 4);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, cap));
      dense_tiled_kernel<K, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p);
      count_launch();
@@ -492,7 +609,7 @@ static int launch_dmma(double2* psi, int L, const int* slots, const double* matr
      }
      const uint64_t groups_per_block = static_cast<uint64_t>(THREADS / 32) * G;
      const uint64_t need = (p.n_groups + groups_per_block - 1) / groups_per_block;
-     const uint64_t cap = static_cast<uint64_t>(kNumSMs) * MINB * 2;
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 2);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(need, cap));
      dense_dmma_kernel<K, THREADS, MINB, G><<<grid, THREADS, smem, stream>>>(p);
      count_launch();

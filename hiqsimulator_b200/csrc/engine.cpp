@@ -95,6 +95,8 @@ Engine::~Engine()
                cudaEventDestroy(t.stop);
           }
           for (auto ev: event_pool_) cudaEventDestroy(ev);
+          for (auto ev: swap_events_)
+               if (ev) cudaEventDestroy(ev);
           if (stream_) cudaStreamDestroy(stream_);
           if (comm_stream_) cudaStreamDestroy(comm_stream_);
      }
@@ -346,6 +348,41 @@ void Engine::d2h(void* dst, const void* src, size_t bytes)
      stats_.d2h_bytes += static_cast<double>(bytes);
 }
 
+namespace {
+uint64_t slot_mask(const hiqk_diag_op& o)
+{
+     uint64_t m = 0;
+     for (int l = 0; l < o.k; ++l) m |= 1ull << o.slots[l];
+     return m;
+}
+
+// Folds `op` into a queued op over a superset of its slots (one table instead of two lookups), or
+// appends it when the queue has room.  Returns false when neither is possible.
+bool merge_or_append(std::vector<hiqk_diag_op>& q, std::vector<int>& refs, const hiqk_diag_op& op, size_t cap)
+{
+     const uint64_t mo = slot_mask(op);
+     for (size_t i = 0; i < q.size(); ++i) {
+          hiqk_diag_op& t = q[i];
+          if ((mo & ~slot_mask(t)) != 0) continue;
+          cplx* tl = reinterpret_cast<cplx*>(t.lut);
+          const cplx* ol = reinterpret_cast<const cplx*>(op.lut);
+          for (int e = 0; e < (1 << t.k); ++e) {
+               int sel = 0;
+               for (int l = 0; l < op.k; ++l)
+                    for (int m = 0; m < t.k; ++m)
+                         if (t.slots[m] == op.slots[l] && ((e >> m) & 1)) sel |= 1 << l;
+               tl[e] *= ol[sel];
+          }
+          ++refs[i];
+          return true;
+     }
+     if (q.size() >= cap) return false;
+     q.push_back(op);
+     refs.push_back(1);
+     return true;
+}
+}  // namespace
+
 void Engine::execute(const Descriptor& d)
 {
      if (tracing_) trace_.push_back(d);
@@ -355,21 +392,28 @@ void Engine::execute(const Descriptor& d)
      int variant = 0;
      if (d.kind == HIQ_DESC_DENSE) variant = dense_variant_ ? dense_variant_ : hiqk_dense_pick_variant(L, d.k, d.slots);
      if (batching_) {
-          // diagonal passes of the plan are deferred: they ride along the next dense launch or go out
-          // as one batched pass at the next observation of the slab
+          // diagonal passes of the plan are deferred: they ride along a neighbouring dense launch or go
+          // out as one batched pass at the next observation of the slab
           if ((d.kind == HIQ_DESC_DIAG || d.kind == HIQ_DESC_SCALE) && d.ctrl_mask == 0) {
                queue_diagonal(d);
                return;
           }
-          if (d.kind == HIQ_DESC_DENSE && d.ctrl_mask == 0 && !pending_.empty() && variant == HIQK_DENSE_DIRECT &&
+          if (d.kind == HIQ_DESC_DENSE && d.ctrl_mask == 0 && variant == HIQK_DENSE_DIRECT &&
               hiqk_dense_prediag_supported(L, d.k, d.slots)) {
-               flush_pending(HIQK_MAX_DIAG_OPS);
-               launch(d, variant, static_cast<int>(pending_.size()));
+               launch_held();                         // the previous dense launch goes out now
+               flush_pending(HIQK_MAX_DIAG_OPS);      // more diagonals than one launch carries: batched passes first
+               held_ = true;
+               held_d_ = d;
+               held_variant_ = variant;
+               held_ops_.swap(pending_);              // they precede this gate: applied to the tuples it loads
+               held_ref_.swap(pending_ref_);
+               pending_.clear();
+               pending_ref_.clear();
                return;
           }
      }
      flush_pending();
-     launch(d, variant, 0);
+     launch(d, variant, {}, {});
 }
 
 void Engine::queue_diagonal(const Descriptor& d)
@@ -379,34 +423,30 @@ void Engine::queue_diagonal(const Descriptor& d)
      op.k = d.kind == HIQ_DESC_SCALE ? 0 : d.k;
      for (int l = 0; l < op.k; ++l) op.slots[l] = d.slots[l];
      std::memcpy(op.lut, d.payload.data(), sizeof(cplx) << op.k);
-     // host-side merge: an op over the same slot set as a pending one (or a global scalar) is folded
-     // into that op's table instead of costing another lookup per amplitude
-     for (size_t i = 0; i < pending_.size(); ++i) {
-          hiqk_diag_op& q = pending_[i];
-          uint64_t mq = 0, mo = 0;
-          for (int l = 0; l < q.k; ++l) mq |= 1ull << q.slots[l];
-          for (int l = 0; l < op.k; ++l) mo |= 1ull << op.slots[l];
-          if ((mo & ~mq) != 0) continue;  // op's slots must be a subset of q's
-          cplx* ql = reinterpret_cast<cplx*>(q.lut);
-          const cplx* ol = reinterpret_cast<const cplx*>(op.lut);
-          for (int e = 0; e < (1 << q.k); ++e) {
-               int sel = 0;
-               for (int l = 0; l < op.k; ++l)
-                    for (int m = 0; m < q.k; ++m)
-                         if (q.slots[m] == op.slots[l] && ((e >> m) & 1)) sel |= 1 << l;
-               ql[e] *= ol[sel];
-          }
-          ++pending_ref_[i];
-          return;
+     if (held_) {
+          uint64_t tm = 0;
+          for (int l = 0; l < held_d_.k; ++l) tm |= 1ull << held_d_.slots[l];
+          // commutes with the held dense gate: joins its launch as a per-tuple scalar
+          if ((slot_mask(op) & tm) == 0 && merge_or_append(held_ops_, held_ref_, op, HIQK_MAX_DIAG_OPS)) return;
      }
-     pending_.push_back(op);
-     pending_ref_.push_back(1);
+     merge_or_append(pending_, pending_ref_, op, static_cast<size_t>(-1));
+}
+
+void Engine::launch_held()
+{
+     if (!held_) return;
+     held_ = false;
+     launch(held_d_, held_variant_, held_ops_, held_ref_);
+     held_ops_.clear();
+     held_ref_.clear();
 }
 
 void Engine::flush_pending(size_t keep)
 {
+     // the held dense launch first (queued diagonals that touch its targets come after it), then
      // batched diagonal launches (full batches first) until at most `keep` ops remain queued
      if (dry_run_) return;
+     launch_held();
      while (pending_.size() > keep) {
           const size_t take = std::min<size_t>(pending_.size(), HIQK_MAX_DIAG_OPS);
           int n_ref = 0;
@@ -428,11 +468,11 @@ void Engine::flush_pending(size_t keep)
      }
 }
 
-void Engine::launch(const Descriptor& d, int variant, int n_pre)
+void Engine::launch(const Descriptor& d, int variant, const std::vector<hiqk_diag_op>& ops, const std::vector<int>& refs)
 {
      const int L = static_cast<int>(locals_.size());
      int n_ref = 1;
-     for (int i = 0; i < n_pre; ++i) n_ref += pending_ref_[i];
+     for (int r: refs) n_ref += r;
      TimedPass tp{d.kind, d.k, variant, n_ref, nullptr, nullptr};
      if (timing_) {
           tp.start = take_event();
@@ -441,16 +481,12 @@ void Engine::launch(const Descriptor& d, int variant, int n_pre)
      }
      switch (d.kind) {
           case HIQ_DESC_DENSE:
-               if (n_pre > 0) {
+               if (!ops.empty())
                     cu(hiqk_apply_dense_prediag(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()),
-                                                pending_.data(), n_pre, stream_));
-                    pending_.clear();
-                    pending_ref_.clear();
-               }
-               else {
+                                                ops.data(), static_cast<int>(ops.size()), stream_));
+               else
                     cu(hiqk_apply_dense(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()),
                                         d.ctrl_mask, variant, stream_));
-               }
                break;
           case HIQ_DESC_DIAG:
                cu(hiqk_apply_diag(slab_.data(), L, d.k, d.slots, reinterpret_cast<const double*>(d.payload.data()), d.ctrl_mask,
@@ -722,7 +758,10 @@ void Engine::copy_slab_from_host(const void* src, uint64_t n_amps)
 {
      need_device("set_local_slab()");
      if (n_amps != (1ull << locals_.size())) fail("set_local_slab(): size must equal 2^(local qubits)");
-     pending_.clear();  // the whole slab is overwritten
+     held_ = false;  // the whole slab is overwritten
+     held_ops_.clear();
+     held_ref_.clear();
+     pending_.clear();
      pending_ref_.clear();
      cu(check_cuda(cudaMemcpyAsync(slab_.data(), src, n_amps * sizeof(double2), cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync"));
      synchronize();
@@ -788,6 +827,11 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
      // Peer p differs from this rank in a non-empty subset of the swapped global bits; the
      // amplitudes whose swapped slots spell p's bits go to p and are replaced, in place, by p's
      // amplitudes whose swapped slots spell this rank's bits.
+     //
+     // Pipeline: the free-index range is cut into pieces; piece i is packed on the engine stream,
+     // exchanged on the communication stream (one NCCL group of send/recv to the 2^q - 1 peers) and
+     // unpacked on the engine stream, with two staging buffers so that pack(i+1) and unpack(i-1)
+     // overlap the NVLink transfer of piece i.  Pieces touch disjoint amplitudes, so in place is safe.
      const int L = static_cast<int>(locals_.size());
      const int q = static_cast<int>(gpos.size());
      std::vector<int> order(q);  // pair indices by ascending slot
@@ -796,15 +840,26 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
      const uint64_t chunk = 1ull << (L - q);
      const int n_peers = (1 << q) - 1;
      const uint64_t piece = std::min(chunk, kSwapPieceAmps);
-     const size_t need = 2ull * n_peers * piece * sizeof(double2);
+     constexpr int NBUF = 2;
+     const size_t need = 2ull * NBUF * n_peers * piece * sizeof(double2);
      if (!swap_buf_ || swap_buf_bytes_ < need) {
           if (swap_buf_) cudaFree(swap_buf_);
           swap_buf_ = nullptr;
           cu(check_cuda(cudaMalloc(&swap_buf_, need), "cudaMalloc swap staging"));
           swap_buf_bytes_ = need;
      }
-     double2* send = static_cast<double2*>(swap_buf_);
-     double2* recv = send + static_cast<uint64_t>(n_peers) * piece;
+     const uint64_t buf_amps = static_cast<uint64_t>(n_peers) * piece;
+     double2* send[NBUF];
+     double2* recv[NBUF];
+     for (int b = 0; b < NBUF; ++b) {
+          send[b] = static_cast<double2*>(swap_buf_) + (2 * b) * buf_amps;
+          recv[b] = static_cast<double2*>(swap_buf_) + (2 * b + 1) * buf_amps;
+     }
+     if (!swap_events_[0]) {
+          for (auto& ev: swap_events_) cu(check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate"));
+     }
+     cudaEvent_t* packed = &swap_events_[0];      // [NBUF] piece packed on stream_
+     cudaEvent_t* exchanged = &swap_events_[NBUF];  // [NBUF] piece exchanged on comm_stream_
      struct Peer {
           int rank;
           uint64_t pat;  // pattern over the sorted swapped slots
@@ -819,20 +874,31 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
                if ((pr >> gpos[order[j]]) & 1) pat |= 1ull << j;
           peers.push_back({pr, pat});
      }
-     for (uint64_t begin = 0; begin < chunk; begin += piece) {
-          const uint64_t cnt = std::min(piece, chunk - begin);
-          for (int i = 0; i < n_peers; ++i)
-               cu(hiqk_swap_pack(slab_.data(), L, q, slots.data(), peers[i].pat, begin, cnt, send + i * piece, stream_));
+     const uint64_t n_pieces = chunk / piece;
+     auto unpack_piece = [&](uint64_t i) {
+          const int b = static_cast<int>(i % NBUF);
+          cu(check_cuda(cudaStreamWaitEvent(stream_, exchanged[b], 0), "cudaStreamWaitEvent"));
+          for (int k = 0; k < n_peers; ++k)
+               cu(hiqk_swap_unpack(slab_.data(), L, q, slots.data(), peers[k].pat, i * piece, piece, recv[b] + k * piece, stream_));
+     };
+     for (uint64_t i = 0; i < n_pieces; ++i) {
+          const int b = static_cast<int>(i % NBUF);
+          // send[b]/recv[b] were last used by piece i - NBUF, whose unpack is already queued on stream_
+          for (int k = 0; k < n_peers; ++k)
+               cu(hiqk_swap_pack(slab_.data(), L, q, slots.data(), peers[k].pat, i * piece, piece, send[b] + k * piece, stream_));
+          cu(check_cuda(cudaEventRecord(packed[b], stream_), "cudaEventRecord"));
+          cu(check_cuda(cudaStreamWaitEvent(comm_stream_, packed[b], 0), "cudaStreamWaitEvent"));
           nccl().GroupStart();
-          for (int i = 0; i < n_peers; ++i) {
-               nccl().Send(send + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_p_->handle(), stream_);
-               nccl().Recv(recv + i * piece, cnt * 2, ncclDouble, peers[i].rank, comm_p_->handle(), stream_);
+          for (int k = 0; k < n_peers; ++k) {
+               nccl().Send(send[b] + k * piece, piece * 2, ncclDouble, peers[k].rank, comm_p_->handle(), comm_stream_);
+               nccl().Recv(recv[b] + k * piece, piece * 2, ncclDouble, peers[k].rank, comm_p_->handle(), comm_stream_);
           }
           ncclResult_t r = nccl().GroupEnd();
           if (r != ncclSuccess) throw EngineError(HIQ_ERR_CUDA, std::string("ncclGroupEnd: ") + nccl().GetErrorString(r));
-          for (int i = 0; i < n_peers; ++i)
-               cu(hiqk_swap_unpack(slab_.data(), L, q, slots.data(), peers[i].pat, begin, cnt, recv + i * piece, stream_));
+          cu(check_cuda(cudaEventRecord(exchanged[b], comm_stream_), "cudaEventRecord"));
+          if (i >= 1) unpack_piece(i - 1);
      }
+     unpack_piece(n_pieces - 1);
      stats_.swap_bytes_sent += static_cast<double>(n_peers) * chunk * sizeof(double2);
 }
 

@@ -119,7 +119,8 @@ private:
      double probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
      void normalize(double norm, uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
      void execute(const Descriptor& d);
-     void launch(const Descriptor& d, int variant, int n_pre);
+     void launch(const Descriptor& d, int variant, const std::vector<hiqk_diag_op>& ops, const std::vector<int>& refs);
+     void launch_held();
      void queue_diagonal(const Descriptor& d);
      void flush_pending(size_t keep = 0);
      void ensure_scratch();
@@ -142,6 +143,7 @@ private:
      double* d_blocks_ = nullptr; // world * 2^15 block sums
      void* swap_buf_ = nullptr;   // staging for the exchange (send | recv)
      size_t swap_buf_bytes_ = 0;
+     cudaEvent_t swap_events_[4] = {nullptr, nullptr, nullptr, nullptr};  // packed[2], exchanged[2]
      int dense_variant_ = 0;
 
      EngineStats stats_;
@@ -155,6 +157,14 @@ private:
      // passes of the reference's plan op i stands for (ops over the same slots are multiplied on the host).
      std::vector<hiqk_diag_op> pending_;
      std::vector<int> pending_ref_;
+     // The most recent dense launch is held back until the next dense gate (or the next observation):
+     // diagonal gates that arrive meanwhile and avoid its targets commute with it and join its launch as
+     // per-tuple scalars; the ones that touch its targets wait in pending_ for the next dense launch.
+     bool held_ = false;
+     Descriptor held_d_;
+     int held_variant_ = 0;
+     std::vector<hiqk_diag_op> held_ops_;
+     std::vector<int> held_ref_;
      std::vector<TimedPass> timed_;
      std::vector<cudaEvent_t> event_pool_;
      cudaEvent_t take_event();

@@ -44,21 +44,27 @@ __device__ __forceinline__ double norm2(const double2 a) { return fma(a.x, a.x, 
 // ---------------------------------------------------------------------------------------------
 // Batched diagonal factors.  Consecutive diagonal fused gates of the reference's plan (each one
 // would be a full pass of kernel_core_diag, reference: kernels/intrin/kernels_diag.hpp:35-144)
-// commute with every index permutation and compose by multiplication, so a launch can apply up
-// to kMaxDiagOps of them in ONE pass over HBM: psi[i] *= prod_j lut_j[bits of i at slots_j].
-// The same structure rides along a dense launch as "pre-diagonals" applied to the loaded tuple.
+// compose by multiplication, so a launch can apply up to kMaxDiagOps of them in ONE pass over HBM:
+// psi[i] *= prod_j lut_j[bits of i at slots_j].  The same program rides along a dense launch,
+// applied to the tuple it loads.
+//
+// Cost model: an element index is split as  (chunk bits | u bits | tid bits).  The selector of op j
+// is the OR of three partial selectors: selh_j(chunk) computed once per CTA iteration by warp 0,
+// selt_j(tid) computed once per thread per kernel, usel_j[u] tabulated by the host.  Ops that do not
+// depend on u (class S0) collapse into ONE factor per thread per chunk; ops that do (class S1) cost a
+// lookup + complex multiply per element.  The host picks the u bit positions among the index bits the
+// ops touch least, so S1 is usually empty.
 // ---------------------------------------------------------------------------------------------
 constexpr int kMaxDiagOps = 16;
+constexpr int kMaxUBits = 4;
 
-// Work is cut into *chunks* of consecutive indices (one CTA iteration each).  A slot whose index
-// bit cannot change inside a chunk is "chunk-constant": its selector bits are computed once per
-// chunk by one warp; an op made only of such slots collapses into a single per-chunk factor.
-struct DiagBatch {
-     int n;                               // ops in use
-     int n_lo;                            // ops [0, n_lo) need per-element work, ops [n_lo, n) are chunk-constant
-     uint8_t n_lo_slots[kMaxDiagOps];     // leading entries of slots[j] that vary inside a chunk
-     uint8_t slots[kMaxDiagOps][8];       // reordered: chunk-varying slots first; unused entries = 63 (always-0 bit)
-     double2 lut[kMaxDiagOps][1 << kMaxTargets];  // permuted to the reordered slots
+struct DiagProg {
+     int n;                                        // ops in use, ordered S0 | S1 | E
+     int n_s0, n_s1, n_e;                          // class sizes (n_e > 0 only along a dense launch)
+     int n_s0a;                                    // leading S0 ops that do not depend on tid either: one factor per CTA per chunk
+     uint8_t slots[kMaxDiagOps][8];                // selector bit l <-> index bit slots[j][l]; unused = 63 (always 0)
+     uint8_t usel[kMaxDiagOps][1 << kMaxUBits];    // selector bits contributed by the u part of the index
+     double2 lut[kMaxDiagOps][1 << kMaxTargets];
 };
 
 // selector of an op for index idx (bit l of the selector = bit slots[l] of idx)
@@ -70,32 +76,47 @@ __device__ __forceinline__ uint32_t diag_select(const uint8_t (&slots)[8], uint6
      return sel;
 }
 
-// selector bits contributed by the n_lo leading (chunk-varying) slots
-__device__ __forceinline__ uint32_t diag_select_lo(const uint8_t (&slots)[8], int n_lo, uint64_t idx)
-{
-     uint32_t sel = 0;
-     for (int l = 0; l < n_lo; ++l) sel |= static_cast<uint32_t>((idx >> slots[l]) & 1ull) << l;
-     return sel;
-}
-
-struct DiagHoist {
-     double2 s_hi;                  // product of the chunk-constant ops
-     uint32_t selh[kMaxDiagOps];    // chunk-constant selector bits of every op
+struct DiagShared {
+     double2 lut[kMaxDiagOps][1 << kMaxTargets];
+     uint32_t selh[kMaxDiagOps];                   // per-chunk partial selectors
+     double2 s_hi;                                 // per-chunk product of the CTA-uniform ops [0, n_s0a)
 };
 
-// Once per chunk (all threads of the CTA call it): selectors at the chunk's base index, then the
-// product of the chunk-constant factors by a shuffle tree in warp 0.
-__device__ __forceinline__ void diag_hoist(const DiagBatch& b, const double2 (*lut)[1 << kMaxTargets], uint64_t chunk_base_idx,
-                                           DiagHoist& h)
+// kernel start: LUTs to shared memory, this thread's partial selectors to `selt` (packed 8 bits per op)
+template <int THREADS>
+__device__ __forceinline__ void diag_prog_init(const DiagProg& p, DiagShared& sh, uint64_t tid_idx, uint32_t (&selt)[kMaxDiagOps / 4])
 {
-     __syncthreads();  // readers of the previous chunk's values are done
+     for (int i = threadIdx.x; i < p.n * (1 << kMaxTargets); i += THREADS)
+          sh.lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)] = p.lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)];
+#pragma unroll
+     for (int w = 0; w < kMaxDiagOps / 4; ++w) {
+          uint32_t v = 0;
+#pragma unroll
+          for (int b = 0; b < 4; ++b)
+               if (4 * w + b < p.n) v |= diag_select(p.slots[4 * w + b], tid_idx) << (8 * b);
+          selt[w] = v;
+     }
+}
+
+__device__ __forceinline__ uint32_t diag_selt(const uint32_t (&selt)[kMaxDiagOps / 4], int j)
+{
+     // j is uniform across the CTA: a 4-way select on registers, no local memory
+     const uint32_t w = (j < 4) ? selt[0] : (j < 8) ? selt[1] : (j < 12) ? selt[2] : selt[3];
+     return (w >> (8 * (j & 3))) & 0xffu;
+}
+
+// once per chunk (all threads call it): partial selectors at the chunk's base index and the product
+// of the CTA-uniform factors (shuffle tree in warp 0)
+__device__ __forceinline__ void diag_prog_chunk(const DiagProg& p, DiagShared& sh, uint64_t chunk_idx)
+{
+     __syncthreads();  // readers of the previous chunk's values are done (and the LUT fill is visible)
      if (threadIdx.x < 32) {
           const int j = threadIdx.x;
           double2 f = make_double2(1.0, 0.0);
-          if (j < b.n) {
-               const uint32_t sel = diag_select(b.slots[j], chunk_base_idx);
-               h.selh[j] = sel;
-               if (j >= b.n_lo) f = lut[j][sel];
+          if (j < p.n) {
+               const uint32_t sel = diag_select(p.slots[j], chunk_idx);
+               sh.selh[j] = sel;
+               if (j < p.n_s0a) f = sh.lut[j][sel];
           }
 #pragma unroll
           for (int o = kMaxDiagOps / 2; o > 0; o >>= 1) {
@@ -104,9 +125,31 @@ __device__ __forceinline__ void diag_hoist(const DiagBatch& b, const double2 (*l
                g.y = __shfl_xor_sync(0xffffffffu, f.y, o);
                f = cmul(f, g);
           }
-          if (j == 0) h.s_hi = f;
+          if (j == 0) sh.s_hi = f;
      }
      __syncthreads();
+}
+
+// product of the class-S0 factors for this thread in this chunk (two independent chains)
+__device__ __forceinline__ double2 diag_prog_s0(const DiagProg& p, const DiagShared& sh, const uint32_t (&selt)[kMaxDiagOps / 4])
+{
+     double2 s = sh.s_hi;
+     double2 r = make_double2(1.0, 0.0);
+     int j = p.n_s0a;
+     for (; j + 1 < p.n_s0; j += 2) {
+          s = cmul(s, sh.lut[j][sh.selh[j] | diag_selt(selt, j)]);
+          r = cmul(r, sh.lut[j + 1][sh.selh[j + 1] | diag_selt(selt, j + 1)]);
+     }
+     if (j < p.n_s0) s = cmul(s, sh.lut[j][sh.selh[j] | diag_selt(selt, j)]);
+     return cmul(s, r);
+}
+
+// multiply `s` by the class-S1 factors for element part u
+__device__ __forceinline__ double2 diag_prog_s1(const DiagProg& p, const DiagShared& sh, const uint32_t (&selt)[kMaxDiagOps / 4], int u,
+                                               double2 s)
+{
+     for (int j = p.n_s0; j < p.n_s0 + p.n_s1; ++j) s = cmul(s, sh.lut[j][sh.selh[j] | diag_selt(selt, j) | p.usel[j][u]]);
+     return s;
 }
 
 // 128-bit global accesses. Slabs are streamed once per pass: the loads skip L1

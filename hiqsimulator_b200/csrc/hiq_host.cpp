@@ -23,6 +23,13 @@ int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what)
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+static std::atomic<uint64_t> g_max_grid{0};
+uint64_t grid_cap(uint64_t natural)
+{
+     const uint64_t m = g_max_grid.load(std::memory_order_relaxed);
+     return (m != 0 && m < natural) ? m : natural;
+}
+
 }  // namespace hiq
 
 extern "C" const char* hiq_last_error(void) { return hiq::g_last_error.c_str(); }
@@ -36,4 +43,10 @@ extern "C" int hiq_device_count(void)
           return -1;
      }
      return n;
+}
+
+extern "C" int hiqk_debug_set_max_grid(int max_ctas)
+{
+     hiq::g_max_grid.store(max_ctas > 0 ? static_cast<uint64_t>(max_ctas) : 0, std::memory_order_relaxed);
+     return HIQ_OK;
 }

@@ -15,11 +15,15 @@ int set_error(int code, const std::string& msg);
 int check_launch(const char* what);
 int check_cuda(cudaError_t e, const char* what);
 void count_launch(unsigned n = 1);
+// grid-size cap of the persistent kernels: `natural` unless hiqk_debug_set_max_grid() lowered it (tests use
+// that to drive the multi-iteration / prefetch paths on small slabs)
+uint64_t grid_cap(uint64_t natural);
 
-struct DiagBatch;
-// hiqk_diag_op[] (host, validated) -> kernel-side batch; defined in stream_kernels.cu
-int make_diag_batch(DiagBatch& b, int L, const hiqk_diag_op* ops, int n_ops, uint64_t varying_mask, uint64_t force_lo_mask,
-                    const char* who);
+struct DiagProg;
+// host builders of the batched-diagonal program (defined in stream_kernels.cu)
+int choose_u_positions(int L, const hiqk_diag_op* ops, int n_ops, uint64_t exclude, int want, int* out);
+int build_diag_prog(DiagProg& p, int L, const hiqk_diag_op* ops, int n_ops, const int* upos, int n_u, uint64_t target_mask,
+                    uint64_t tid_mask, int* order_out, const char* who);
 
 #define HIQ_CUDA(call)                                          \
      do {                                                       \

@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <complex>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,7 +22,7 @@ static unsigned stream_grid(uint64_t items, int per_thread = 4)
 {
      const uint64_t need = (items + static_cast<uint64_t>(kStreamThreads) * per_thread - 1) /
                            (static_cast<uint64_t>(kStreamThreads) * per_thread);
-     const uint64_t cap = static_cast<uint64_t>(kNumSMs) * 8 * 4;  // 8 CTAs/SM resident, 4 waves
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * 8 * 4);  // 8 CTAs/SM resident, 4 waves
      return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(need, cap)));
 }
 
@@ -70,42 +71,46 @@ __global__ void __launch_bounds__(kStreamThreads) diag_kernel(const __grid_const
 }
 
 // ----------------------------------------------------------------------------- batched diagonal gates
-// One HBM pass for up to kMaxDiagOps diagonal fused gates (see DiagBatch in hiq_device.cuh).
-// A CTA iteration covers kDiagChunk consecutive amplitudes; ops whose slots all lie above the chunk
-// cost one factor per chunk, the others one lookup + one complex multiply per amplitude.
-constexpr int kDiagPerThread = 16;
-constexpr uint64_t kDiagChunk = static_cast<uint64_t>(kStreamThreads) * kDiagPerThread;
+// One HBM pass for up to kMaxDiagOps diagonal fused gates (DiagProg, hiq_device.cuh).  Index =
+// (chunk bits | u bits | tid bits): tid = index bits 0..7 (one coalesced 4 KiB run per (chunk, u)),
+// the u positions are the index bits >= 8 that the ops touch least.
+struct DiagBatchParams {
+     double2* psi;
+     uint64_t n;         // amplitudes
+     uint64_t n_chunks;
+     int n_u;            // u bits in use
+     InsertBits ins;     // the u positions, ascending (zero bits inserted into chunk << 8)
+     uint64_t uoff[1 << kMaxUBits];
+     DiagProg prog;
+};
 
-__global__ void __launch_bounds__(kStreamThreads, 4) diag_batch_kernel(const __grid_constant__ DiagBatch b, double2* psi, uint64_t n)
+__global__ void __launch_bounds__(kStreamThreads, 4) diag_batch_kernel(const __grid_constant__ DiagBatchParams p)
 {
-     __shared__ double2 lut[kMaxDiagOps][1 << kMaxTargets];
-     __shared__ DiagHoist h;
-     for (int i = threadIdx.x; i < b.n * (1 << kMaxTargets); i += kStreamThreads)
-          lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)] = b.lut[i >> kMaxTargets][i & ((1 << kMaxTargets) - 1)];
-     const uint64_t n_chunks = (n + kDiagChunk - 1) / kDiagChunk;
-     for (uint64_t chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-          const uint64_t base = chunk * kDiagChunk;
-          diag_hoist(b, lut, base, h);  // also orders the LUT fill before its first use
-          const double2 s_hi = h.s_hi;
+     __shared__ DiagShared sh;
+     uint32_t selt[kMaxDiagOps / 4];
+     diag_prog_init<kStreamThreads>(p.prog, sh, threadIdx.x, selt);
+     const int nu = 1 << p.n_u;
+     for (uint64_t chunk = blockIdx.x; chunk < p.n_chunks; chunk += gridDim.x) {
+          const uint64_t cidx = insert_zero_bits(chunk << 8, p.ins);
+          diag_prog_chunk(p.prog, sh, cidx);
+          const double2 s0 = diag_prog_s0(p.prog, sh, selt);
+          const uint64_t base = cidx | threadIdx.x;
 #pragma unroll 1
-          for (int u0 = 0; u0 < kDiagPerThread; u0 += 4) {
+          for (int u0 = 0; u0 < nu; u0 += 4) {
                uint64_t idx[4];
                double2 v[4], f[4];
+               bool ok[4];
 #pragma unroll
                for (int u = 0; u < 4; ++u) {
-                    idx[u] = base + static_cast<uint64_t>(u0 + u) * kStreamThreads + threadIdx.x;
-                    if (idx[u] < n) v[u] = ldg_stream(psi + idx[u]);
-                    f[u] = s_hi;
+                    idx[u] = base | p.uoff[(u0 + u) & ((1 << kMaxUBits) - 1)];
+                    ok[u] = (u0 + u < nu) && idx[u] < p.n;
+                    if (ok[u]) v[u] = ldg_stream(p.psi + idx[u]);
                }
-               for (int j = 0; j < b.n_lo; ++j) {
-                    const uint32_t sh = h.selh[j];
-                    const int nl = b.n_lo_slots[j];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) f[u] = cmul(f[u], lut[j][sh | diag_select_lo(b.slots[j], nl, idx[u])]);
-               }
+               for (int u = 0; u < 4; ++u) f[u] = p.prog.n_s1 ? diag_prog_s1(p.prog, sh, selt, (u0 + u) & ((1 << kMaxUBits) - 1), s0) : s0;
 #pragma unroll
                for (int u = 0; u < 4; ++u)
-                    if (idx[u] < n) psi[idx[u]] = cmul(v[u], f[u]);
+                    if (ok[u]) p.psi[idx[u]] = cmul(v[u], f[u]);
           }
      }
 }
@@ -328,23 +333,36 @@ extern "C" int hiqk_apply_diag(void* slab, int L, int k, const int* slots, const
      return check_launch("diag_kernel");
 }
 
-// Validates `ops` and builds the kernel-side batch (shared with the dense pre-diagonal launcher).
-// varying_mask: index bits that change inside one chunk of the calling kernel; force_lo_mask: slots
-// that must be treated per element regardless (the dense targets).
-int hiq::make_diag_batch(DiagBatch& b, int L, const hiqk_diag_op* ops, int n_ops, uint64_t varying_mask, uint64_t force_lo_mask,
-                         const char* who)
+// Picks up to `want` index positions for the u part: positions < L outside `exclude`, the ones the ops
+// touch least first.  Returns how many were found (ascending order in `out`).
+int hiq::choose_u_positions(int L, const hiqk_diag_op* ops, int n_ops, uint64_t exclude, int want, int* out)
+{
+     int touches[64] = {0};
+     for (int j = 0; j < n_ops; ++j)
+          for (int l = 0; l < ops[j].k && l < kMaxTargets; ++l)
+               if (ops[j].slots[l] >= 0 && ops[j].slots[l] < 64) ++touches[ops[j].slots[l]];
+     std::vector<int> cand;
+     for (int pos = 0; pos < L; ++pos)
+          if (!((exclude >> pos) & 1ull)) cand.push_back(pos);
+     std::stable_sort(cand.begin(), cand.end(), [&](int a, int c) { return touches[a] < touches[c]; });
+     const int n = std::min<int>(want, static_cast<int>(cand.size()));
+     std::sort(cand.begin(), cand.begin() + n);
+     for (int i = 0; i < n; ++i) out[i] = cand[i];
+     return n;
+}
+
+// Validates `ops` and builds the kernel-side program.  upos[b] = index position of u bit b;
+// target_mask = dense targets (ops touching them become class E); tid_mask = index bits spelled by threadIdx.  order_out[j] = original index of
+// the op placed at position j.
+int hiq::build_diag_prog(DiagProg& p, int L, const hiqk_diag_op* ops, int n_ops, const int* upos, int n_u, uint64_t target_mask,
+                         uint64_t tid_mask, int* order_out, const char* who)
 {
      if (!ops || n_ops < 1 || n_ops > kMaxDiagOps)
           return set_error(HIQ_ERR_ARG, std::string(who) + ": need 1.." + std::to_string(kMaxDiagOps) + " diagonal ops");
-     std::memset(&b, 0, sizeof(b));
-     b.n = n_ops;
-     struct Tmp {
-          int k, n_lo;
-          int slots[kMaxTargets];
-          cplx lut[1 << kMaxTargets];
-          bool per_element;
-     };
-     std::vector<Tmp> tmp(n_ops);
+     std::memset(&p, 0, sizeof(p));
+     uint64_t umask = 0;
+     for (int b = 0; b < n_u; ++b) umask |= 1ull << upos[b];
+     std::vector<int> cls(n_ops);
      for (int j = 0; j < n_ops; ++j) {
           const hiqk_diag_op& o = ops[j];
           if (o.k < 0 || o.k > kMaxTargets) return set_error(HIQ_ERR_ARG, std::string(who) + ": diagonal op with k outside 0..5");
@@ -354,39 +372,30 @@ int hiq::make_diag_batch(DiagBatch& b, int L, const hiqk_diag_op* ops, int n_ops
                     return set_error(HIQ_ERR_ARG, std::string(who) + ": diagonal op slots must be distinct and < L");
                seen |= 1ull << o.slots[l];
           }
-          // new slot order: chunk-varying slots (ascending) first, then the rest (ascending)
-          Tmp& t = tmp[j];
-          t.k = o.k;
-          std::vector<int> order(o.k);
-          for (int l = 0; l < o.k; ++l) order[l] = l;
-          auto is_lo = [&](int l) { return ((varying_mask >> o.slots[l]) & 1ull) != 0; };
-          std::stable_sort(order.begin(), order.end(), [&](int a, int c) {
-               if (is_lo(a) != is_lo(c)) return is_lo(a);
-               return o.slots[a] < o.slots[c];
-          });
-          t.n_lo = 0;
-          for (int l = 0; l < o.k; ++l) {
-               t.slots[l] = o.slots[order[l]];
-               t.n_lo += is_lo(order[l]) ? 1 : 0;
-          }
-          const cplx* src = reinterpret_cast<const cplx*>(o.lut);
-          for (int e = 0; e < (1 << o.k); ++e) {
-               int old = 0;
-               for (int l = 0; l < o.k; ++l)
-                    if ((e >> l) & 1) old |= 1 << order[l];
-               t.lut[e] = src[old];
-          }
-          t.per_element = t.n_lo > 0 || (seen & force_lo_mask) != 0;
+          // 0: CTA-uniform per chunk, 1: per thread per chunk, 2: per element (u-dependent), 3: touches dense targets
+          cls[j] = (seen & target_mask) ? 3 : ((seen & umask) ? 2 : ((seen & tid_mask) ? 1 : 0));
      }
-     // per-element ops first
-     std::stable_sort(tmp.begin(), tmp.end(), [](const Tmp& a, const Tmp& c) { return a.per_element && !c.per_element; });
+     std::vector<int> order(n_ops);
+     for (int j = 0; j < n_ops; ++j) order[j] = j;
+     std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return cls[a] < cls[c]; });
+     p.n = n_ops;
      for (int j = 0; j < n_ops; ++j) {
-          const Tmp& t = tmp[j];
-          if (t.per_element) b.n_lo = j + 1;
-          b.n_lo_slots[j] = static_cast<uint8_t>(t.n_lo);
-          for (int l = 0; l < 8; ++l) b.slots[j][l] = l < t.k ? static_cast<uint8_t>(t.slots[l]) : 63;  // bit 63 is always 0
+          const hiqk_diag_op& o = ops[order[j]];
+          if (order_out) order_out[j] = order[j];
+          if (cls[order[j]] == 0) ++p.n_s0a;
+          if (cls[order[j]] <= 1) ++p.n_s0;
+          else if (cls[order[j]] == 2) ++p.n_s1;
+          else ++p.n_e;
+          for (int l = 0; l < 8; ++l) p.slots[j][l] = l < o.k ? static_cast<uint8_t>(o.slots[l]) : 63;  // bit 63 is always 0
+          for (int u = 0; u < (1 << n_u); ++u) {
+               uint32_t sel = 0;
+               for (int l = 0; l < o.k; ++l)
+                    for (int b = 0; b < n_u; ++b)
+                         if (o.slots[l] == upos[b] && ((u >> b) & 1)) sel |= 1u << l;
+               p.usel[j][u] = static_cast<uint8_t>(sel);
+          }
           // entries beyond 2^k are never selected (their selector bits read as 0)
-          std::memcpy(b.lut[j], t.lut, sizeof(cplx) << t.k);
+          std::memcpy(p.lut[j], o.lut, sizeof(double2) << o.k);
      }
      return HIQ_OK;
 }
@@ -394,13 +403,29 @@ int hiq::make_diag_batch(DiagBatch& b, int L, const hiqk_diag_op* ops, int n_ops
 extern "C" int hiqk_apply_diag_batch(void* slab, int L, const hiqk_diag_op* ops, int n_ops, void* stream)
 {
      if (!slab || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag_batch: bad argument");
-     DiagBatch b;
-     const int rc = make_diag_batch(b, L, ops, n_ops, kDiagChunk - 1, 0, "hiqk_apply_diag_batch");
+     if (!ops || n_ops < 1 || n_ops > kMaxDiagOps) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag_batch: need 1..16 diagonal ops");
+     static DiagBatchParams p;  // ~9 KB, launches are issued from one host thread per engine
+     static std::mutex mu;
+     std::lock_guard<std::mutex> lock(mu);
+     int upos[kMaxUBits];
+     const int n_u = choose_u_positions(L, ops, n_ops, 0xffull, kMaxUBits, upos);
+     const int rc = build_diag_prog(p.prog, L, ops, n_ops, upos, n_u, 0, 0xffull, nullptr, "hiqk_apply_diag_batch");
      if (rc != HIQ_OK) return rc;
-     const uint64_t n = 1ull << L;
-     const uint64_t n_chunks = (n + kDiagChunk - 1) / kDiagChunk;
-     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_chunks, static_cast<uint64_t>(kNumSMs) * 4 * 8));
-     diag_batch_kernel<<<grid, kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(b, static_cast<double2*>(slab), n);
+     p.psi = static_cast<double2*>(slab);
+     p.n = 1ull << L;
+     p.n_u = n_u;
+     p.n_chunks = L > 8 + n_u ? 1ull << (L - 8 - n_u) : 1;
+     std::memset(&p.ins, 0, sizeof(p.ins));
+     p.ins.n = n_u;
+     for (int b = 0; b < n_u; ++b) p.ins.pos[b] = static_cast<uint8_t>(upos[b]);
+     for (int u = 0; u < (1 << kMaxUBits); ++u) {
+          uint64_t o = 0;
+          for (int b = 0; b < n_u; ++b)
+               if ((u >> b) & 1) o |= 1ull << upos[b];
+          p.uoff[u] = o;
+     }
+     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_chunks, grid_cap(static_cast<uint64_t>(kNumSMs) * 4 * 8)));
+     diag_batch_kernel<<<grid, kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
      count_launch();
      return check_launch("diag_batch_kernel");
 }

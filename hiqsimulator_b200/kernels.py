@@ -160,6 +160,11 @@ def swap_unpack(state, slots, pat, begin, count, buf):
     check(lib().hiqk_swap_unpack(p, L, len(slots), _ints(slots), pat, begin, count, C.c_void_p(buf.data_ptr()), _stream()))
 
 
+def debug_set_max_grid(max_ctas: int) -> None:
+    """cap the grid of the persistent kernels (0 = natural): lets small slabs take the multi-iteration paths"""
+    check(lib().hiqk_debug_set_max_grid(int(max_ctas)))
+
+
 def microbench(what: int, iters: int = 5) -> float:
     out = C.c_double(0.0)
     check(lib().hiqk_microbench(what, iters, C.byref(out)))

@@ -149,6 +149,10 @@ int hiqk_microbench(int what, int iters, double* out_value);
 #define HIQK_MB_DFMA_TFLOPS 1
 #define HIQK_MB_DMMA_TFLOPS 2
 
+/* Test hook: cap the grid of the persistent kernels at `max_ctas` CTAs (0 = natural size) so that small slabs
+ * exercise the multi-iteration and prefetch paths that large slabs take. */
+int hiqk_debug_set_max_grid(int max_ctas);
+
 /* Number of kernels launched by this library in the calling process (bench evidence). */
 uint64_t hiqk_launch_count(void);
 

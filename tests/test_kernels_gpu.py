@@ -185,6 +185,74 @@ def test_apply_dense_prediag(k, slots, n_pre):
     assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
 
 
+@pytest.fixture
+def tiny_grid():
+    """3 CTAs only: every persistent kernel iterates many times per CTA (the path 2^30+ slabs take)"""
+    from hiqsimulator_b200 import kernels as K
+    K.debug_set_max_grid(3)
+    yield
+    K.debug_set_max_grid(0)
+
+
+@pytest.mark.parametrize("k,slots,ctrl", [(3, (4, 5, 6), 0), (3, (13, 6, 2), "one"), (4, (5, 2, 9, 12), 0), (4, (10, 11, 12, 13), "three"),
+                                          (4, (4, 8, 6, 10), "one"), (2, (3, 9), 0), (5, (9, 10, 11, 12, 13), 0)])
+def test_apply_dense_multi_iteration(tiny_grid, k, slots, ctrl):
+    """grid-stride / cp.async-staged paths: each thread processes many tuples"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 16
+    ref = rand_state(L, 90 + k)
+    m = rand_matrix(k, 17 * k)
+    cm = _ctrl_mask(L, slots, ctrl, 3)
+    for variant in (K.AUTO, K.DIRECT, K.TILED):
+        dev = torch.from_numpy(ref.copy()).cuda()
+        K.apply_dense(dev, list(slots), m, cm, variant)
+        exp = ref.copy()
+        statevec.apply_dense(exp, list(slots), m, cm)
+        assert np.abs(dev.cpu().numpy() - exp).max() <= TOL, variant
+
+
+@pytest.mark.parametrize("k,slots", [(2, (3, 9)), (3, (13, 6, 2)), (4, (5, 2, 9, 12)), (4, (12, 13, 14, 15)), (4, (4, 8, 6, 10))])
+@pytest.mark.parametrize("n_pre", [1, 5, 16])
+def test_apply_dense_prediag_multi_iteration(tiny_grid, k, slots, n_pre):
+    """folded diagonals with many chunks per CTA (per-chunk hoisting + prefetch across chunk boundaries)"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 17
+    ref = rand_state(L, 170 + k)
+    m = rand_matrix(k, 5 * k + n_pre)
+    ops = _rand_diag_ops(L, n_pre, 300 * k + n_pre)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_dense_prediag(dev, list(slots), m, ops)
+    K.apply_diag_batch(dev, ops[:max(1, n_pre // 2)])
+    ref2 = ref
+    for sl, d in ops:
+        if sl:
+            statevec.apply_diag(ref2, sl, d, 0)
+        else:
+            ref2 *= d[0]
+    statevec.apply_dense(ref2, list(slots), m, 0)
+    for sl, d in ops[:max(1, n_pre // 2)]:
+        if sl:
+            statevec.apply_diag(ref2, sl, d, 0)
+        else:
+            ref2 *= d[0]
+    assert np.abs(dev.cpu().numpy() - ref2).max() <= TOL
+
+
+def test_streaming_kernels_multi_iteration(tiny_grid):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 15
+    ref = rand_state(L, 5)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    d = np.exp(1j * np.linspace(0, 3, 8))
+    K.apply_diag(dev, [1, 7, 12], d, 1 << 4)
+    statevec.apply_diag(ref, [1, 7, 12], d, 1 << 4)
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+    assert abs(K.prob_masked(dev, 0b101, 0b001) - float((np.abs(ref[(np.arange(1 << L) & 0b101) == 1]) ** 2).sum())) <= TOL
+
+
 def test_dense_prediag_rejects_low_slots():
     from hiqsimulator_b200 import kernels as K
     assert not K.dense_prediag_supported(14, (0, 5, 6, 7))

@@ -29,3 +29,12 @@ for _ in range(args.reps):
     K.apply_dense(state, [0, 9, 17, 25], u4, 0, K.TILED)
 torch.cuda.synchronize()
 print("ok", K.prob_masked(state))
+# folded-diagonal launches (QFT-like: one op overlapping two targets + 11 chunk-constant ops)
+tg = [L - 8, L - 7, L - 6, L - 5]
+hi = [s for s in range(12, L) if s not in tg]
+ops = [([tg[0], tg[1], 3, 15], d4)] + [([int(x) for x in rng.choice(hi, size=4, replace=False)], d4) for _ in range(11)]
+for _ in range(args.reps):
+    K.apply_dense_prediag(state, tg, u4, ops)
+    K.apply_diag_batch(state, ops[1:])
+torch.cuda.synchronize()
+print("ok2", K.prob_masked(state))
