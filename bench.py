@@ -436,7 +436,12 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "circuit_seconds": {"device_only": ms_per_step * 1e-3, "host_schedule_s": shape["host_schedule_s"],
                                 "end_to_end": e2e["seconds_per_step"] if e2e else None},
-            "swap_nvlink_gbs_per_gpu": swap_gbs, "kernel_breakdown": breakdown,
+            "swap_nvlink_gbs_per_gpu": swap_gbs,
+            "swap_transport": {"peer_mapped_in_place": int(stats1["swaps_p2p"] - stats0["swaps_p2p"]),
+                               "staged_nccl": int(stats1["swaps_staged"] - stats0["swaps_staged"]),
+                               "nvlink_peak_gbs_per_dir": 900.0,
+                               "frac_of_nvlink": (swap_gbs / 900.0) if swap_gbs else None},
+            "kernel_breakdown": breakdown,
             "host_enqueue_seconds_per_step": t_host / args.steps,
         }
         print(json.dumps(line))

@@ -53,6 +53,8 @@ _SIGNATURES = {
     "hiqk_compact_bit": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _u64, _vp]),
     "hiqk_swap_pack": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _u64, _u64, _u64, _vp, _vp]),
     "hiqk_swap_unpack": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _u64, _u64, _u64, _vp, _vp]),
+    "hiqk_swap_p2p": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _ip, C.POINTER(_u64), _u64, C.POINTER(_u64),
+                               C.POINTER(_u64), _vp]),
     "hiqk_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
     "hiqk_launch_count": (_u64, []),
     "hiqk_debug_set_max_grid": (C.c_int, [C.c_int]),

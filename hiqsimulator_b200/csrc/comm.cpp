@@ -45,6 +45,10 @@ int Comm::init(int rank, int world_size, const void* unique_id, int device)
           int rc = nccl_load();
           if (rc != HIQ_OK) return rc;
      }
+     // bind the descriptor socket BEFORE the NCCL rendezvous: once CommInitRank returns, every rank's socket exists
+     if (fds_.open(std::string(static_cast<const char*>(unique_id), 128), rank) != HIQ_OK) {
+          // not fatal: the swap falls back to the staged NCCL exchange
+     }
      HIQ_NCCL(nccl().CommInitRank(&comm_, world_size, id, rank));
      HIQ_CUDA(cudaMalloc(&stage_, kStageBytes));
      return HIQ_OK;

@@ -10,6 +10,8 @@
 #include <cstdint>
 #include <vector>
 
+#include "peer_ipc.hpp"
+
 namespace hiq {
 
 class Comm {
@@ -32,6 +34,11 @@ public:
      int rank() const { return rank_; }
      int size() const { return size_; }
      ncclComm_t handle() const { return comm_; }
+     // descriptor channel to the peer processes (opened with the communicator; world size > 1 only)
+     FdChannel& fds() { return fds_; }
+     // engines of this process created so far on this communicator: the slab generation ("epoch") that the
+     // peer-mapping handshake tags its messages with (all ranks create their engines in the same order)
+     uint64_t next_epoch() { return ++epoch_; }
 
      // host-value collectives (values staged through a small device buffer on `stream`)
      int allreduce_sum(double* vals, int n, cudaStream_t stream);
@@ -44,6 +51,8 @@ private:
      int size_ = 1;
      ncclComm_t comm_ = nullptr;
      double* stage_ = nullptr;  // 4 KiB device staging
+     FdChannel fds_;
+     uint64_t epoch_ = 0;
 };
 
 }  // namespace hiq

@@ -2,6 +2,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <unistd.h>
+
+#include <cstdlib>
 #include <cstring>
 #include <sstream>
 
@@ -67,11 +70,17 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
      rng_ = std::bind(dist, std::ref(rnd_eng_));
      if (!dry_run_) {
           cu(check_cuda(cudaSetDevice(device_), "cudaSetDevice"));
-          cu(slab_.init(device_, 1ull << max_local_));
+          cu(slab_.init(device_, 1ull << max_local_, world_size > 1));
+          if (const char* m = std::getenv("HIQ_SWAP_MODE")) {
+               if (!std::strcmp(m, "staged") || !std::strcmp(m, "nccl")) swap_mode_ = 1;
+               else if (!std::strcmp(m, "p2p")) swap_mode_ = 2;
+          }
+          if (const char* m = std::getenv("HIQ_SWAP_P2P_MIN_SLOT")) min_p2p_slot_ = std::atoi(m);
           cu(check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           cu(check_cuda(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           comm_p_ = Comm::shared(rank, world_size, nccl_id, device_);
           if (!comm_p_) throw EngineError(HIQ_ERR_CUDA, hiq_last_error());
+          epoch_ = comm_p_->next_epoch();
           cu(check_cuda(cudaMalloc(&workspace_, hiqk_workspace_bytes()), "cudaMalloc workspace"));
           cu(check_cuda(cudaMalloc(&d_vals_, 64 * sizeof(double)), "cudaMalloc"));
           cu(slab_.ensure(1));
@@ -823,6 +832,175 @@ void Engine::swap_qubits(const std::vector<Index>& pairs)
 
 void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slots)
 {
+     // Two transports for the same transposition:
+     //   peer-mapped  one kernel per GPU swaps the pairs in place through NVLink loads/stores, no staging and
+     //                no extra HBM passes; its accesses are runs of 2^(lowest swapped slot) amplitudes
+     //   staged       pack -> NCCL send/recv -> unpack pipeline; contiguous messages whatever the slots
+     const int lowest = *std::min_element(slots.begin(), slots.end());
+     const bool want_p2p = swap_mode_ == 2 || (swap_mode_ == 0 && lowest >= min_p2p_slot_);
+     if (want_p2p && !p2p_broken_ && exchange_p2p(gpos, slots)) return;
+     if (swap_mode_ == 2) fail(std::string("SwapQubits(): peer-mapped exchange unavailable: ") + hiq_last_error());
+     exchange_staged(gpos, slots);
+}
+
+void Engine::group_barrier(const std::vector<int>& peer_ranks)
+{
+     // stream-ordered barrier among the swap group: a 1-element send/recv with every peer completes
+     // only after the peer's stream has reached the same point
+     double* buf = d_vals_ + 16;
+     nccl().GroupStart();
+     for (size_t k = 0; k < peer_ranks.size(); ++k) {
+          nccl().Send(buf, 1, ncclDouble, peer_ranks[k], comm_p_->handle(), stream_);
+          nccl().Recv(buf + 1 + k, 1, ncclDouble, peer_ranks[k], comm_p_->handle(), stream_);
+     }
+     ncclResult_t r = nccl().GroupEnd();
+     if (r != ncclSuccess) throw EngineError(HIQ_ERR_CUDA, std::string("ncclGroupEnd: ") + nccl().GetErrorString(r));
+}
+
+bool Engine::map_peers(const std::vector<int>& peer_ranks)
+{
+     // Handshake: send every group peer the chunks of my slab it has not seen yet, and map the chunks the
+     // peers send me.  Slabs grow in lock-step on all ranks (allocation is collective), so a peer's view is
+     // complete when it has as many chunks as my own slab.
+     FdChannel& ch = comm_p_->fds();
+     if (!ch.is_open()) {
+          set_error(HIQ_ERR_RUNTIME, "descriptor channel is not open");
+          return false;
+     }
+     if (peer_views_.empty()) peer_views_.resize(world_);
+     struct Out {
+          int rank;
+          size_t index;
+     };
+     std::vector<Out> outbox;
+     for (int pr: peer_ranks) {
+          PeerView& v = peer_views_[pr];
+          for (size_t i = v.sent; i < slab_.n_chunks(); ++i) outbox.push_back({pr, i});
+     }
+     auto complete = [&] {
+          for (int pr: peer_ranks)
+               if (peer_views_[pr].slab.n_chunks() < slab_.n_chunks()) return false;
+          return true;
+     };
+     auto receive_one = [&](int timeout_ms) -> bool {
+          FdMessage m;
+          if (ch.recv_fd(m, timeout_ms) != HIQ_OK) return false;
+          if (m.src_rank < 0 || m.src_rank >= world_) {
+               ::close(m.fd);
+               set_error(HIQ_ERR_RUNTIME, "peer ipc: message from an unknown rank");
+               return false;
+          }
+          PeerView& v = peer_views_[m.src_rank];
+          if (m.epoch != epoch_) {  // a message of another engine generation: not for this slab
+               ::close(m.fd);
+               return true;
+          }
+          if (!v.slab.data()) {
+               if (v.slab.init(device_, slab_.reserved_bytes()) != HIQ_OK) {
+                    ::close(m.fd);
+                    return false;
+               }
+               v.slab.epoch = m.epoch;
+          }
+          if (m.index != v.slab.n_chunks()) {
+               ::close(m.fd);
+               set_error(HIQ_ERR_RUNTIME, "peer ipc: chunk arrived out of order");
+               return false;
+          }
+          return v.slab.map_next_chunk(m.fd, m.size) == HIQ_OK;
+     };
+     size_t next = 0;
+     const auto t0 = Clock::now();
+     while (next < outbox.size() || !complete()) {
+          if (seconds_since(t0) > 60.0) {
+               set_error(HIQ_ERR_RUNTIME, "peer ipc: handshake timed out");
+               return false;
+          }
+          if (next < outbox.size()) {
+               const Out& o = outbox[next];
+               FdMessage m;
+               m.index = static_cast<uint32_t>(o.index);
+               m.total = static_cast<uint32_t>(slab_.n_chunks());
+               m.size = slab_.chunk_bytes(o.index);
+               m.epoch = epoch_;
+               if (slab_.export_chunk(o.index, &m.fd) != HIQ_OK) return false;
+               const int rc = ch.send_fd(o.rank, m, 0 /* do not wait: drain my own queue instead */);
+               ::close(m.fd);
+               if (rc == HIQ_OK) {
+                    peer_views_[o.rank].sent = o.index + 1;
+                    ++next;
+                    continue;
+               }
+               // the peer's queue is full (or it is not there yet): make progress on my side, then retry
+               if (!complete()) receive_one(5);
+               continue;
+          }
+          if (!receive_one(20000)) return false;
+     }
+     return true;
+}
+
+bool Engine::exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& slots)
+{
+     const int L = static_cast<int>(locals_.size());
+     const int q = static_cast<int>(gpos.size());
+     if (q > 3) {
+          set_error(HIQ_ERR_RUNTIME, "more than 3 swapped pairs");
+          return false;
+     }
+     std::vector<int> order(q);
+     for (int i = 0; i < q; ++i) order[i] = i;
+     std::sort(order.begin(), order.end(), [&](int a, int b) { return slots[a] < slots[b]; });
+     auto pattern_of = [&](int r) {
+          uint64_t pat = 0;
+          for (int j = 0; j < q; ++j)
+               if ((r >> gpos[order[j]]) & 1) pat |= 1ull << j;
+          return pat;
+     };
+     std::vector<int> peer_ranks;
+     for (int x = 1; x < (1 << q); ++x) {
+          int pr = rank_;
+          for (int i = 0; i < q; ++i)
+               if ((x >> i) & 1) pr ^= 1 << gpos[i];
+          peer_ranks.push_back(pr);
+     }
+     // The handshake runs only when some view is incomplete — a condition that is the same on every rank,
+     // because slabs grow in lock-step — and its outcome is agreed on by the whole world, so that either
+     // all ranks take the peer-mapped path or all fall back to the staged one.
+     bool stale = peer_views_.empty();
+     for (int pr: peer_ranks)
+          if (!stale && (peer_views_[pr].sent < slab_.n_chunks() || peer_views_[pr].slab.n_chunks() < slab_.n_chunks())) stale = true;
+     if (stale) {
+          double failed = map_peers(peer_ranks) ? 0.0 : 1.0;
+          const std::string why = failed != 0.0 ? hiq_last_error() : "";
+          cu(comm_p_->allreduce_sum(&failed, 1, stream_));
+          if (failed != 0.0) {
+               p2p_broken_ = true;
+               set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not map the slabs" : why);
+               return false;
+          }
+     }
+     const uint64_t n = 1ull << (L - q);
+     const uint64_t half = (n + 1) / 2;
+     std::vector<void*> ptrs;
+     std::vector<uint64_t> pats, begins, counts;
+     for (int pr: peer_ranks) {
+          ptrs.push_back(peer_views_[pr].slab.data());
+          pats.push_back(pattern_of(pr));
+          begins.push_back(rank_ < pr ? 0 : half);  // the lower rank of a pair takes the lower half of the free indices
+          counts.push_back(rank_ < pr ? half : n - half);
+     }
+     group_barrier(peer_ranks);  // every peer has finished the gates before its slab is touched
+     cu(hiqk_swap_p2p(slab_.data(), ptrs.data(), static_cast<int>(ptrs.size()), L, q, slots.data(), pats.data(), pattern_of(rank_),
+                      begins.data(), counts.data(), stream_));
+     group_barrier(peer_ranks);  // ... and nobody moves on while a peer still writes into its slab
+     stats_.swap_bytes_sent += static_cast<double>(peer_ranks.size()) * n * sizeof(double2);
+     ++stats_.swaps_p2p;
+     return true;
+}
+
+void Engine::exchange_staged(const std::vector<int>& gpos, const std::vector<int>& slots)
+{
      // Net effect: transpose global-index bit (L + gpos_i) with bit slot_i.
      // Peer p differs from this rank in a non-empty subset of the swapped global bits; the
      // amplitudes whose swapped slots spell p's bits go to p and are replaced, in place, by p's
@@ -900,6 +1078,7 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
      }
      unpack_piece(n_pieces - 1);
      stats_.swap_bytes_sent += static_cast<double>(n_peers) * chunk * sizeof(double2);
+     ++stats_.swaps_staged;
 }
 
 }  // namespace hiq

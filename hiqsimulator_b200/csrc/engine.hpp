@@ -43,6 +43,7 @@ struct EngineStats {
      uint64_t dense_passes = 0, diag_passes = 0, scale_passes = 0, skipped_passes = 0;
      double runs_s = 0, swaps_s = 0, measures_s = 0, allocs_s = 0, deallocs_s = 0;
      double swap_bytes_sent = 0;
+     uint64_t swaps_p2p = 0, swaps_staged = 0;
      double h2d_bytes = 0, d2h_bytes = 0;
      uint64_t gate_launches = 0;  // device launches that carried the dense/diag/scale passes above
 };
@@ -114,6 +115,10 @@ private:
      void deallocate_global(Index id);
      void swap_qubits(const std::vector<Index>& pairs);
      void exchange(const std::vector<int>& gpos, const std::vector<int>& slots);
+     void exchange_staged(const std::vector<int>& gpos, const std::vector<int>& slots);  // pack -> NCCL send/recv -> unpack
+     bool exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& slots);     // in place over peer-mapped slabs
+     bool map_peers(const std::vector<int>& peer_ranks);
+     void group_barrier(const std::vector<int>& peer_ranks);
      void masks(const std::vector<Index>& ids, const std::vector<bool>& bits, const char* what, uint64_t& lm, uint64_t& lv,
                 uint64_t& gm, uint64_t& gv) const;
      double probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
@@ -144,6 +149,16 @@ private:
      void* swap_buf_ = nullptr;   // staging for the exchange (send | recv)
      size_t swap_buf_bytes_ = 0;
      cudaEvent_t swap_events_[4] = {nullptr, nullptr, nullptr, nullptr};  // packed[2], exchanged[2]
+     // peer-mapped slabs (NVLink P2P): views of the other ranks' slabs and how many of my chunks each has been sent
+     struct PeerView {
+          PeerSlab slab;
+          size_t sent = 0;
+     };
+     std::vector<PeerView> peer_views_;
+     uint64_t epoch_ = 0;
+     int swap_mode_ = 0;        // 0 auto, 1 staged NCCL only, 2 peer-mapped only
+     bool p2p_broken_ = false;  // the handshake failed once: stay on the staged path
+     int min_p2p_slot_ = 0;     // lowest swapped slot for which the in-place kernel is used in auto mode
      int dense_variant_ = 0;
 
      EngineStats stats_;

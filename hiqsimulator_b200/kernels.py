@@ -160,6 +160,17 @@ def swap_unpack(state, slots, pat, begin, count, buf):
     check(lib().hiqk_swap_unpack(p, L, len(slots), _ints(slots), pat, begin, count, C.c_void_p(buf.data_ptr()), _stream()))
 
 
+def swap_p2p(local, peers, slots, peer_pats, my_pat, begins, counts):
+    """in-place exchange of `local` with the peer slabs (torch tensors; on one GPU they simply are other buffers)"""
+    p, L = _slab(local)
+    n = len(peers)
+    ptrs = (C.c_void_p * n)(*[t.data_ptr() for t in peers])
+    pats = (C.c_uint64 * n)(*[int(x) for x in peer_pats])
+    b = (C.c_uint64 * n)(*[int(x) for x in begins])
+    c = (C.c_uint64 * n)(*[int(x) for x in counts])
+    check(lib().hiqk_swap_p2p(p, ptrs, n, L, len(slots), _ints(slots), pats, int(my_pat), b, c, _stream()))
+
+
 def debug_set_max_grid(max_ctas: int) -> None:
     """cap the grid of the persistent kernels (0 = natural): lets small slabs take the multi-iteration paths"""
     check(lib().hiqk_debug_set_max_grid(int(max_ctas)))

@@ -142,6 +142,14 @@ int hiqk_swap_pack(const void* slab, int L, int q, const int* slots, uint64_t pa
 int hiqk_swap_unpack(void* slab, int L, int q, const int* slots, uint64_t pat, uint64_t begin,
                      uint64_t count, const void* src, void* stream);
 
+/* In-place exchange over peer-mapped slabs (one launch per GPU, no staging): for every free index f in
+ * [begin[k], begin[k]+count[k]) and peer k, swap  local[deposit(f) | spread(peer_pats[k])]  with
+ * peer_slabs[k][deposit(f) | spread(my_pat)]  (patterns over the sorted swapped slots, as in hiqk_swap_pack).
+ * The two GPUs of a pair must be given complementary ranges.  Replaces pack + mpi::all_to_all + unpack
+ * (reference: SwapperMT.cpp:30-126) when the peers' slabs are mapped into this process (NVLink P2P). */
+int hiqk_swap_p2p(void* local, void* const* peer_slabs, int n_peers, int L, int q, const int* slots,
+                  const uint64_t* peer_pats, uint64_t my_pat, const uint64_t* begin, const uint64_t* count, void* stream);
+
 /* Micro-benchmarks used by bench.py to state the roofline denominators next to the
  * kernels: device copy GB/s, FP64 FMA TFLOP/s (DFMA) and FP64 tensor TFLOP/s (DMMA). */
 int hiqk_microbench(int what, int iters, double* out_value);
@@ -231,6 +239,7 @@ typedef struct hiq_stats {
      uint64_t dense_passes, diag_passes, scale_passes, skipped_passes;
      double runs_s, swaps_s, measures_s, allocs_s, deallocs_s;
      double swap_bytes_sent;
+     uint64_t swaps_p2p, swaps_staged; /* exchanges done in place over peer-mapped slabs / through the staged NCCL pipeline */
      double h2d_bytes, d2h_bytes; /* host<->device traffic issued by the engine (descriptor payloads, results) */
      uint64_t gate_launches;      /* device launches that carried the dense/diag/scale passes (<= their sum) */
 } hiq_stats;

@@ -342,3 +342,41 @@ def test_swap_pack_unpack(slots):
         got = dev.cpu().numpy()
         assert np.abs(got[sel2] - ref[sel]).max() == 0
         dev = torch.from_numpy(ref.copy()).cuda()
+
+
+@pytest.mark.parametrize("slots", [(13,), (0,), (5, 12), (1, 0), (11, 3, 7), (0, 1, 2), (12, 13, 11)])
+@pytest.mark.parametrize("grid", [0, 2])
+def test_swap_p2p_in_place(slots, grid):
+    """the peer-mapped in-place exchange == transposing index bit (L + gpos_j) with bit slots[j]
+    (virtual ranks = separate buffers on one GPU; on a multi-GPU box the peers are NVLink-mapped slabs)"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L, q = 14, len(slots)
+    R = 1 << q
+    rng = np.random.default_rng(sum(slots) + q)
+    full = rng.normal(size=R << L) + 1j * rng.normal(size=R << L)
+    ranks = [torch.from_numpy(full[r << L:(r + 1) << L].copy()).cuda() for r in range(R)]
+    order = sorted(range(q), key=lambda j: slots[j])  # pair indices by ascending slot
+
+    def pat(r):  # bit j' of the pattern <-> j'-th lowest swapped slot <-> gpos of that pair
+        return sum(((r >> order[j]) & 1) << j for j in range(q))
+    n = 1 << (L - q)
+    half = (n + 1) // 2
+    K.debug_set_max_grid(grid)
+    try:
+        for r in range(R):
+            peers = [p for p in range(R) if p != r]
+            begins = [0 if r < p else half for p in peers]
+            counts = [half if r < p else n - half for p in peers]
+            K.swap_p2p(ranks[r], [ranks[p] for p in peers], list(slots), [pat(p) for p in peers], pat(r), begins, counts)
+        torch.cuda.synchronize()
+    finally:
+        K.debug_set_max_grid(0)
+    got = np.concatenate([t.cpu().numpy() for t in ranks])
+    idx = np.arange(R << L, dtype=np.int64)
+    src = idx.copy()
+    for j in range(q):
+        hi, lo = L + j, slots[j]
+        bh, bl = (src >> hi) & 1, (src >> lo) & 1
+        src = src & ~((1 << hi) | (1 << lo)) | (bl << hi) | (bh << lo)
+    assert np.array_equal(got, full[src])
