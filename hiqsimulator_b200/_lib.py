@@ -32,6 +32,17 @@ class DiagOp(C.Structure):
     _fields_ = [("k", C.c_int), ("slots", C.c_int * 5), ("lut", C.c_double * 64)]
 
 
+class PauliTerm(C.Structure):
+    """hiqk_pauli_term of include/hiq_b200.h"""
+    _fields_ = [("zmask", C.c_uint64), ("re", C.c_double), ("im", C.c_double)]
+
+
+class Perm(C.Structure):
+    """hiqk_perm of include/hiq_b200.h"""
+    _fields_ = [("kind", C.c_int), ("n_bits", C.c_int), ("pos", C.c_int * 40), ("ctrl_mask", C.c_uint64),
+                ("a", C.c_uint64), ("N", C.c_uint64), ("table", C.c_void_p)]
+
+
 _SIGNATURES = {
     "hiq_last_error": (C.c_char_p, []),
     "hiq_version": (C.c_char_p, []),
@@ -55,6 +66,10 @@ _SIGNATURES = {
     "hiqk_swap_unpack": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _u64, _u64, _u64, _vp, _vp]),
     "hiqk_swap_p2p": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _ip, C.POINTER(_u64), _u64, C.POINTER(_u64),
                                C.POINTER(_u64), _vp]),
+    "hiqk_pauli_expect": (C.c_int, [_vp, C.c_int, _u64, C.POINTER(PauliTerm), C.c_int, _vp, _u64, _u64, _vp, _vp, _vp]),
+    "hiqk_pauli_apply": (C.c_int, [_vp, C.c_int, _u64, C.POINTER(PauliTerm), C.c_int, _vp, C.c_int, _vp, _u64, _u64, _vp]),
+    "hiqk_permute_gather": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.POINTER(Perm), _vp]),
+    "hiq_modinv": (C.c_int, [_u64, _u64, C.POINTER(_u64)]),
     "hiqk_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
     "hiqk_launch_count": (_u64, []),
     "hiqk_debug_set_max_grid": (C.c_int, [C.c_int]),

@@ -41,19 +41,33 @@ class SimulatorMPI:
         return self._simulator.cheat_local()
 
     def cheat(self):
-        """(id2pos, full state vector) — concatenation of the rank slabs (reference: :348-380)."""
-        id2pos, vec = self.cheat_local()
-        rank, world = _M.world()[:2]
-        if world == 1:
+        """(id2pos, full state vector) — concatenation of the rank slabs on every rank (reference: :348-380 does an
+        MPI Allgather of cheat_local; here the engine gathers over NCCL)."""
+        if hasattr(self._simulator, "cheat"):
+            id2pos, vec = self._simulator.cheat()
             return id2pos, np.asarray(vec)
-        import torch
-        import torch.distributed as dist
-        t = torch.from_numpy(np.ascontiguousarray(vec)).view(torch.float64)
-        if dist.get_backend() == "nccl":
-            t = t.cuda()
-        parts = [torch.empty_like(t) for _ in range(world)]
-        dist.all_gather(parts, t)
-        return id2pos, np.concatenate([p.cpu().numpy().view(np.complex128) for p in parts])
+        return self.cheat_local()  # single-rank stand-ins (the compiled reference, the numpy oracle)
+
+    # reference: _simulator_mpi.py:148-223 — qubit_operator is a list of (term, coefficient) with
+    # term = sequence of (index into qureg, 'X'|'Y'|'Z') (a projectq QubitOperator's .terms.items())
+    @staticmethod
+    def _terms(qubit_operator, num_qubits):
+        items = qubit_operator.terms.items() if hasattr(qubit_operator, "terms") else qubit_operator
+        operator = [(list(term), coeff) for (term, coeff) in items]
+        for term, _ in operator:
+            if len(term) and max(t[0] for t in term) >= num_qubits:
+                raise Exception("qubit_operator acts on more qubits than contained in the qureg.")
+        return operator
+
+    def get_expectation_value(self, qubit_operator, qureg):
+        return self._simulator.get_expectation_value(self._terms(qubit_operator, len(qureg)), list(qureg))
+
+    def apply_qubit_operator(self, qubit_operator, qureg):
+        return self._simulator.apply_qubit_operator(self._terms(qubit_operator, len(qureg)), list(qureg))
+
+    def set_wavefunction(self, wavefunction, qureg):
+        """reference: _simulator_mpi.py:279-305"""
+        self._simulator.set_wavefunction(np.asarray(wavefunction, dtype=np.complex128), list(qureg))
 
     def get_qubits_ids(self):
         return self._simulator.get_qubits_ids()
@@ -86,6 +100,18 @@ class SimulatorMPI:
             self._simulator.allocate_qureg(list(cmd.qubits), cmd.init)
         elif cmd.kind == ops.DEALLOCATE:
             self._simulator.deallocate_qubit(cmd.qubits[0])
+        elif cmd.kind == ops.MATH:  # reference: the BasicMathGate branch, _simulator_mpi.py:459-468
+            ctrls = list(cmd.controls)
+            if cmd.math[0] == "fn":
+                self._simulator.emulate_math(cmd.math[1], [list(qr) for qr in cmd.quregs], ctrls)
+            elif cmd.math[0] == "add":
+                self._simulator.emulate_math_add_constant(cmd.math[1], list(cmd.quregs[0]), ctrls)
+            elif cmd.math[0] == "add_mod":
+                self._simulator.emulate_math_add_constant_modN(cmd.math[1], cmd.math[2], list(cmd.quregs[0]), ctrls)
+            elif cmd.math[0] == "mul_mod":
+                self._simulator.emulate_math_multiply_by_constant_modN(cmd.math[1], cmd.math[2], list(cmd.quregs[0]), ctrls)
+            else:
+                raise Exception("unknown math gate %r" % (cmd.math,))
         elif cmd.kind == ops.GATE and len(cmd.matrix) <= 2 ** 5:
             if not 2 ** len(cmd.qubits) == len(cmd.matrix):
                 raise Exception("Simulator: Error applying {} gate: {}-qubit gate applied to {} qubits.".format(

@@ -99,3 +99,41 @@ def inverse(cmds):
     for c in reversed(cmds):
         out.append(Gate(c.matrix.conj().T, list(c.qubits), list(c.controls), name=c.name + "^", is_z=c.is_z))
     return out
+
+
+def run_shor(eng, N: int, a: int, n: int | None = None, verbose: bool = False):
+    """C5: the quantum subroutine of Shor's algorithm as the reference example runs it
+    (reference: examples/shor_mpi.py:45-105): an n-qubit register |1>, one phase-estimation qubit, 2n rounds of
+    H / controlled MultiplyByConstantModN(a^(2^(2n-1-k)) mod N) / conditional R / H / Measure / conditional X.
+    The reference decomposes the multiplication through projectq.libs.math (2n+3 qubits with ancillas); here it is
+    emulated by the engine (ops.MultiplyByConstantModN -> emulate_math), so the circuit needs n + 1 qubits.
+    `eng` is a HiQMainEngine.  Returns (candidate period r, the 2n measured bits)."""
+    from fractions import Fraction
+
+    from . import ops
+    if n is None:
+        n = int(math.ceil(math.log(N, 2)))
+    x = eng.allocate_qureg(n)
+    eng.receive([Gate(G.X, [x[0]], name="X")])
+    measurements = [0] * (2 * n)
+    ctrl = eng.allocate_qubit()
+    for k in range(2 * n):
+        current_a = pow(a, 1 << (2 * n - 1 - k), N)
+        cmds = [Gate(G.H, [ctrl], name="H"), ops.MultiplyByConstantModN(current_a, N, x, [ctrl])]
+        for i in range(k):
+            if measurements[i]:
+                cmds.append(Gate(G.R(-math.pi / (1 << (k - i))), [ctrl], name="R"))
+        cmds.append(Gate(G.H, [ctrl], name="H"))
+        cmds.append(ops.Measure([ctrl]))
+        eng.receive(cmds)
+        eng.flush()
+        measurements[k] = int(eng.measurements[ctrl])
+        if measurements[k]:
+            eng.receive([Gate(G.X, [ctrl], name="X")])
+        if verbose:
+            print(measurements[k], end="", flush=True)
+    eng.receive([ops.Measure(list(x))])
+    eng.flush()
+    y = sum(measurements[2 * n - 1 - i] * 1.0 / (1 << (i + 1)) for i in range(2 * n))
+    r = Fraction(y).limit_denominator(N - 1).denominator
+    return r, measurements

@@ -173,6 +173,86 @@ int hiq_cheat_local(hiq_engine* e, int64_t* ids, int* pos, int cap, int* n_map, 
      });
 }
 
+int hiq_cheat(hiq_engine* e, int64_t* ids, int* pos, int cap, int* n_map, void* host_dst, uint64_t cap_amps, uint64_t* n_amps)
+{
+     NEED(e);
+     return guarded([&] {
+          auto m = e->impl.id2pos();
+          if (n_map) *n_map = static_cast<int>(m.size());
+          if (ids && pos) {
+               if (cap < static_cast<int>(m.size())) throw EngineError(HIQ_ERR_ARG, "hiq_cheat: map buffer too small");
+               int i = 0;
+               for (auto& kv: m) {
+                    ids[i] = kv.first;
+                    pos[i] = kv.second;
+                    ++i;
+               }
+          }
+          if (n_amps) *n_amps = static_cast<uint64_t>(e->impl.world_size()) << e->impl.local_qubits();
+          if (host_dst) e->impl.gather_state_to_host(host_dst, cap_amps);
+     });
+}
+
+static std::vector<Engine::PauliTerm> pauli_terms(const int* term_offsets, const int* factor_index, const char* factor_pauli,
+                                                  const double* coefs, int n_terms)
+{
+     if (n_terms < 0 || (n_terms > 0 && (!term_offsets || !coefs))) throw EngineError(HIQ_ERR_ARG, "qubit operator: null argument");
+     std::vector<Engine::PauliTerm> terms(n_terms);
+     for (int t = 0; t < n_terms; ++t) {
+          if (term_offsets[t + 1] < term_offsets[t]) throw EngineError(HIQ_ERR_ARG, "qubit operator: term offsets must ascend");
+          if (term_offsets[t + 1] > term_offsets[t] && (!factor_index || !factor_pauli))
+               throw EngineError(HIQ_ERR_ARG, "qubit operator: null factor arrays");
+          for (int f = term_offsets[t]; f < term_offsets[t + 1]; ++f) terms[t].factors.emplace_back(factor_index[f], factor_pauli[f]);
+          terms[t].coef = cplx(coefs[2 * t], coefs[2 * t + 1]);
+     }
+     return terms;
+}
+
+int hiq_get_expectation_value(hiq_engine* e, const int* term_offsets, const int* factor_index, const char* factor_pauli,
+                              const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids, double* out)
+{
+     NEED(e);
+     if (!out) return set_error(HIQ_ERR_ARG, "hiq_get_expectation_value: null output");
+     return guarded([&] {
+          *out = e->impl.get_expectation_value(pauli_terms(term_offsets, factor_index, factor_pauli, coefs_re_im, n_terms), vec_ids(ids, n_ids));
+     });
+}
+
+int hiq_apply_qubit_operator(hiq_engine* e, const int* term_offsets, const int* factor_index, const char* factor_pauli,
+                             const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids)
+{
+     NEED(e);
+     return guarded([&] {
+          e->impl.apply_qubit_operator(pauli_terms(term_offsets, factor_index, factor_pauli, coefs_re_im, n_terms), vec_ids(ids, n_ids));
+     });
+}
+
+int hiq_set_wavefunction(hiq_engine* e, const double* amps_re_im, uint64_t n_amps, const int64_t* ids, int n_ids)
+{
+     NEED(e);
+     return guarded([&] { e->impl.set_wavefunction(reinterpret_cast<const cplx*>(amps_re_im), n_amps, vec_ids(ids, n_ids)); });
+}
+
+int hiq_emulate_math_table(hiq_engine* e, const uint64_t* table, uint64_t table_len, const int64_t* reg_ids, int n_reg,
+                           const int64_t* ctrls, int n_ctrls)
+{
+     NEED(e);
+     if (!table) return set_error(HIQ_ERR_ARG, "hiq_emulate_math_table: null table");
+     return guarded([&] {
+          e->impl.emulate_math(HIQK_PERM_TABLE, 0, 0, std::vector<uint64_t>(table, table + table_len), vec_ids(reg_ids, n_reg),
+                               vec_ids(ctrls, n_ctrls));
+     });
+}
+
+int hiq_emulate_math_const(hiq_engine* e, int kind, uint64_t a, uint64_t N, const int64_t* reg_ids, int n_reg, const int64_t* ctrls,
+                           int n_ctrls)
+{
+     NEED(e);
+     if (kind != HIQK_PERM_ADD && kind != HIQK_PERM_ADD_MOD && kind != HIQK_PERM_MUL_MOD)
+          return set_error(HIQ_ERR_ARG, "hiq_emulate_math_const: kind must be HIQK_PERM_ADD, _ADD_MOD or _MUL_MOD");
+     return guarded([&] { e->impl.emulate_math(kind, a, N, {}, vec_ids(reg_ids, n_reg), vec_ids(ctrls, n_ctrls)); });
+}
+
 int hiq_local_slab(hiq_engine* e, void** dev_ptr, int* L)
 {
      NEED(e);

@@ -940,6 +940,31 @@ bool Engine::map_peers(const std::vector<int>& peer_ranks)
      return true;
 }
 
+bool Engine::ensure_peer_views(const std::vector<int>& peer_ranks)
+{
+     // The handshake runs only when some view is incomplete — a condition that is the same on every rank,
+     // because slabs grow in lock-step — and its outcome is agreed on by the whole world, so that either
+     // all ranks take the peer-mapped path or all fall back (swap: staged exchange; emulate_math: error).
+     if (p2p_broken_) {
+          set_error(HIQ_ERR_RUNTIME, "peer-mapped slabs are unavailable in this process group");
+          return false;
+     }
+     bool stale = peer_views_.empty();
+     for (int pr: peer_ranks)
+          if (!stale && (peer_views_[pr].sent < slab_.n_chunks() || peer_views_[pr].slab.n_chunks() < slab_.n_chunks())) stale = true;
+     if (stale) {
+          double failed = map_peers(peer_ranks) ? 0.0 : 1.0;
+          const std::string why = failed != 0.0 ? hiq_last_error() : "";
+          cu(comm_p_->allreduce_sum(&failed, 1, stream_));
+          if (failed != 0.0) {
+               p2p_broken_ = true;
+               set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not map the slabs" : why);
+               return false;
+          }
+     }
+     return true;
+}
+
 bool Engine::exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& slots)
 {
      const int L = static_cast<int>(locals_.size());
@@ -964,22 +989,7 @@ bool Engine::exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& 
                if ((x >> i) & 1) pr ^= 1 << gpos[i];
           peer_ranks.push_back(pr);
      }
-     // The handshake runs only when some view is incomplete — a condition that is the same on every rank,
-     // because slabs grow in lock-step — and its outcome is agreed on by the whole world, so that either
-     // all ranks take the peer-mapped path or all fall back to the staged one.
-     bool stale = peer_views_.empty();
-     for (int pr: peer_ranks)
-          if (!stale && (peer_views_[pr].sent < slab_.n_chunks() || peer_views_[pr].slab.n_chunks() < slab_.n_chunks())) stale = true;
-     if (stale) {
-          double failed = map_peers(peer_ranks) ? 0.0 : 1.0;
-          const std::string why = failed != 0.0 ? hiq_last_error() : "";
-          cu(comm_p_->allreduce_sum(&failed, 1, stream_));
-          if (failed != 0.0) {
-               p2p_broken_ = true;
-               set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not map the slabs" : why);
-               return false;
-          }
-     }
+     if (!ensure_peer_views(peer_ranks)) return false;
      const uint64_t n = 1ull << (L - q);
      const uint64_t half = (n + 1) / 2;
      std::vector<void*> ptrs;

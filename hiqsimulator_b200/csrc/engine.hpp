@@ -98,6 +98,21 @@ public:
      void clear_trace() { trace_.clear(); }
      void set_dense_variant(int v) { dense_variant_ = v; }
 
+     // ---- operator-level calls of the reference wrapper that the reference class lacks (engine_ops.cpp;
+     // reference call sites: _simulator_mpi.py:180-183, 220-223, 305, 459-468, 377-380; semantics: ProjectQ simulator.hpp)
+     struct PauliTerm {
+          std::vector<std::pair<int, char>> factors;  // (index into ids, 'X' | 'Y' | 'Z'), applied in this order
+          cplx coef;
+     };
+     double get_expectation_value(const std::vector<PauliTerm>& terms, const std::vector<Index>& ids);
+     void apply_qubit_operator(const std::vector<PauliTerm>& terms, const std::vector<Index>& ids);
+     void set_wavefunction(const cplx* amps, uint64_t n_amps, const std::vector<Index>& ordering);
+     // kind = HIQK_PERM_*; fwd_table (TABLE only) = f(v) for every value of the concatenated registers
+     void emulate_math(int kind, uint64_t a, uint64_t N, const std::vector<uint64_t>& fwd_table, const std::vector<Index>& reg_ids,
+                       const std::vector<Index>& ctrls);
+     // cheat(): every rank receives the concatenation of all rank slabs (world * 2^L amplitudes, rank-major)
+     void gather_state_to_host(void* dst, uint64_t cap_amps);
+
 private:
      static constexpr Index kNone = -1;  // empty global slot (reference: kNotFound_ stored in an int64)
      using Clock = std::chrono::steady_clock;
@@ -118,6 +133,15 @@ private:
      void exchange_staged(const std::vector<int>& gpos, const std::vector<int>& slots);  // pack -> NCCL send/recv -> unpack
      bool exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& slots);     // in place over peer-mapped slabs
      bool map_peers(const std::vector<int>& peer_ranks);
+     bool ensure_peer_views(const std::vector<int>& peer_ranks);  // world-agreed: all ranks succeed or all fail
+     struct PauliGroup {
+          uint64_t lx = 0;  // flip mask over local slots
+          int gx = 0;       // flip mask over rank bits: the source amplitudes live on rank ^ gx
+          std::vector<hiqk_pauli_term> terms;
+     };
+     std::vector<PauliGroup> pauli_groups(const std::vector<PauliTerm>& terms, const std::vector<Index>& ids, const char* what) const;
+     void exchange_piece(int partner, uint64_t begin, uint64_t count, double2* staging);
+     double2* ensure_staging(uint64_t amps);
      void group_barrier(const std::vector<int>& peer_ranks);
      void masks(const std::vector<Index>& ids, const std::vector<bool>& bits, const char* what, uint64_t& lm, uint64_t& lv,
                 uint64_t& gm, uint64_t& gv) const;

@@ -6,6 +6,9 @@
 //   * the MPI world is replaced by one process per GPU; `init_world(rank, world_size, nccl_id,
 //     device)` plays the role of MPI_Init (world size 1 needs no call);
 //   * `cheat_local()` returns the local slab as a numpy complex128 array instead of a Python list;
+//   * the methods the reference wrapper calls but the reference binding never exported
+//     (`get_expectation_value`, `apply_qubit_operator`, `set_wavefunction`), a working `emulate_math`
+//     (the reference's throws) with closed forms of ProjectQ's math gates, and `cheat()`;
 //   * extra helpers: `synchronize`, `stats`, `local_slab_ptr`, descriptor trace accessors.
 #include <pybind11/complex.h>
 #include <pybind11/numpy.h>
@@ -103,9 +106,119 @@ public:
           check(hiq_apply_controlled_gate(e_, reinterpret_cast<const double*>(m.data()), static_cast<int>(m.shape(0)), q.data(),
                                           static_cast<int>(q.size()), ctrls.data(), static_cast<int>(ctrls.size())));
      }
-     void emulate_math(py::function, const std::vector<std::vector<unsigned>>&, const std::vector<int64_t>&)
+     // emulate_math(f, quregs, ctrls) (reference binding: _cppsim_mpi.cpp:42-59,75; the reference engine throws,
+     // SimulatorMPI.hpp:217-225).  f maps the list of register values to the list of new values (ProjectQ's
+     // BasicMathGate.get_math_function); it is tabulated once on the host — the device applies the permutation.
+     void emulate_math(py::function f, const std::vector<std::vector<int64_t>>& quregs, const std::vector<int64_t>& ctrls)
      {
-          throw std::runtime_error("SimulatorMPI::emulate_math() is not supported");
+          std::vector<int64_t> reg_ids;
+          for (auto& qr: quregs) reg_ids.insert(reg_ids.end(), qr.begin(), qr.end());
+          if (reg_ids.empty() || reg_ids.size() > 22)
+               throw std::runtime_error("emulate_math(): a Python function can be tabulated over at most 22 register qubits; "
+                                        "use emulate_math_add_constant / _add_constant_modN / _multiply_by_constant_modN");
+          const uint64_t space = 1ull << reg_ids.size();
+          std::vector<uint64_t> table(space);
+          for (uint64_t v = 0; v < space; ++v) {
+               py::list args;
+               unsigned shift = 0;
+               for (auto& qr: quregs) {
+                    args.append(py::int_((v >> shift) & ((1ull << qr.size()) - 1ull)));
+                    shift += static_cast<unsigned>(qr.size());
+               }
+               py::object res = f(args);
+               py::sequence out = py::reinterpret_borrow<py::sequence>(res);
+               if (static_cast<size_t>(py::len(out)) != quregs.size())
+                    throw std::runtime_error("emulate_math(): the function must return one value per register");
+               uint64_t w = 0;
+               shift = 0;
+               for (size_t r = 0; r < quregs.size(); ++r) {
+                    // Python integers of any sign and size: keep the low bits of the two's complement
+                    const py::int_ mask((1ull << quregs[r].size()) - 1ull);
+                    const uint64_t val = py::cast<uint64_t>(py::int_(out[r]).attr("__and__")(mask));
+                    w |= val << shift;
+                    shift += static_cast<unsigned>(quregs[r].size());
+               }
+               table[v] = w;
+          }
+          py::gil_scoped_release nogil;
+          check(hiq_emulate_math_table(e_, table.data(), space, reg_ids.data(), static_cast<int>(reg_ids.size()), ctrls.data(),
+                                       static_cast<int>(ctrls.size())));
+     }
+     // ProjectQ's math gates in closed form (projectq.libs.math: AddConstant, AddConstantModN, MultiplyByConstantModN)
+     void emulate_math_add_constant(int64_t a, const std::vector<int64_t>& qureg, const std::vector<int64_t>& ctrls)
+     {
+          check(hiq_emulate_math_const(e_, HIQK_PERM_ADD, static_cast<uint64_t>(a), 0, qureg.data(), static_cast<int>(qureg.size()),
+                                       ctrls.data(), static_cast<int>(ctrls.size())));
+     }
+     void emulate_math_add_constant_modN(int64_t a, uint64_t N, const std::vector<int64_t>& qureg, const std::vector<int64_t>& ctrls)
+     {
+          if (N == 0) throw std::runtime_error("emulate_math(): the modulus must be positive");
+          const int64_t n = static_cast<int64_t>(N);
+          const uint64_t ar = static_cast<uint64_t>(((a % n) + n) % n);
+          check(hiq_emulate_math_const(e_, HIQK_PERM_ADD_MOD, ar, N, qureg.data(), static_cast<int>(qureg.size()), ctrls.data(),
+                                       static_cast<int>(ctrls.size())));
+     }
+     void emulate_math_multiply_by_constant_modN(uint64_t a, uint64_t N, const std::vector<int64_t>& qureg,
+                                                 const std::vector<int64_t>& ctrls)
+     {
+          check(hiq_emulate_math_const(e_, HIQK_PERM_MUL_MOD, a, N, qureg.data(), static_cast<int>(qureg.size()), ctrls.data(),
+                                       static_cast<int>(ctrls.size())));
+     }
+     using Term = std::vector<std::pair<int, char>>;
+     using TermsDict = std::vector<std::pair<Term, cplx>>;
+     struct FlatTerms {
+          std::vector<int> offsets{0}, index;
+          std::vector<char> pauli;
+          std::vector<double> coefs;
+          explicit FlatTerms(const TermsDict& td)
+          {
+               for (auto& t: td) {
+                    for (auto& f: t.first) {
+                         index.push_back(f.first);
+                         pauli.push_back(f.second);
+                    }
+                    offsets.push_back(static_cast<int>(index.size()));
+                    coefs.push_back(t.second.real());
+                    coefs.push_back(t.second.imag());
+               }
+          }
+     };
+     // the wrapper's call shapes (reference: _simulator_mpi.py:180-183, 220-223, 304-305)
+     double get_expectation_value(const TermsDict& td, const std::vector<int64_t>& ids)
+     {
+          FlatTerms f(td);
+          double out = 0.0;
+          py::gil_scoped_release nogil;
+          check(hiq_get_expectation_value(e_, f.offsets.data(), f.index.data(), f.pauli.data(), f.coefs.data(), static_cast<int>(td.size()),
+                                          ids.data(), static_cast<int>(ids.size()), &out));
+          return out;
+     }
+     void apply_qubit_operator(const TermsDict& td, const std::vector<int64_t>& ids)
+     {
+          FlatTerms f(td);
+          py::gil_scoped_release nogil;
+          check(hiq_apply_qubit_operator(e_, f.offsets.data(), f.index.data(), f.pauli.data(), f.coefs.data(), static_cast<int>(td.size()),
+                                         ids.data(), static_cast<int>(ids.size())));
+     }
+     void set_wavefunction(py::array_t<cplx, py::array::c_style | py::array::forcecast> wf, const std::vector<int64_t>& ids)
+     {
+          check(hiq_set_wavefunction(e_, reinterpret_cast<const double*>(wf.data()), static_cast<uint64_t>(wf.size()), ids.data(),
+                                     static_cast<int>(ids.size())));
+     }
+     // cheat(): (id -> bit position, the concatenation of every rank's slab) on every rank
+     // (reference: _simulator_mpi.py:348-380 does this with mpi4py on top of cheat_local)
+     py::tuple cheat()
+     {
+          int n_map = 0;
+          uint64_t n_amps = 0;
+          check(hiq_cheat(e_, nullptr, nullptr, 0, &n_map, nullptr, 0, &n_amps));
+          std::vector<int64_t> idv(n_map);
+          std::vector<int> posv(n_map);
+          py::array_t<cplx> vec(static_cast<py::ssize_t>(n_amps));
+          check(hiq_cheat(e_, idv.data(), posv.data(), n_map, &n_map, vec.mutable_data(), n_amps, &n_amps));
+          py::dict d;
+          for (int i = 0; i < n_map; ++i) d[py::int_(idv[i])] = posv[i];
+          return py::make_tuple(d, vec);
      }
      cplx get_amplitude(const std::vector<bool>& bits, const std::vector<int64_t>& q)
      {
@@ -279,6 +392,13 @@ PYBIND11_MODULE(_cppsim_mpi, m)
          .def("apply_controlled_gate", &SimulatorB200::apply_controlled_gate)
          .def("apply_controlled_matrix", &SimulatorB200::apply_controlled_matrix)
          .def("emulate_math", &SimulatorB200::emulate_math)
+         .def("emulate_math_add_constant", &SimulatorB200::emulate_math_add_constant)
+         .def("emulate_math_add_constant_modN", &SimulatorB200::emulate_math_add_constant_modN)
+         .def("emulate_math_multiply_by_constant_modN", &SimulatorB200::emulate_math_multiply_by_constant_modN)
+         .def("get_expectation_value", &SimulatorB200::get_expectation_value)
+         .def("apply_qubit_operator", &SimulatorB200::apply_qubit_operator)
+         .def("set_wavefunction", &SimulatorB200::set_wavefunction)
+         .def("cheat", &SimulatorB200::cheat)
          .def("get_amplitude", &SimulatorB200::get_amplitude)
          .def("get_probability", &SimulatorB200::get_probability)
          .def("run", &SimulatorB200::run)

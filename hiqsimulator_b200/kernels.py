@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from ._lib import DiagOp, check, lib
+from ._lib import DiagOp, PauliTerm, Perm, check, lib
 
 AUTO, DIRECT, TILED, DMMA = 0, 1, 2, 3
 
@@ -169,6 +169,54 @@ def swap_p2p(local, peers, slots, peer_pats, my_pat, begins, counts):
     b = (C.c_uint64 * n)(*[int(x) for x in begins])
     c = (C.c_uint64 * n)(*[int(x) for x in counts])
     check(lib().hiqk_swap_p2p(p, ptrs, n, L, len(slots), _ints(slots), pats, int(my_pat), b, c, _stream()))
+
+
+def _pauli_terms(terms):
+    """terms: [(zmask, coefficient), ...] -> ctypes array of hiqk_pauli_term"""
+    arr = (PauliTerm * len(terms))()
+    for o, (z, c) in zip(arr, terms):
+        c = complex(c)
+        o.zmask, o.re, o.im = int(z), c.real, c.imag
+    return arr
+
+
+def pauli_expect(state, xmask, terms, src=None, begin=0, count=None) -> complex:
+    """sum_i conj(state[i ^ xmask]) F(i) S[i] over [begin, begin+count); S = src (a staged partner slab) or state"""
+    import torch
+    p, L = _slab(state)
+    count = state.numel() - begin if count is None else count
+    out = torch.empty(2, dtype=torch.float64, device=state.device)
+    check(lib().hiqk_pauli_expect(p, L, int(xmask), _pauli_terms(terms), len(terms),
+                                  C.c_void_p(src.data_ptr()) if src is not None else None, begin, count,
+                                  C.c_void_p(out.data_ptr()), C.c_void_p(_workspace(state.device).data_ptr()), _stream()))
+    re, im = out.cpu().tolist()
+    return complex(re, im)
+
+
+def pauli_apply(state, xmask, terms, acc=None, accumulate=False, src=None, begin=0, count=None):
+    """acc None: state <- P state in place; else acc[i ^ xmask] (+)= F(i) S[i] over [begin, begin+count)"""
+    p, L = _slab(state)
+    count = state.numel() - begin if count is None else count
+    check(lib().hiqk_pauli_apply(p, L, int(xmask), _pauli_terms(terms), len(terms),
+                                 C.c_void_p(acc.data_ptr()) if acc is not None else None, int(bool(accumulate)),
+                                 C.c_void_p(src.data_ptr()) if src is not None else None, begin, count, _stream()))
+
+
+PERM_TABLE, PERM_ADD, PERM_ADD_MOD, PERM_MUL_MOD = 0, 1, 2, 3
+
+
+def permute_gather(dst, slabs, rank, kind, pos, ctrl_mask=0, a=0, N=0, table=None):
+    """dst <- gather of rank `rank` through the inverse register map; slabs = one tensor per rank (or None);
+    a, N are the FORWARD constants, table (torch int32/uint32 tensor on the device) the INVERSE map"""
+    p, L = _slab(dst)
+    n = len(slabs)
+    ptrs = (C.c_void_p * n)(*[(t.data_ptr() if t is not None else None) for t in slabs])
+    d = Perm()
+    d.kind, d.n_bits, d.ctrl_mask, d.a, d.N = int(kind), len(pos), int(ctrl_mask), int(a), int(N)
+    for b, q in enumerate(pos):
+        d.pos[b] = int(q)
+    d.table = table.data_ptr() if table is not None else None
+    check(lib().hiqk_permute_gather(p, ptrs, n, int(rank), L, C.byref(d), _stream()))
 
 
 def debug_set_max_grid(max_ctas: int) -> None:

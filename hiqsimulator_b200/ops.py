@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-GATE, ALLOCATE, ALLOCATE_QUREG, DEALLOCATE, MEASURE, FLUSH, METASWAP = range(7)
+GATE, ALLOCATE, ALLOCATE_QUREG, DEALLOCATE, MEASURE, FLUSH, METASWAP, MATH = range(8)
 
 
 @dataclass
@@ -23,11 +23,14 @@ class Command:
     name: str = ""
     init: complex = 0                               # ALLOCATE_QUREG initial amplitude
     is_z: bool = False                              # ZGate (target/control roles may be exchanged)
+    quregs: list = field(default_factory=list)      # MATH: one id list per register
+    math: tuple = ()                                # MATH: ("add", a) | ("add_mod", a, N) | ("mul_mod", a, N) | ("fn", callable)
 
     @property
     def fast_forwarding(self) -> bool:
-        """ProjectQ FastForwardingGate family: Measure, Flush, Deallocate, MetaSwap."""
-        return self.kind in (MEASURE, FLUSH, DEALLOCATE, METASWAP)
+        """ProjectQ FastForwardingGate family: Measure, Flush, Deallocate, MetaSwap.  Math gates are emulated on
+        the whole state (reference call site: _simulator_mpi.py:459-468), so everything pending runs first."""
+        return self.kind in (MEASURE, FLUSH, DEALLOCATE, METASWAP, MATH)
 
 
 def Gate(matrix, qubits, controls=(), name="", is_z=False):
@@ -56,3 +59,26 @@ def Flush():
 
 def MetaSwap(pairs):
     return Command(METASWAP, list(pairs), name="MetaSwap")
+
+
+# ProjectQ's math gates (projectq.libs.math: AddConstant, AddConstantModN, MultiplyByConstantModN and the generic
+# BasicMathGate), emulated by the engine instead of being decomposed into adders (reference: the wrapper's
+# BasicMathGate branch, _simulator_mpi.py:459-468, which the reference engine answers with "not supported")
+def AddConstant(a, qureg, controls=()):
+    return Command(MATH, [q for q in qureg], list(controls), name="AddConstant", quregs=[list(qureg)], math=("add", int(a)))
+
+
+def AddConstantModN(a, N, qureg, controls=()):
+    return Command(MATH, [q for q in qureg], list(controls), name="AddConstantModN", quregs=[list(qureg)],
+                   math=("add_mod", int(a), int(N)))
+
+
+def MultiplyByConstantModN(a, N, qureg, controls=()):
+    return Command(MATH, [q for q in qureg], list(controls), name="MultiplyByConstantModN", quregs=[list(qureg)],
+                   math=("mul_mod", int(a), int(N)))
+
+
+def BasicMath(fn, quregs, controls=()):
+    """fn maps the list of register values to the list of new values (BasicMathGate.get_math_function)"""
+    return Command(MATH, [q for qr in quregs for q in qr], list(controls), name="BasicMathGate",
+                   quregs=[list(qr) for qr in quregs], math=("fn", fn))

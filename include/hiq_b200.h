@@ -150,6 +150,49 @@ int hiqk_swap_unpack(void* slab, int L, int q, const int* slots, uint64_t pat, u
 int hiqk_swap_p2p(void* local, void* const* peer_slabs, int n_peers, int L, int q, const int* slots,
                   const uint64_t* peer_pats, uint64_t my_pat, const uint64_t* begin, const uint64_t* count, void* stream);
 
+/* ---- Pauli-operator passes ------------------------------------------------------------------
+ * The reference wrapper calls get_expectation_value / apply_qubit_operator on its C++ simulator
+ * (reference: hiq/projectq/backends/_sim/_simulator_mpi.py:180-183, 220-223) although the reference
+ * class exports neither (_cppsim_mpi.cpp:63-82); semantics = ProjectQ simulator.hpp.  A Pauli string
+ * acts as (P psi)[i ^ x] = i^{#Y} (-1)^{popcount(i & z)} psi[i]; the terms of an operator that share the
+ * flip mask x form one group with F(i) = sum_t c_t (-1)^{popcount(i & zmask_t)} (c_t carries i^{#Y}). */
+#define HIQK_MAX_PAULI_TERMS 64
+typedef struct hiqk_pauli_term {
+     uint64_t zmask; /* sign mask over the local slots (Z and Y factors) */
+     double re, im;  /* coefficient, times i^{#Y}, times the sign contributed by global qubits */
+} hiqk_pauli_term;
+/* d_out[0..1] = Re, Im of  sum_{i in [begin, begin+count)} conj(slab[i ^ xmask]) F(i) S[i],  S[i] = src[i - begin]
+ * (src != NULL: amplitudes of a partner GPU staged on this one) or slab[i].  src == NULL over the whole slab
+ * reads every amplitude once (pairs (i, i ^ xmask) are visited together).  workspace as for hiqk_prob_masked. */
+int hiqk_pauli_expect(const void* slab, int L, uint64_t xmask, const hiqk_pauli_term* terms, int n_terms, const void* src,
+                      uint64_t begin, uint64_t count, double* d_out, void* workspace, void* stream);
+/* acc == NULL: slab <- P slab in place over the whole slab, (P psi)[i ^ xmask] = F(i) psi[i] (src NULL, begin 0,
+ * count 2^L).  Otherwise acc[i ^ xmask] (+)= F(i) S[i] for i in [begin, begin+count) (accumulate != 0 adds). */
+int hiqk_pauli_apply(void* slab, int L, uint64_t xmask, const hiqk_pauli_term* terms, int n_terms, void* acc, int accumulate,
+                     const void* src, uint64_t begin, uint64_t count, void* stream);
+
+/* ---- register permutation (emulate_math) ------------------------------------------------------
+ * ProjectQ's emulate_math (simulator.hpp; the reference C++ class throws, SimulatorMPI.hpp:217-225,
+ * call site _simulator_mpi.py:459-468): basis states that satisfy the control mask have the value v of a
+ * register replaced by f(v).  The device pass is a gather through the inverse map:
+ *   dst[j] = slabs[s >> L][s & (2^L - 1)],  G = rank << L | j,  s = G with the register bits replaced by f^-1(v)
+ * where register bit b is index bit pos[b] (>= L: a global qubit, read from a peer-mapped slab). */
+#define HIQK_PERM_TABLE 0   /* f^-1 given as a device table of 2^n_bits uint32 entries */
+#define HIQK_PERM_ADD 1     /* f(v) = (v + a) mod 2^n_bits */
+#define HIQK_PERM_ADD_MOD 2 /* f(v) = (v + a) mod N for v < N, v otherwise */
+#define HIQK_PERM_MUL_MOD 3 /* f(v) = (a v) mod N for v < N, v otherwise; gcd(a, N) = 1, N <= 2^32 */
+typedef struct hiqk_perm {
+     int kind;
+     int n_bits;
+     int pos[40];
+     uint64_t ctrl_mask; /* over the global amplitude index */
+     uint64_t a, N;      /* the FORWARD constants; the launcher inverts them */
+     const uint32_t* table;
+} hiqk_perm;
+int hiqk_permute_gather(void* dst, const void* const* slabs, int n_slabs, int rank, int L, const hiqk_perm* perm, void* stream);
+/* a^-1 mod N (host helper; error when gcd(a, N) != 1) */
+int hiq_modinv(uint64_t a, uint64_t N, uint64_t* out);
+
 /* Micro-benchmarks used by bench.py to state the roofline denominators next to the
  * kernels: device copy GB/s, FP64 FMA TFLOP/s (DFMA) and FP64 tensor TFLOP/s (DMMA). */
 int hiqk_microbench(int what, int iters, double* out_value);
@@ -185,6 +228,14 @@ typedef struct hiq_engine hiq_engine;
 #define HIQ_DESC_SWAP 4
 #define HIQ_DESC_GROW 5
 #define HIQ_DESC_FILL 6
+/* operator-level passes: aux = [mode, flip mask over local slots, source rank, zmask_0 .. zmask_{k-1}], payload = the k
+ * coefficients; mode 0 = in place (APPLY) / sum (EXPECT), 1 = overwrite the accumulator, 2 = add to it */
+#define HIQ_DESC_PAULI_EXPECT 7
+#define HIQ_DESC_PAULI_APPLY 8
+#define HIQ_DESC_PAULI_COMMIT 9 /* slab <- accumulator */
+/* aux = [HIQK_PERM_*, a, N, ctrl mask over the global index, this rank takes part (0/1), pos_0 .. pos_{k-1}, inverse table] */
+#define HIQ_DESC_PERMUTE 10
+#define HIQ_DESC_LOAD 11 /* set_wavefunction: aux = [slice of the host vector this rank copies, -1 = zeros] */
 
 typedef struct hiq_descriptor {
      int kind;           /* HIQ_DESC_* */
@@ -224,6 +275,28 @@ int hiq_set_qubits_perm(hiq_engine* e, const int64_t* p, int n);                
  * (host_dst may be NULL to query sizes only; *n_amps = 2^L) */
 int hiq_cheat_local(hiq_engine* e, int64_t* ids, int* pos, int cap, int* n_map, void* host_dst, uint64_t cap_amps,
                     uint64_t* n_amps);
+/* cheat() (reference: _simulator_mpi.py:348-380, an MPI Allgather of the rank slabs): the same map as
+ * hiq_cheat_local and world_size * 2^L amplitudes, rank-major, on every rank (host_dst may be NULL to query sizes) */
+int hiq_cheat(hiq_engine* e, int64_t* ids, int* pos, int cap, int* n_map, void* host_dst, uint64_t cap_amps, uint64_t* n_amps);
+
+/* Operator-level calls the reference wrapper makes on its simulator object but the reference class never
+ * exported (reference: _simulator_mpi.py:180-183, 220-223, 305, 459-468).  Semantics: ProjectQ simulator.hpp.
+ * A Pauli operator is a list of n_terms terms; term t has the factors [term_offsets[t], term_offsets[t+1]):
+ * factor f acts with factor_pauli[f] in {'X','Y','Z'} on qubit ids[factor_index[f]]; coefs = (re, im) per term. */
+int hiq_get_expectation_value(hiq_engine* e, const int* term_offsets, const int* factor_index, const char* factor_pauli,
+                              const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids, double* out);
+int hiq_apply_qubit_operator(hiq_engine* e, const int* term_offsets, const int* factor_index, const char* factor_pauli,
+                             const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids);
+/* amps: 2^n_ids complex128 on the host (the whole vector on every rank); index bit i <-> ids[i] */
+int hiq_set_wavefunction(hiq_engine* e, const double* amps_re_im, uint64_t n_amps, const int64_t* ids, int n_ids);
+/* emulate_math with the function tabulated over the concatenated registers (reg_ids in bit order, register 0
+ * lowest): table[v] = f(v), 2^n_reg entries; must be a permutation */
+int hiq_emulate_math_table(hiq_engine* e, const uint64_t* table, uint64_t table_len, const int64_t* reg_ids, int n_reg,
+                           const int64_t* ctrls, int n_ctrls);
+/* closed forms of ProjectQ's math gates on one register: kind = HIQK_PERM_ADD / _ADD_MOD / _MUL_MOD */
+int hiq_emulate_math_const(hiq_engine* e, int kind, uint64_t a, uint64_t N, const int64_t* reg_ids, int n_reg,
+                           const int64_t* ctrls, int n_ctrls);
+
 /* device pointer of the local slab and L (zero-copy views; valid until the next (de)allocation) */
 int hiq_local_slab(hiq_engine* e, void** dev_ptr, int* L);
 int hiq_set_local_slab(hiq_engine* e, const void* host_src, uint64_t n_amps);

@@ -1,7 +1,9 @@
 """Rank body of the multi-process tests (launched with torch.distributed.run).
 
 usage: mp_worker.py <golden name> <mode>      mode = dry (CPU, gloo) | gpu (NCCL)
-Rank 0 compares the merged outputs with the golden fixture and exits non-zero on mismatch."""
+       mp_worker.py ops:<qubits>:<seed> <mode>   operator-level script (scripts.operator_script) checked against the
+                                                 numpy oracle instead of a golden fixture
+Rank 0 compares the merged outputs with the expectation and exits non-zero on mismatch."""
 import os
 import sys
 
@@ -19,9 +21,13 @@ def main():
     name, mode = sys.argv[1], sys.argv[2]
     from hiqsimulator_b200 import _cppsim_mpi as M
     from hiqsimulator_b200 import world
-    R, script, exp = load_golden(name)
     flags = M.FLAG_DRY_RUN if mode == "dry" else 0
     rank, size = world.init_world(flags)
+    if name.startswith("ops:"):
+        return operator_case(name, mode, M, world, rank, size)
+    if name.startswith("shor:"):
+        return shor_case(name, mode, M, world, rank, size)
+    R, script, exp = load_golden(name)
     assert size == R, (size, R)
     if mode == "dry":
         e = M.SimulatorMPI(*script[0][1:])
@@ -44,6 +50,75 @@ def main():
         if rank == 0:
             merged = scripts.merge_rank_outputs(gathered)
             scripts.assert_outputs_match(script, merged, exp)
+    world.barrier()
+    if rank == 0:
+        print("MP_WORKER_OK", name, mode)
+
+
+def shor_case(name, mode, M, world, rank, R):
+    """C5 at test size through the whole host pipeline (GreedyScheduler + backend): the measured bits and the
+    final state must equal the numpy oracle's driven by the same pipeline and seed."""
+    from hiqsimulator_b200 import backends, cengines, circuits
+    from oracle import statevec
+    assert mode == "gpu"
+    _, N, a, n, seed = name.split(":")
+    N, a, n, seed = int(N), int(a), int(n), int(seed)
+    L = n + 1 - (R.bit_length() - 1)
+
+    def run(backend_class):
+        be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=seed, num_local_qubits=L, max_fused_qubits=3, backend_class=backend_class)
+        eng = cengines.HiQMainEngine(be, [cengines.GreedyScheduler(cluster_size=3)])
+        r, bits = circuits.run_shor(eng, N, a, n)
+        return r, bits, [eng.measurements[q] for q in range(n + 1)], be
+    r, bits, final, be = run(None)
+    id2pos, full = be.cheat()
+    gathered = world.gather_objects((r, bits, final, np.asarray(full).copy(), dict(id2pos)))
+    if rank == 0:
+        r0, bits0, final0, be0 = run(lambda s, ml, mc: statevec.SimulatorMPI(s, ml, mc, R))
+        id2pos0, full0 = be0.cheat()
+        for g in gathered:
+            assert (g[0], g[1], g[2]) == (r0, bits0, final0), (g[:3], (r0, bits0, final0))
+            assert g[4] == id2pos0 and np.abs(g[3] - full0).max() <= 1e-12
+    world.barrier()
+    if rank == 0:
+        print("MP_WORKER_OK", name, mode)
+
+
+def operator_case(name, mode, M, world, rank, R):
+    _, nq, seed = name.split(":")
+    script = scripts.operator_script(int(nq), R, int(seed))
+    if mode == "dry":
+        stop = next(j for j, op in enumerate(script) if op[0] == "measure_qubits")
+        script = script[:stop]
+        e = M.SimulatorMPI(*script[0][1:])
+        loads = []
+        for op in script[1:]:
+            if op[0] in ("cheat_local", "get_probability"):
+                continue
+            if op[0] == "set_wavefunction":
+                loads.append(op[1])
+            scripts._dispatch(e, op)
+        gathered = world.gather_objects(e.trace())
+        if rank == 0:
+            exp = scripts.run_on_oracle(script, R)
+            state = scripts.replay_traces(gathered, R, {"loads": loads})
+            last = max(j for j, op in enumerate(script) if op[0] == "cheat_local")
+            assert np.abs(state - exp[last][1]).max() <= 1e-12
+    else:
+        keep = []
+        out = scripts.run_on_sim(M.SimulatorMPI, script, keep)
+        errors = [(j, script[j][0], o) for j, o in enumerate(out) if isinstance(o, tuple) and len(o) == 2 and o[0] == "error"]
+        assert not errors, errors[:3]
+        # cheat(): every rank holds the concatenation of all slabs
+        id2pos, full = keep[0].cheat()
+        last = max(j for j, op in enumerate(script) if op[0] == "cheat_local")
+        gathered = world.gather_objects((out, np.asarray(full).copy(), dict(id2pos)))
+        if rank == 0:
+            exp = scripts.run_on_oracle(script, R)
+            merged = scripts.merge_rank_outputs([g[0] for g in gathered])
+            scripts.assert_outputs_match(script, merged, exp)
+            for g in gathered:
+                assert np.array_equal(g[1], merged[last][1]) and g[2] == merged[last][0]
     world.barrier()
     if rank == 0:
         print("MP_WORKER_OK", name, mode)

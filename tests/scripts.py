@@ -130,7 +130,7 @@ def run_on_oracle(script, R):
                 id2pos, full = o.cheat()
                 out.append((id2pos, full.copy()))
             else:
-                out.append(getattr(o, op[0])(*op[1:]))
+                out.append(_dispatch(o, op))
         except RuntimeError as e:
             out.append(("error", str(e)))
     return out
@@ -153,20 +153,23 @@ def merge_rank_outputs(per_rank):
     return out
 
 
-def run_on_sim(make_sim, script):
-    """Execute on one rank of an object with the pybind surface (reference module or ours)."""
+def run_on_sim(make_sim, script, keep=None):
+    """Execute on one rank of an object with the pybind surface (reference module or ours).
+    keep: optional list that receives the simulator object (so the caller can go on using it)."""
     sim = None
     out = []
     for op in script:
         try:
             if op[0] == "ctor":
                 sim = make_sim(*op[1:])
+                if keep is not None:
+                    keep.append(sim)
                 out.append(None)
             elif op[0] == "cheat_local":
                 d, v = sim.cheat_local()
                 out.append((dict(d), np.asarray(v, dtype=np.complex128).copy()))
             else:
-                out.append(getattr(sim, op[0])(*op[1:]))
+                out.append(_dispatch(sim, op))
         except RuntimeError as e:
             out.append(("error", str(e)))
     return out
@@ -184,12 +187,117 @@ def assert_outputs_match(script, got, exp, tol=1e-12):
             assert np.abs(g[1] - e[1]).max() <= tol, (j, float(np.abs(g[1] - e[1]).max()))
         elif op[0] in ("get_qubits_ids", "get_local_qubits_ids", "get_global_qubits_ids", "measure_qubits"):
             assert list(g) == list(e), (j, op[0], g, e)  # bit-exact
-        elif op[0] in ("get_probability", "entropy"):
-            assert abs(g - e) <= (tol if op[0] == "get_probability" else 1e-10), (j, op[0], g, e)
+        elif op[0] in ("get_probability", "entropy", "get_expectation_value"):
+            assert abs(g - e) <= (1e-10 if op[0] == "entropy" else tol), (j, op[0], g, e)
         elif op[0] == "get_amplitude":
             assert abs(g - e) <= tol
         else:
             assert g is None or g == e, (j, op[0], g)
+
+
+# ------------------------------------------------------------------ operator-level scripts
+# Python callables for emulate_math, by name (scripts stay JSON-able)
+MATH_FUNCS = {
+    "plus2": lambda v: [v[0] + 2],                     # the reference's commented-out Plus2Gate (_simulator_mpi_test.py:223-226)
+    "minus3": lambda v: [v[0] - 3],
+    "swap_regs": lambda v: [v[1], v[0]],
+    "xor_into": lambda v: [v[0], v[0] ^ v[1]],
+    "add_regs": lambda v: [v[0], v[0] + v[1]],
+}
+
+
+def random_terms(rng, n_ids, n_terms, real_coefs, max_factors=4):
+    terms = []
+    for _ in range(n_terms):
+        nf = int(rng.integers(0, min(max_factors, n_ids) + 1))
+        idx = sorted(int(x) for x in rng.choice(n_ids, size=nf, replace=False))
+        term = [(i, "XYZ"[int(rng.integers(0, 3))]) for i in idx]
+        c = float(rng.normal()) if real_coefs else complex(rng.normal(), rng.normal())
+        terms.append((term, c))
+    return terms
+
+
+def operator_script(nq, R, seed, max_cluster=3, ngates=25):
+    """Random gates, then the operator-level calls of the wrapper (get_expectation_value, apply_qubit_operator,
+    emulate_math in its closed and tabulated forms, set_wavefunction), each followed by a look at the state."""
+    rng = np.random.default_rng(1000 + seed)
+    script = random_script(nq, R, seed, ngates=ngates, max_cluster=max_cluster, queries=False)
+    o = statevec.SimulatorMPI(*script[0][1:], R)
+    for op in script[1:]:
+        if op[0] not in ("cheat_local", "get_qubits_ids"):
+            getattr(o, op[0])(*op[1:])
+    allq = [q for q in o.get_qubits_ids() if q >= 0]
+    glo = [q for q in o.get_global_qubits_ids() if q >= 0]
+    loc = o.get_local_qubits_ids()
+
+    def look():
+        script.append(("cheat_local",))
+
+    ids = [int(x) for x in rng.permutation(allq)]
+    # expectation values: mixed terms, the identity, a term with a repeated qubit, a long diagonal group
+    script.append(("get_expectation_value", random_terms(rng, len(ids), 6, True) + [([], 0.4)], ids))
+    script.append(("get_expectation_value", [([(0, "Y"), (0, "X"), (1, "Z")], 0.7), ([(2, "Z"), (2, "Y")], -0.2)], ids))
+    zterms = []
+    for _ in range(70):
+        sub = sorted(int(x) for x in rng.choice(len(ids), size=int(rng.integers(1, 4)), replace=False))
+        zterms.append(([(i, "Z") for i in sub], float(rng.normal())))
+    script.append(("get_expectation_value", zterms, ids))
+    if glo:
+        gi = ids.index(glo[0])
+        li = ids.index(loc[0])
+        script.append(("get_expectation_value", [([(gi, "X")], 1.0), (sorted([(gi, "Y"), (li, "Z")]), 0.5), ([(gi, "Z")], -1.5)], ids))
+    # one flip mask for every term -> in place; then a general operator -> accumulator
+    a, b, c = 0, 1, 2
+    script.append(("apply_qubit_operator", [([(a, "X"), (b, "Z")], 0.6 + 0.1j), ([(a, "Y")], -0.3j), ([(a, "X"), (c, "Z")], 0.2)], ids))
+    look()
+    script.append(("apply_qubit_operator", zterms[:5], ids))
+    look()
+    script.append(("apply_qubit_operator", random_terms(rng, len(ids), 7, False) + [([], 0.25)], ids))
+    look()
+    if glo:
+        script.append(("apply_qubit_operator", [([(gi, "Y"), (li, "X")], 1.0)], ids))
+        look()
+    script.append(("get_probability", [True], [ids[0]]))
+    # emulate_math: closed forms and tabulated Python functions, registers anywhere (local and global qubits)
+    perm = [int(x) for x in rng.permutation(allq)]
+    reg, rest = perm[:4], perm[4:]
+    script.append(("emulate_math_add_constant", 5, reg, rest[:1]))
+    look()
+    script.append(("emulate_math_add_constant", -3, reg[:3], []))
+    look()
+    script.append(("emulate_math_add_constant_modN", 4, 11, reg, rest[:2]))
+    look()
+    script.append(("emulate_math_multiply_by_constant_modN", 7, 15, reg, rest[1:2]))
+    look()
+    if glo:
+        reg_g = glo + [q for q in loc if q not in glo][:3]
+        script.append(("emulate_math_multiply_by_constant_modN", 3, 1 << len(reg_g), reg_g, [q for q in allq if q not in reg_g][:1]))
+        look()
+        script.append(("emulate_math_add_constant", 1, sorted(allq), []))
+        look()
+    script.append(("emulate_math_fn", "plus2", [perm[:2]], perm[2:3]))
+    look()
+    script.append(("emulate_math_fn", "swap_regs", [perm[:2], perm[3:5]], []))
+    look()
+    script.append(("emulate_math_fn", "xor_into", [perm[1:3], perm[4:6]], perm[:1]))
+    look()
+    # set_wavefunction adopts the ordering it is given
+    wf = rng.normal(size=1 << len(allq)) + 1j * rng.normal(size=1 << len(allq))
+    wf /= np.linalg.norm(wf)
+    order = [int(x) for x in rng.permutation(allq)]
+    script.append(("set_wavefunction", [complex(x) for x in wf], order))
+    script.append(("get_qubits_ids",))
+    look()
+    script.append(("get_expectation_value", random_terms(rng, len(order), 4, True), order))
+    script.append(("measure_qubits", order[:3]))
+    look()
+    return script
+
+
+def _dispatch(sim, op):
+    if op[0] == "emulate_math_fn":
+        return sim.emulate_math(MATH_FUNCS[op[1]], op[2], op[3])
+    return getattr(sim, op[0])(*op[1:])
 
 
 # ------------------------------------------------------------------ JSON (golden fixtures)
@@ -218,18 +326,28 @@ def script_from_json(s):
 
 
 # ------------------------------------------------------------------ dry-run trace replay
-def replay_traces(traces, R):
+KIND = {"none": 0, "dense": 1, "diag": 2, "scale": 3, "swap": 4, "grow": 5, "fill": 6,
+        "pauli_expect": 7, "pauli_apply": 8, "pauli_commit": 9, "permute": 10, "load": 11}
+_COLLECTIVE = {KIND["swap"], KIND["pauli_expect"], KIND["pauli_apply"], KIND["pauli_commit"], KIND["permute"], KIND["load"]}
+
+
+def replay_traces(traces, R, info=None):
     """Apply per-rank descriptor traces (engine dry-run) with the oracle kernels.
-    Swaps are collective: the i-th SWAP descriptor of every rank is executed together."""
-    KIND = {"none": 0, "dense": 1, "diag": 2, "scale": 3, "swap": 4, "grow": 5, "fill": 6}
+    Swaps and the operator-level passes are collective: the i-th such descriptor of every rank is executed
+    together.  `info` (optional dict): "loads" = host vectors consumed by LOAD descriptors in order;
+    on return "expect" = the value (summed over ranks) of every PAULI_EXPECT descriptor."""
+    info = info if info is not None else {}
+    loads = list(info.get("loads", []))
+    info["expect"] = []
     vec = [np.zeros(1, dtype=np.complex128) for _ in range(R)]
     vec[0][0] = 1.0
+    acc = [None] * R
     cursors = [0] * R
     while True:
-        swaps = []
+        stops = []
         for r in range(R):
             t = traces[r]
-            while cursors[r] < len(t) and t[cursors[r]]["kind"] != KIND["swap"]:
+            while cursors[r] < len(t) and t[cursors[r]]["kind"] not in _COLLECTIVE:
                 d = t[cursors[r]]
                 cursors[r] += 1
                 if d["kind"] == KIND["grow"]:
@@ -243,18 +361,66 @@ def replay_traces(traces, R):
                 elif d["kind"] == KIND["scale"]:
                     vec[r] *= d["payload"][0]
             if cursors[r] < len(t):
-                swaps.append(tuple(int(x) for x in t[cursors[r]]["aux"]))
+                stops.append(t[cursors[r]])
                 cursors[r] += 1
-        if not swaps:
+        if not stops:
             break
-        assert len(swaps) == R and len(set(swaps)) == 1, "ranks disagree on the swap plan"
-        aux = swaps[0]
+        assert len(stops) == R and len({d["kind"] for d in stops}) == 1, "ranks disagree on the collective sequence"
+        kind = stops[0]["kind"]
         L = int(np.log2(vec[0].shape[0]))
-        g = int(np.log2(R))
-        full = np.concatenate(vec).reshape((2,) * (g + L))
-        nb = g + L
-        for i in range(0, len(aux), 2):
-            full = np.swapaxes(full, nb - 1 - (L + aux[i]), nb - 1 - aux[i + 1])
-        full = np.ascontiguousarray(full).reshape(R, 1 << L)
-        vec = [full[r].copy() for r in range(R)]
+        if kind == KIND["swap"]:
+            plans = {tuple(int(x) for x in d["aux"]) for d in stops}
+            assert len(plans) == 1, "ranks disagree on the swap plan"
+            aux = plans.pop()
+            g = int(np.log2(R))
+            full = np.concatenate(vec).reshape((2,) * (g + L))
+            nb = g + L
+            for i in range(0, len(aux), 2):
+                full = np.swapaxes(full, nb - 1 - (L + aux[i]), nb - 1 - aux[i + 1])
+            full = np.ascontiguousarray(full).reshape(R, 1 << L)
+            vec = [full[r].copy() for r in range(R)]
+        elif kind in (KIND["pauli_expect"], KIND["pauli_apply"]):
+            total = 0j
+            new = [None] * R
+            for r, d in enumerate(stops):
+                aux = [int(x) for x in d["aux"]]
+                mode, lx, src_rank = aux[0], aux[1], aux[2]
+                terms = list(zip(aux[3:], [complex(c) for c in d["payload"]]))
+                src = None if src_rank == r else vec[src_rank]
+                if kind == KIND["pauli_expect"]:
+                    total += statevec.pauli_expect(vec[r], lx, terms, src=src)
+                elif mode == 0:
+                    assert src is None
+                    new[r] = vec[r].copy()
+                    statevec.pauli_apply(new[r], lx, terms)
+                else:
+                    if mode == 1:
+                        acc[r] = np.full(1 << L, np.nan + 0j)  # every element must be written by the first pass
+                    statevec.pauli_apply(vec[r], lx, terms, acc=acc[r], accumulate=(mode == 2), src=src)
+            if kind == KIND["pauli_expect"]:
+                info["expect"].append(total)
+            for r in range(R):
+                if new[r] is not None:
+                    vec[r] = new[r]
+        elif kind == KIND["pauli_commit"]:
+            vec = [a for a in acc]
+            acc = [None] * R
+        elif kind == KIND["permute"]:
+            out = []
+            for r, d in enumerate(stops):
+                aux = [int(x) for x in d["aux"]]
+                pk, a, N, cmask, takes_part = aux[:5]
+                k = int(d["k"])
+                pos = aux[5:5 + k]
+                table = aux[5 + k:]
+                gather = statevec.permute_gather(vec, r, L, pk, pos, cmask, a, N, table)
+                if not takes_part:  # the rank filter is only a shortcut: the gather must be the identity there
+                    assert np.array_equal(gather, vec[r])
+                out.append(gather)
+            vec = out
+        elif kind == KIND["load"]:
+            wf = np.asarray(loads.pop(0), dtype=np.complex128)
+            for r, d in enumerate(stops):
+                sl = int(d["aux"][0])
+                vec[r] = np.zeros(1 << L, dtype=np.complex128) if sl < 0 else wf[sl << L:(sl + 1) << L].copy()
     return np.concatenate(vec)

@@ -269,3 +269,225 @@ def test_ref_multi_controlled_x():  # :652-706 (huge gate / ctrl-mask path)
         _apply(sim, G.X, [nctrl], list(range(nctrl))); sim.run()
         d, v = sim.cheat_local()
         assert abs(v[(1 << n) - 1]) == pytest.approx(1.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# Operator-level calls the reference wrapper makes but the reference class lacks:
+# parity unpinned in the reference; checked against the numpy restatement of ProjectQ's algorithm and
+# against the reference's commented-out expectations.
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("nq,seed", [(7, 31), (10, 32), (12, 33), (9, 34)])
+def test_engine_operator_calls_match_oracle(nq, seed):
+    M = _M()
+    script = scripts.operator_script(nq, 1, seed)
+    exp = scripts.run_on_oracle(script, 1)
+    keep = []
+    got = scripts.run_on_sim(M.SimulatorMPI, script, keep)
+    scripts.assert_outputs_match(script, got, exp)
+    d, full = keep[0].cheat()  # world size 1: cheat() == cheat_local()
+    last = max(j for j, op in enumerate(script) if op[0] == "cheat_local")
+    assert dict(d) == exp[last][0] and np.array_equal(np.asarray(full), got[last][1])
+
+
+@pytest.mark.parametrize("name,R", [("ops:9:41", 2), ("ops:10:42", 4), ("ops:11:43", 8), ("ops:10:44", 2)])
+def test_engine_operator_calls_multi_gpu(name, R):
+    if _gpu_count() < R:
+        pytest.skip("needs %d GPUs" % R)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
+def test_ref_expectation():  # commented-out reference test, _simulator_mpi_test.py:382-424
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    q = [0, 1, 2]
+    sim.allocate_qureg(q, 0)
+
+    def g(m, t):
+        _apply(sim, m, [t])
+        sim.run()
+    S = np.diag([1, 1j])
+    assert sim.get_expectation_value([([(0, "Z")], 1.0)], q) == pytest.approx(1.0)
+    g(G.X, 0)
+    assert sim.get_expectation_value([([(0, "Z")], 1.0)], q) == pytest.approx(-1.0)
+    g(G.H, 0)
+    assert sim.get_expectation_value([([(0, "X")], 1.0)], q) == pytest.approx(-1.0)
+    g(G.Z, 0)
+    assert sim.get_expectation_value([([(0, "X")], 1.0)], q) == pytest.approx(1.0)
+    for m in (G.X, S, G.Z, G.X):
+        g(m, 0)
+    assert sim.get_expectation_value([([(0, "Y")], 1.0)], q) == pytest.approx(1.0)
+    g(G.Z, 0)
+    assert sim.get_expectation_value([([(0, "Y")], 1.0)], q) == pytest.approx(-1.0)
+    op_sum = [([(0, "Y"), (1, "X"), (2, "Z")], 1.0), ([(1, "X")], 1.0)]
+    g(G.H, 1)
+    g(G.X, 2)
+    assert sim.get_expectation_value(op_sum, q) == pytest.approx(2.0)
+    g(G.X, 2)
+    assert sim.get_expectation_value(op_sum, q) == pytest.approx(0.0)
+    assert sim.get_expectation_value([((), 0.4)], q) == pytest.approx(0.4)
+    # :427-438
+    sim.get_expectation_value([([(2, "Z")], 1.0)], q)
+    with pytest.raises(RuntimeError):
+        sim.get_expectation_value([([(3, "Z")], 1.0)], q)
+    with pytest.raises(RuntimeError):
+        sim.apply_qubit_operator([([(1, "Z")], 1.0), ([(1, "X"), (3, "Y")], 1.0)], q)
+
+
+def test_ref_applyqubitoperator():  # :454-478
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    q = [0, 1, 2]
+    sim.allocate_qureg(q, 0)
+    zero = [False] * 3
+
+    def g(m, t):
+        _apply(sim, m, [t])
+        sim.run()
+    sim.apply_qubit_operator([([(0, "X"), (1, "Y"), (2, "Z")], 1.0)], q)
+    g(G.X, 0)
+    g(G.Y, 1)
+    g(G.Z, 2)
+    assert sim.get_amplitude(zero, q) == pytest.approx(1.0)
+    g(G.H, 0)
+    r2 = 1.0 / math.sqrt(2.0)
+    sim.apply_qubit_operator([([(0, "X")], r2), ([(0, "Z")], r2)], [0])
+    assert sim.get_amplitude(zero, q) == pytest.approx(1.0)
+    g(G.H, 0)
+    sim.apply_qubit_operator([((), 0.5), ([(0, "Z")], 0.5)], [0])
+    assert sim.get_amplitude(zero, q) == pytest.approx(r2)
+    sim.apply_qubit_operator([((), 0.5), ([(0, "Z")], -0.5)], [0])
+    assert sim.get_amplitude(zero, q) == pytest.approx(0.0)
+
+
+def test_ref_set_wavefunction():  # :546-560
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    wf = [0.0, 0.0, math.sqrt(0.2), math.sqrt(0.8)]
+    with pytest.raises(RuntimeError):
+        sim.set_wavefunction(wf, [0, 1])
+    sim.allocate_qureg([0, 1], 0)
+    sim.set_wavefunction(wf, [0, 1])
+    assert sim.get_probability([True], [0]) == pytest.approx(0.8)
+    assert sim.get_probability([False, True], [0, 1]) == pytest.approx(0.2)
+    assert sim.get_probability([True], [1]) == pytest.approx(1.0)
+    assert sim.measure_qubits([1]) == [True]
+
+
+def test_ref_emulation_plus2():  # :223-244
+    M = _M()
+    sim = M.SimulatorMPI(1, 20, 4)
+    sim.allocate_qureg([0, 1, 2], 0)
+    sim.emulate_math(scripts.MATH_FUNCS["plus2"], [[0, 1]], [2])
+    assert sim.cheat()[1][0] == pytest.approx(1.0)
+    _apply(sim, G.X, [2])
+    sim.emulate_math(scripts.MATH_FUNCS["plus2"], [[0, 1]], [2])
+    assert sim.cheat()[1][6] == pytest.approx(1.0)
+    assert sim.measure_qubits([0, 1, 2]) == [False, True, True]
+
+
+def test_modular_multiplication_chain_is_reversible():
+    """size-independent property at a size the numpy oracle does not reach (24 qubits): a chain of controlled
+    modular multiplications followed by the inverse chain restores the state exactly (amplitudes are only moved)"""
+    M = _M()
+    n = 24
+    sim = M.SimulatorMPI(3, n, 4)
+    sim.allocate_qureg(list(range(n)), 0)
+    rng = np.random.default_rng(5)
+    for q in range(n):
+        _apply(sim, G.haar_unitary(2, rng), [q])
+        sim.run()
+    _, before = sim.cheat_local()
+    before = np.asarray(before).copy()
+    N = (1 << 22) - 3
+    reg = list(range(1, 23))
+    consts = [3, 65537, 1234567, 7]
+    for a in consts:
+        sim.emulate_math_multiply_by_constant_modN(a, N, reg, [0])
+        sim.emulate_math_add_constant_modN(a, N, reg, [23])
+    _, mid = sim.cheat_local()
+    assert not np.array_equal(np.asarray(mid), before)
+    assert abs(sim.get_probability([], []) - 1.0) <= 1e-12
+    for a in reversed(consts):
+        sim.emulate_math_add_constant_modN(-a, N, reg, [23])
+        sim.emulate_math_multiply_by_constant_modN(pow(a, -1, N), N, reg, [0])
+    _, after = sim.cheat_local()
+    assert np.array_equal(np.asarray(after), before)
+
+
+# ---------------------------------------------------------------------------------------------
+# Whole host pipeline (HiQMainEngine -> GreedyScheduler -> backend -> engine) on the benchmark
+# configurations C1 (Grover, examples/grover_mpi.py) and C5 (Shor by emulation, examples/shor_mpi.py)
+# at test sizes: same pipeline and seeds on the numpy oracle -> identical measured bits, states <= 1e-12.
+# ---------------------------------------------------------------------------------------------
+def _pipeline(backend_class, seed, L, cluster):
+    from hiqsimulator_b200 import backends, cengines
+    be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=seed, num_local_qubits=L, max_fused_qubits=cluster,
+                               backend_class=backend_class)
+    return be, cengines.HiQMainEngine(be, [cengines.GreedyScheduler(cluster_size=cluster)])
+
+
+@pytest.mark.parametrize("N,a,n,seed", [(15, 7, 4, 2), (21, 2, 5, 3), (35, 4, 6, 5), (15, 7, 9, 1)])
+def test_pipeline_shor_matches_oracle(N, a, n, seed):
+    from hiqsimulator_b200 import circuits
+    from oracle import statevec
+    _M()
+    out = []
+    for cls in (None, statevec.SimulatorMPI):
+        be, eng = _pipeline(cls, seed, n + 1, 3)
+        r, bits = circuits.run_shor(eng, N, a, n)
+        id2pos, vec = be.cheat()
+        out.append((r, bits, [eng.measurements[q] for q in range(n + 1)], dict(id2pos), np.asarray(vec).copy()))
+    assert out[0][:4] == out[1][:4]
+    assert np.abs(out[0][4] - out[1][4]).max() <= 1e-12
+    if (N, a, n) == (15, 7, 4):
+        assert out[0][0] in (1, 2, 4)  # the order of 7 mod 15 is 4
+
+
+@pytest.mark.parametrize("n_search,iters,cluster", [(9, 6, 4), (12, 3, 4), (10, 4, 3)])
+def test_pipeline_grover_matches_oracle(n_search, iters, cluster):
+    """C1 (reference: examples/grover_mpi.py:23-94): multi-controlled X / Z take the huge-gate path"""
+    import copy
+    from hiqsimulator_b200 import circuits, ops
+    from oracle import statevec
+    _M()
+    n, cmds = circuits.grover_circuit(n_search, iters)
+    out = []
+    for cls in (None, statevec.SimulatorMPI):
+        be, eng = _pipeline(cls, 1, n, cluster)
+        eng.allocate_qureg(n)
+        eng.receive(copy.deepcopy(cmds))
+        eng.flush()
+        id2pos, vec = be.cheat()
+        vec = np.asarray(vec).copy()
+        eng.receive([ops.Measure(list(range(n)))])
+        out.append((dict(id2pos), [eng.measurements[q] for q in range(n)], vec))
+    assert out[0][:2] == out[1][:2]
+    assert np.abs(out[0][2] - out[1][2]).max() <= 1e-12
+    if n_search == 9:
+        # closed form: after k iterations P(marked) = sin^2((2k + 1) asin(2^(-n/2)))
+        marked = ((1 << n_search) - 1) & ~0b10
+        p = sum(abs(out[0][2][i]) ** 2 for i in range(1 << n) if sum(((i >> out[0][0][q]) & 1) << q for q in range(n_search)) == marked)
+        assert abs(p - math.sin((2 * iters + 1) * math.asin(2.0 ** (-n_search / 2))) ** 2) <= 1e-9
+
+
+@pytest.mark.parametrize("name,R", [("shor:15:7:5:2", 2), ("shor:21:2:6:3", 4), ("shor:35:4:7:4", 8)])
+def test_pipeline_shor_multi_gpu(name, R):
+    if _gpu_count() < R:
+        pytest.skip("needs %d GPUs" % R)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -84,8 +84,11 @@ def test_error_conventions_dry_run():
         e.swap_qubits([4, 0, 4, 1])
     with pytest.raises(RuntimeError, match="Can't find"):
         e.swap_qubits([0, 1])
-    with pytest.raises(RuntimeError, match="not supported"):
-        e.emulate_math(lambda x: x, [[0]], [])
+    # emulate_math works here (the reference's throws "not supported", SimulatorMPI.hpp:217-225);
+    # what it rejects is a function that is not reversible on the register
+    e.emulate_math(lambda x: x, [[0]], [])
+    with pytest.raises(RuntimeError, match="not reversible"):
+        e.emulate_math(lambda x: [0], [[0]], [])
     # six fused qubits cannot run (reference: "Run(): cannot apply 6 qubits gate")
     e2 = _dry_engines([("ctor", 1, 8, 4)], 1)[0]
     e2.allocate_qureg(list(range(7)), 0)

@@ -380,3 +380,171 @@ def test_swap_p2p_in_place(slots, grid):
         bh, bl = (src >> hi) & 1, (src >> lo) & 1
         src = src & ~((1 << hi) | (1 << lo)) | (bl << hi) | (bh << lo)
     assert np.array_equal(got, full[src])
+
+
+# ---------------------------------------------------------------------------------------------
+# Operator-level passes (hiqk_pauli_expect / hiqk_pauli_apply / hiqk_permute_gather) against the
+# kernel-level statements in oracle/statevec.py
+# ---------------------------------------------------------------------------------------------
+def _terms(L, n, seed):
+    rng = np.random.default_rng(seed)
+    return [(int(rng.integers(0, 1 << L)), complex(rng.normal(), rng.normal())) for _ in range(n)]
+
+
+PAULI_XMASKS = [0, 1, 2, 1 << 13, (1 << 13) | 1, 0b1010001, (1 << 12) | (1 << 5) | 6, (1 << 14) - 1]
+
+
+@pytest.mark.parametrize("xmask", PAULI_XMASKS)
+@pytest.mark.parametrize("n_terms", [1, 3, 64])
+@pytest.mark.parametrize("grid", [0, 3])
+def test_pauli_expect_local(xmask, n_terms, grid):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    ref = rand_state(L, 7 + xmask % 97)
+    terms = _terms(L, n_terms, xmask + n_terms)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.debug_set_max_grid(grid)
+    try:
+        got = K.pauli_expect(dev, xmask, terms)
+    finally:
+        K.debug_set_max_grid(0)
+    exp = statevec.pauli_expect(ref, xmask, terms)
+    assert abs(got - exp) <= TOL
+    assert np.array_equal(dev.cpu().numpy(), ref)  # read-only
+
+
+@pytest.mark.parametrize("xmask", [0, 5, (1 << 13) | 2])
+@pytest.mark.parametrize("begin,count", [(0, 1 << 14), (0, 1 << 12), (3 << 12, 1 << 12), (5 << 10, 3 << 10), (100, 0)])
+def test_pauli_expect_ranges_and_staged_source(xmask, begin, count):
+    """a partner GPU's amplitudes staged in a separate buffer (src) and sub-ranges of the local slab"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    ref = rand_state(L, 21)
+    other = rand_state(L, 22)
+    terms = _terms(L, 4, 9)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    src = torch.from_numpy(other[begin:begin + count].copy()).cuda() if count else torch.zeros(1, dtype=torch.complex128, device="cuda")
+    got = K.pauli_expect(dev, xmask, terms, src=src, begin=begin, count=count)
+    exp = statevec.pauli_expect(ref, xmask, terms, src=other[begin:begin + count], begin=begin, count=count)
+    assert abs(got - exp) <= TOL
+    got = K.pauli_expect(dev, xmask, terms, begin=begin, count=count)
+    exp = statevec.pauli_expect(ref, xmask, terms, begin=begin, count=count)
+    assert abs(got - exp) <= TOL
+
+
+@pytest.mark.parametrize("xmask", PAULI_XMASKS)
+@pytest.mark.parametrize("n_terms", [1, 5, 64])
+@pytest.mark.parametrize("grid", [0, 3])
+def test_pauli_apply_in_place(xmask, n_terms, grid):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    ref = rand_state(L, 31 + xmask % 89)
+    terms = _terms(L, n_terms, 2 * xmask + n_terms)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.debug_set_max_grid(grid)
+    try:
+        K.pauli_apply(dev, xmask, terms)
+    finally:
+        K.debug_set_max_grid(0)
+    statevec.pauli_apply(ref, xmask, terms)
+    # up to 64 coefficients of magnitude ~1 are summed per amplitude
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+@pytest.mark.parametrize("xmask", [0, 3, (1 << 13) | (1 << 6), (1 << 14) - 1])
+def test_pauli_apply_accumulator(xmask):
+    """overwrite pass, accumulate pass from the slab, accumulate passes from a staged partner slab in pieces"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    n = 1 << L
+    ref = rand_state(L, 41)
+    other = rand_state(L, 42)
+    t1, t2, t3 = _terms(L, 2, 1), _terms(L, 3, 2), _terms(L, 1, 3)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    acc = torch.full((n,), float("nan"), dtype=torch.complex128, device="cuda")
+    exp = np.full(n, np.nan + 0j)
+    K.pauli_apply(dev, xmask, t1, acc=acc, accumulate=False)
+    statevec.pauli_apply(ref, xmask, t1, acc=exp, accumulate=False)
+    K.pauli_apply(dev, xmask ^ 4, t2, acc=acc, accumulate=True)
+    statevec.pauli_apply(ref, xmask ^ 4, t2, acc=exp, accumulate=True)
+    piece = n // 4
+    for b in range(0, n, piece):
+        src = torch.from_numpy(other[b:b + piece].copy()).cuda()
+        K.pauli_apply(dev, xmask, t3, acc=acc, accumulate=True, src=src, begin=b, count=piece)
+        statevec.pauli_apply(ref, xmask, t3, acc=exp, accumulate=True, src=other[b:b + piece], begin=b, count=piece)
+    assert np.abs(acc.cpu().numpy() - exp).max() <= TOL
+    assert np.array_equal(dev.cpu().numpy(), ref)
+
+
+def _perm_case(name, L, g):
+    """(kind, pos, ctrl_mask, a, N, forward table or None)"""
+    top = L + g
+    if name == "add_contig":
+        return 1, list(range(2, 9)), 1 << 11, 37, 0, None
+    if name == "add_neg_scattered":
+        return 1, [9, 0, 4, top - 1, 2], (1 << 1) | (1 << 7), (1 << 64) - 3, 0, None
+    if name == "add_mod":
+        return 2, [5, 6, 7, 8, 9, 10], 1, 17, 53, None
+    if name == "mul_mod":
+        return 3, [3, 1, top - 1, 8, 10, 0, 6], 1 << 4, 29, 101, None
+    if name == "mul_mod_contig_global":
+        return 3, list(range(L - 3, top)), 0, 7, (1 << (g + 3)) - 3, None
+    if name == "whole_index_add":
+        return 1, list(range(top)), 0, 12345, 0, None
+    if name == "table":
+        rng = np.random.default_rng(5)
+        return 0, [2, top - 1, 7, 0, 5], 1 << 3, 0, 0, [int(x) for x in rng.permutation(32)]
+    raise KeyError(name)
+
+
+@pytest.mark.parametrize("name", ["add_contig", "add_neg_scattered", "add_mod", "mul_mod", "mul_mod_contig_global",
+                                  "whole_index_add", "table"])
+@pytest.mark.parametrize("g", [0, 1, 2])
+def test_permute_gather(name, g):
+    """register permutations over R = 2^g slabs (virtual ranks = separate buffers on one GPU)"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 12
+    R = 1 << g
+    kind, pos, cmask, a, N, fwd = _perm_case(name, L, g)
+    rng = np.random.default_rng(g + len(pos))
+    full = rng.normal(size=R << L) + 1j * rng.normal(size=R << L)
+    slabs_np = [full[r << L:(r + 1) << L] for r in range(R)]
+    slabs = [torch.from_numpy(s.copy()).cuda() for s in slabs_np]
+    inv = dev_table = None
+    if fwd is not None:
+        inv = [0] * len(fwd)
+        for v, w in enumerate(fwd):
+            inv[w] = v
+        dev_table = torch.tensor(inv, dtype=torch.int32, device="cuda")
+    a_oracle = a if a < (1 << 63) else a - (1 << 64)  # the C ABI takes the two's complement
+    outs = []
+    for r in range(R):
+        dst = torch.empty(1 << L, dtype=torch.complex128, device="cuda")
+        K.permute_gather(dst, slabs, r, kind, pos, cmask, a, N, dev_table)
+        exp = statevec.permute_gather(slabs_np, r, L, kind, pos, cmask, a_oracle, N, inv)
+        got = dst.cpu().numpy()
+        assert np.array_equal(got, exp), (name, g, r)
+        outs.append(got)
+    # a permutation: every amplitude appears exactly once in the result
+    assert np.array_equal(np.sort_complex(np.concatenate(outs)), np.sort_complex(full))
+
+
+def test_permute_gather_rejects_bad_arguments():
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    from hiqsimulator_b200._lib import HiqError
+    s = torch.zeros(1 << 8, dtype=torch.complex128, device="cuda")
+    d = torch.zeros_like(s)
+    with pytest.raises(HiqError, match="not invertible"):
+        K.permute_gather(d, [s], 0, K.PERM_MUL_MOD, [0, 1, 2, 3], 0, 6, 15)
+    with pytest.raises(HiqError, match="alias"):
+        K.permute_gather(s, [s], 0, K.PERM_ADD, [0, 1], 0, 1, 0)
+    with pytest.raises(HiqError, match="control"):
+        K.permute_gather(d, [s], 0, K.PERM_ADD, [0, 1], 2, 1, 0)
+    with pytest.raises(HiqError, match="missing the slab"):
+        K.permute_gather(d, [s, None], 0, K.PERM_ADD, [0, 8], 0, 1, 0)

@@ -27,3 +27,15 @@ def test_dry_run_world(name, R):
     env = dict(os.environ, OMP_NUM_THREADS="1")
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name,R", [("ops:8:21", 2), ("ops:9:22", 4)])
+def test_dry_run_world_operator_calls(name, R):
+    """get_expectation_value / apply_qubit_operator / emulate_math / set_wavefunction host logic, one dry-run engine
+    per gloo rank, traces replayed on rank 0 against the numpy oracle"""
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(HERE, "mp_worker.py"), name, "dry"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
