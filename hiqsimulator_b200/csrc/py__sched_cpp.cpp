@@ -18,6 +18,8 @@ PYBIND11_MODULE(_sched_cpp, m)
          .def(py::init<const std::vector<std::vector<Id>>&, const std::vector<std::vector<Id>>&, std::vector<bool>,
                        const std::vector<Id>&, const std::vector<Id>&, int>())
          .def("ScheduleCluster", &ClusterScheduler::ScheduleCluster, py::call_guard<py::gil_scoped_release>())
-         .def("candidates", &ClusterScheduler::candidates);
+         .def("candidates", &ClusterScheduler::candidates)
+         .def("evaluated", &ClusterScheduler::evaluated);
+     m.def("set_mode", &ClusterScheduler::set_mode, "0 = bounded search (default), 1 = replay the reference's enumeration and score every candidate");
      m.def("set_threads", &ClusterScheduler::set_threads, "host threads used to score candidate clusters (0 = auto)");
 }

@@ -255,9 +255,154 @@ void ClusterScheduler::visit(Mask cluster, int b0)
      }
 }
 
+static std::atomic<int> g_mode{0};
+void ClusterScheduler::set_mode(int mode) { g_mode.store(mode); }
+
 std::vector<int> ClusterScheduler::ScheduleCluster()
 {
      if (gate_.empty()) return {};
+     n_evaluated_ = 0;
+     if (g_mode.load() == 0) {
+          std::vector<int> out;
+          if (schedule_bounded(out)) return out;
+     }
+     return schedule_replay();
+}
+
+// Bounded search for the same winner as schedule_replay() without replaying the enumeration.
+//
+// Facts used (C, D clusters; a gate's "seed" = its local qubits):
+//  * score is monotone (C subset of D => score(C) <= score(D)) and score(C) = score(used(C)), used(C) = union of the
+//    seeds of the gates C admits; so the winner (more gates, then fewer qubits) satisfies used(W) = W: every
+//    qubit of W has its FIRST gate admitted.  Qubits whose first gate can never run are left out.
+//  * chain bound: an admitted gate is preceded, on each of its local qubits, only by admitted gates, so
+//    score(C) <= free + sum over q in C of sum over the leading gates of q's chain with seed inside C of 1/|seed|.
+//    Only clusters whose bound reaches the best score so far are walked exactly.
+//  * first-visit order of the reference's enumeration, needed for ties: a cluster X is first met in the
+//    expansion of the first gate (program order) whose seed lies inside X, and inside one expansion clusters
+//    are met in lexicographic order of their added qubits (ascending, prefix first).
+bool ClusterScheduler::schedule_bounded(std::vector<int>& out)
+{
+     constexpr int W = 60;  // divisible by every seed size up to 6
+     if (cluster_size_ > 6 || cluster_size_ < 0) return false;
+     const int n = static_cast<int>(gate_.size());
+     struct Link {
+          Mask seed;
+          int w;
+     };
+     std::vector<Link> chain[64];
+     std::vector<Mask> seed(n);
+     int free_takes = 0;
+     bool empty_seed = false;
+     for (int i = 0; i < n; ++i) {
+          seed[i] = all_[i] & locals_;
+          const bool takeable = diag_[i] || subset(gate_[i], locals_);
+          const int pc = popcount(seed[i]);
+          if (pc == 0) {
+               empty_seed = true;
+               if (takeable) ++free_takes;
+               continue;
+          }
+          const bool ok = takeable && pc <= cluster_size_;
+          for (Mask m = seed[i]; m; m &= m - 1) chain[__builtin_ctzll(m)].push_back(Link{ok ? seed[i] : ~Mask(0), ok ? W / pc : 0});
+     }
+     int act[64];
+     int na = 0;
+     for (int p = 0; p < 64; ++p)
+          if (!chain[p].empty() && chain[p][0].w) act[na++] = p;
+
+     auto bound = [&](Mask c) {
+          int u = free_takes * W;
+          for (Mask m = c; m; m &= m - 1) {
+               const std::vector<Link>& ch = chain[__builtin_ctzll(m)];
+               for (const Link& l: ch) {
+                    if (!subset(l.seed, c)) break;
+                    u += l.w;
+               }
+          }
+          return u;
+     };
+
+     std::vector<std::pair<int, Mask>> cand;
+     if (empty_seed) cand.emplace_back(free_takes * W, Mask(0));
+     {
+          // subsets of the active qubits with 1..cluster_size members
+          int idx[8];
+          Mask acc[8];
+          int depth = 0;
+          idx[0] = 0;
+          acc[0] = 0;
+          while (depth >= 0) {
+               if (depth >= cluster_size_ || idx[depth] >= na) {
+                    --depth;
+                    continue;
+               }
+               const Mask c = acc[depth] | (Mask(1) << act[idx[depth]]);
+               ++idx[depth];
+               cand.emplace_back(bound(c), c);
+               if (depth + 1 < cluster_size_) {
+                    idx[depth + 1] = idx[depth];
+                    acc[depth + 1] = c;
+                    ++depth;
+               }
+          }
+     }
+     n_candidates_ = cand.size();
+
+     int best_score = 0, best_bits = 0;
+     std::vector<Mask> ties;
+     auto consider = [&](Mask c) {
+          ++n_evaluated_;
+          const int s = score(c);
+          if (s == 0) return;
+          const int b = popcount(c);
+          if (s > best_score || (s == best_score && b < best_bits)) {
+               best_score = s;
+               best_bits = b;
+               ties.clear();
+               ties.push_back(c);
+          }
+          else if (s == best_score && b == best_bits) ties.push_back(c);
+     };
+     // start from the most promising candidate so that the bound bites at once
+     size_t top = 0;
+     for (size_t k = 1; k < cand.size(); ++k)
+          if (cand[k].first > cand[top].first) top = k;
+     if (!cand.empty()) consider(cand[top].second);
+     for (size_t k = 0; k < cand.size(); ++k)
+          if (k != top && cand[k].first >= best_score * W && cand[k].first > 0) consider(cand[k].second);
+
+     if (ties.empty()) {
+          out = huge_gate();
+          return true;
+     }
+     auto first_seed_gate = [&](Mask c) {
+          for (int i = 0; i < n; ++i)
+               if (subset(seed[i], c) && popcount(seed[i]) <= cluster_size_) return i;
+          return n;
+     };
+     Mask win = ties[0];
+     int win_gate = ties.size() > 1 ? first_seed_gate(win) : 0;
+     for (size_t k = 1; k < ties.size(); ++k) {
+          const Mask c = ties[k];
+          const int g = first_seed_gate(c);
+          bool earlier;
+          if (g != win_gate) earlier = g < win_gate;
+          else {
+               const Mask diff = c ^ win;  // same seed, same size: the one holding the lowest differing qubit comes first
+               earlier = (c & (diff & (~diff + 1))) != 0;
+          }
+          if (earlier) {
+               win = c;
+               win_gate = g;
+          }
+     }
+     out = gates_of(win);
+     return true;
+}
+
+std::vector<int> ClusterScheduler::schedule_replay()
+{
      order_.clear();
      top_ = locals_ ? 63 - __builtin_clzll(locals_) : -1;
      {
@@ -329,8 +474,12 @@ std::vector<int> ClusterScheduler::ScheduleCluster()
                if (p.index != static_cast<size_t>(-1) && (best.index == static_cast<size_t>(-1) || p.better_than(best))) best = p;
      }
      if (best.index != static_cast<size_t>(-1)) return gates_of(order_[best.index]);
+     return huge_gate();
+}
 
-     // nothing fits a cluster: the first gate that can run when every local qubit is allowed ("huge gate")
+// nothing fits a cluster: the first gate that can run when every local qubit is allowed ("huge gate")
+std::vector<int> ClusterScheduler::huge_gate() const
+{
      Mask bad = 0;
      for (int i = 0; i < static_cast<int>(gate_.size()); ++i) {
           if (can_take(i, locals_, bad)) return {i};

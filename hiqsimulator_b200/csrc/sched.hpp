@@ -62,8 +62,15 @@ public:
      // number of candidate clusters scored by the last call (diagnostics)
      size_t candidates() const { return n_candidates_; }
      static void set_threads(int n);
+     // 0 = bounded search (default), 1 = replay-and-score-everything (kept as the cross-check of the former)
+     static void set_mode(int mode);
+     // exact walks done by the last call (diagnostics)
+     size_t evaluated() const { return n_evaluated_; }
 
 private:
+     std::vector<int> schedule_replay();
+     std::vector<int> huge_gate() const;
+     bool schedule_bounded(std::vector<int>& out);
      bool can_take(int i, Mask cluster, Mask bad) const;
      int score(Mask cluster) const;
      std::vector<int> gates_of(Mask cluster) const;
@@ -86,6 +93,7 @@ private:
      int top_ = -1;                      // position of the highest local qubit
      std::vector<Mask> order_;           // candidates in first-visit order
      size_t n_candidates_ = 0;
+     size_t n_evaluated_ = 0;
 };
 
 }  // namespace sched

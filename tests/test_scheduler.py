@@ -54,6 +54,53 @@ def test_cluster_scheduler_fuzz(seed):
     assert list(got) == list(exp)
 
 
+@pytest.mark.parametrize("block", range(8))
+def test_cluster_bounded_search_equals_replay(block):
+    """The bounded search (chain bound + analytic first-visit order, csrc/sched.cpp) picks the very cluster
+    the replay of the reference's enumeration picks, ties included; the replay itself is pinned to the
+    reference above.  Layered circuits (a 1-qubit gate on every qubit, then pairs) are the tie-heavy case."""
+    S = _mine()
+    try:
+        for seed in range(block * 60, block * 60 + 60):
+            rng = np.random.default_rng(50000 + seed)
+            n = int(rng.integers(3, 30))
+            g = int(rng.integers(0, 4))
+            ids = [int(x) for x in rng.permutation(n + 3)[:n]]
+            n_glob = min(g, n - 2)
+            locals_, globals_ = ids[: n - n_glob], ids[n - n_glob:]
+            if seed % 5 == 0:
+                globals_ = globals_ + [-1]
+            if seed % 4 == 3:  # layered: singles everywhere, then a random matching
+                gate, ctrl, diag = [], [], []
+                for _ in range(int(rng.integers(1, 6))):
+                    gate += [[q] for q in range(n)]
+                    ctrl += [[] for _ in range(n)]
+                    diag += [bool(rng.random() < 0.2) for _ in range(n)]
+                    perm = [int(x) for x in rng.permutation(n)]
+                    for a, b in zip(perm[0::2], perm[1::2]):
+                        if rng.random() < 0.5:
+                            gate.append([a]); ctrl.append([b]); diag.append(bool(rng.random() < 0.5))
+                        else:
+                            gate.append([a, b]); ctrl.append([]); diag.append(False)
+                drop = int(rng.integers(0, len(gate)))
+                gate, ctrl, diag = gate[drop:], ctrl[drop:], diag[drop:]
+            else:
+                gate, ctrl, diag = _random_gates(rng, n, int(rng.integers(1, 200)), max_targets=int(rng.integers(1, 4)),
+                                                 max_ctrls=int(rng.integers(0, 3)), diag_prob=[0.0, 0.3, 0.8][seed % 3])
+            gate = [[ids[q] for q in t] for t in gate]
+            ctrl = [[ids[q] for q in t] for t in ctrl]
+            size = int(rng.integers(1, 7))
+            S.set_mode(1)
+            exp = S.ClusterScheduler(gate, ctrl, diag, locals_, globals_, size).ScheduleCluster()
+            S.set_mode(0)
+            cs = S.ClusterScheduler(gate, ctrl, diag, locals_, globals_, size)
+            got = cs.ScheduleCluster()
+            assert list(got) == list(exp), (seed, n, size)
+            assert cs.evaluated() <= max(1, cs.candidates())
+    finally:
+        S.set_mode(0)
+
+
 @needs_ref
 @pytest.mark.parametrize("seed", range(40))
 def test_swap_scheduler_fuzz(seed):
