@@ -121,45 +121,123 @@ std::vector<Id> SwapScheduler::ScheduleSwap()
      if (gate_.empty()) return {};
      best_score_ = 0;
      best_locals_ = 0;
+     // tables for the zero-budget tails (see tail())
+     const int n = static_cast<int>(gate_.size());
+     all_.resize(n);
+     isdiag_.resize(n);
+     suffix_w_.assign(n + 1, 0);
+     kmax_ = 1;
+     min_qubits_ = 64;
+     future_.assign(n + 1, 0);
+     Mask used = 0;
+     for (int i = n - 1; i >= 0; --i) {
+          all_[i] = gate_[i] | ctrl_[i];
+          future_[i] = future_[i + 1] | all_[i];
+          min_qubits_ = std::min(min_qubits_, popcount(all_[i]));
+          isdiag_[i] = diag_[i] ? 1 : 0;
+          suffix_w_[i] = suffix_w_[i + 1] + weight_[i];
+          kmax_ = std::max(kmax_, popcount(all_[i]));
+          used |= all_[i];
+     }
+     nq_ = used ? 64 - __builtin_clzll(used) : 0;
+     qubit_suffix_w_.assign(static_cast<size_t>(nq_) * (n + 1), 0);
+     for (int q = 0; q < nq_; ++q) {
+          int* row = &qubit_suffix_w_[static_cast<size_t>(q) * (n + 1)];
+          for (int i = n - 1; i >= 0; --i) row[i] = row[i + 1] + (((all_[i] >> q) & 1) ? weight_[i] : 0);
+     }
+     // the path that takes every gate it can is part of the walk for any budget: its score is a floor of the result
+     {
+          Mask locals = 0, bad = 0;
+          int score = 0;
+          for (int i = 0; i < n; ++i) {
+               if (can_take(i, locals, bad)) {
+                    score += weight_[i];
+                    if (!isdiag_[i]) locals |= gate_[i];
+               }
+               else bad |= all_[i];
+          }
+          floor_ = score;
+     }
      search(0, 0, 0, 0, num_splits_);
      return u_.ids_of(best_locals_);
 }
 
-// Budgeted backtracking; returns the unused split budget.  Branch order: skip first, then take.
-int SwapScheduler::search(int pos, Mask locals, Mask bad, int score, int splits)
+// A node entered without budget never branches again (a takeable gate is taken, anything else is skipped), hands
+// back no budget, and only its end matters: scores grow along the path and the local set stops changing after
+// the last take.  The result of ScheduleSwap() is the FIRST node of the walk with the highest score, so a tail
+// that cannot reach floor_ (<= that highest score) is irrelevant and is not walked.  Bound: a remaining gate on
+// a blocked qubit is lost; every lost gate is counted at most kmax_ times in the per-qubit suffix weights.
+void SwapScheduler::tail(int pos, Mask locals, Mask bad, int score)
 {
+     const int n = static_cast<int>(gate_.size());
+     {
+          long lost = 0;
+          const size_t stride = static_cast<size_t>(n) + 1;
+          for (Mask m = bad; m; m &= m - 1) {
+               const int q = __builtin_ctzll(m);
+               if (q < nq_) lost += qubit_suffix_w_[q * stride + pos];
+          }
+          const long reach = score + suffix_w_[pos] - (lost + kmax_ - 1) / kmax_;
+          if (reach < floor_) return;
+     }
+     for (; pos < n; ++pos) {
+          const Mask a = all_[pos];
+          bool take = (a & bad) == 0;
+          if (take && !isdiag_[pos]) take = popcount(gate_[pos] | locals) <= num_locals_;
+          if (take) {
+               score += weight_[pos];
+               if (!isdiag_[pos]) locals |= gate_[pos];
+          }
+          else bad |= a;
+     }
      if (score > best_score_) {
           best_score_ = score;
           best_locals_ = locals;
      }
-     if (pos == static_cast<int>(gate_.size())) return splits;
+}
 
-     const bool takeable = can_take(pos, locals, bad);
-     bool skip = true;
-     int branches = 1;
-     if (takeable) {
-          if (!diag_[pos]) {
-               if (subset(gate_[pos], locals)) skip = false;  // already local: always take
-               else branches = 2;
+// Budgeted backtracking; returns the unused split budget.  Branch order: skip first, then take.
+// Only a gate that can be taken AND needs new local qubits branches (one unit of budget; the skip side gets half
+// of what is left and hands back what it did not use).  Everything else — a gate that cannot be taken, a diagonal
+// gate, a gate whose targets are already local — has a single continuation that receives and returns the whole
+// budget, so those nodes are walked in a loop and only branches recurse; the take side of a branch continues in
+// the same frame.  Visit order, budget flow and best-so-far updates are those of the node-per-gate recursion
+// (reference: swap_scheduler.cpp:86-170); the reference walk is ~99 % such single-continuation nodes.
+int SwapScheduler::search(int pos, Mask locals, Mask bad, int score, int splits)
+{
+     const int n = static_cast<int>(gate_.size());
+     for (;;) {
+          if (splits == 0) {
+               tail(pos, locals, bad, score);
+               return 0;
           }
-          else {
-               skip = false;  // diagonal gates never constrain the local set
+          if (score > best_score_) {
+               best_score_ = score;
+               best_locals_ = locals;
           }
+          if (pos == n) return splits;
+          const Mask a = all_[pos];
+          const bool is_diag = isdiag_[pos] != 0;
+          const bool takeable = (a & bad) == 0 && (is_diag || popcount(gate_[pos] | locals) <= num_locals_);
+          if (!takeable) {
+               bad |= a;
+               ++pos;
+               // no remaining gate has all its qubits unblocked: the rest of the path neither scores nor branches
+               if (popcount(future_[pos] & ~bad) < min_qubits_) return splits;
+               continue;
+          }
+          if (is_diag || subset(gate_[pos], locals)) {
+               score += weight_[pos];
+               ++pos;
+               continue;
+          }
+          splits -= 1;
+          const int give = splits / 2;
+          splits += search(pos + 1, locals, bad | a, score, give) - give;
+          locals |= gate_[pos];
+          score += weight_[pos];
+          ++pos;
      }
-     if (splits == 0 && takeable && skip) {  // out of budget: take only
-          skip = false;
-          branches = 1;
-     }
-     splits -= branches - 1;
-     if (skip) {
-          const int give = splits / branches;
-          splits += search(pos + 1, locals, bad | gate_[pos] | ctrl_[pos], score, give) - give;
-     }
-     if (takeable) {
-          const Mask next_locals = diag_[pos] ? locals : (locals | gate_[pos]);
-          splits = search(pos + 1, next_locals, bad, score + weight_[pos], splits);
-     }
-     return splits;
 }
 
 // ------------------------------------------------------------------------------------ ClusterScheduler

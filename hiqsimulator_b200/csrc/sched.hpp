@@ -42,6 +42,7 @@ private:
      bool merge_next(int i);
      void fuse_single_qubit_gates();
      int search(int pos, Mask locals, Mask bad, int score, int splits);
+     void tail(int pos, Mask locals, Mask bad, int score);
 
      int num_splits_, num_locals_;
      Universe u_;
@@ -50,6 +51,13 @@ private:
      std::vector<int> weight_;
      int best_score_ = 0;
      Mask best_locals_ = 0;
+     // zero-budget tails
+     std::vector<Mask> all_;
+     std::vector<uint8_t> isdiag_;
+     std::vector<int> suffix_w_;         // weight of gates pos..end
+     std::vector<int> qubit_suffix_w_;   // [qubit][pos]: weight of gates pos..end touching the qubit
+     std::vector<Mask> future_;          // qubits touched by gates pos..end
+     int nq_ = 0, kmax_ = 1, floor_ = 0, min_qubits_ = 0;
 };
 
 class ClusterScheduler {

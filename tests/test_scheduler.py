@@ -118,6 +118,34 @@ def test_swap_scheduler_fuzz(seed):
         assert list(got) == list(exp)
 
 
+@needs_ref
+@pytest.mark.parametrize("block", range(6))
+def test_swap_scheduler_layered_small_budgets(block):
+    """Layered circuits (long single-continuation runs, dead paths) under tight and ample split budgets: the
+    looped walk, the zero-budget tails and the dead-path exit of csrc/sched.cpp keep the reference's answer."""
+    R = ref.load_ref_sched()
+    for seed in range(block * 20, block * 20 + 20):
+        rng = np.random.default_rng(7000 + seed)
+        n = int(rng.integers(4, 22))
+        gate, ctrl, diag = [], [], []
+        for _ in range(int(rng.integers(1, 5))):
+            gate += [[q] for q in range(n)]
+            ctrl += [[] for _ in range(n)]
+            diag += [bool(rng.random() < 0.2) for _ in range(n)]
+            perm = [int(x) for x in rng.permutation(n)]
+            for a, b in zip(perm[0::2], perm[1::2]):
+                if rng.random() < 0.5:
+                    gate.append([a]); ctrl.append([b]); diag.append(bool(rng.random() < 0.5))
+                else:
+                    gate.append([a, b]); ctrl.append([]); diag.append(False)
+        num_locals = int(rng.integers(3, n + 1))
+        splits = int(rng.choice([0, 1, 2, 3, 7, 20, 100, 1000, 10 ** 4, 10 ** 6]))
+        for fuse in (True, False):
+            exp = R.SwapScheduler(gate, ctrl, diag, splits, num_locals, fuse).ScheduleSwap()
+            got = _mine().SwapScheduler(gate, ctrl, diag, splits, num_locals, fuse).ScheduleSwap()
+            assert list(got) == list(exp), (seed, splits, fuse)
+
+
 def greedy_log(n, cmds, R, max_local, sched_module, cluster=4, supremacy=False):
     """Full GreedyScheduler run against a dry-run engine; returns the emitted schedule."""
     from hiqsimulator_b200 import _cppsim_mpi as M
