@@ -357,6 +357,17 @@ def main():
                     "reference_passes_per_launch": mean_ref, "effective_gbs_per_launch": achieved * mean_ref,
                     "note": "achieved counts the bytes a launch really moves (32 B x 2^L); a launch that also carries folded "
                             "diagonal passes of the plan does their work in the same pass (effective = achieved x passes per launch)"}
+        # measured DRAM traffic of the same kernel (ncu --set full capture at L = 30, profiles/ncu_traffic.json)
+        try:
+            with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+                cap = json.load(f)["kernels"].get(gname(dom))
+            if cap:
+                per_amp = cap["dram_gbytes"] * 1e9 / (1 << cap["L"])
+                roofline["traffic"] = per_amp * (1 << L)
+                roofline["traffic_source"] = "%s: %.3f GB at L=%d (%.2f B/amplitude), scaled to L=%d" % (
+                    cap["source"], cap["dram_gbytes"], cap["L"], per_amp, L)
+        except (OSError, KeyError, ValueError):
+            pass
         for g, v in sorted(groups.items(), key=lambda kv: -tot(kv[1])):
             per = 32.0 * (1 << L) if g[0] != 4 else 16.0 * (1 << L) * (1 - 2.0 ** -g[1])
             m = tot(v) / len(v)
