@@ -31,6 +31,7 @@ import copy
 import gc
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -333,14 +334,16 @@ def main():
     groups = {}
     for kind_id, k, variant, ms, n_ref in timings:
         folded = kind_id == 1 and n_ref > 1
-        groups.setdefault((kind_id, k if kind_id != 2 else 0, variant, folded), []).append((ms, n_ref))
+        # dense DIRECT launches of block-structured matrices carry their mixing bits in variant bits 8..
+        groups.setdefault((kind_id, k if kind_id != 2 else 0, variant & 0xff, folded, variant >> 8), []).append((ms, n_ref))
     names = {1: "dense", 2: "diag_batch", 3: "scale", 4: "swap"}
     vnames = {0: "", 1: "direct", 2: "tiled", 3: "dmma"}
 
     def gname(g):
         if g[0] == 2:
             return "diag_batch" if not args.no_batch else "diag"
-        return "%s_k%d_%s%s" % (names.get(g[0], "?"), g[1], vnames.get(g[2], ""), "+prediag" if g[3] else "")
+        return "%s_k%d_%s%s%s" % (names.get(g[0], "?"), g[1], vnames.get(g[2], ""), ("_mix%d" % g[4]) if g[4] else "",
+                                  "+prediag" if g[3] else "")
     peak, peak_src = measured_peaks()
     gate_groups = {g: v for g, v in groups.items() if g[0] in (1, 2, 3)}
     roofline = None
@@ -360,7 +363,7 @@ def main():
         # measured DRAM traffic of the same kernel (ncu --set full capture at L = 30, profiles/ncu_traffic.json)
         try:
             with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-                cap = json.load(f)["kernels"].get(gname(dom))
+                cap = json.load(f)["kernels"].get(re.sub(r"_mix\d", "", gname(dom)))  # same kernel, fewer flops: same traffic
             if cap:
                 per_amp = cap["dram_gbytes"] * 1e9 / (1 << cap["L"])
                 roofline["traffic"] = per_amp * (1 << L)

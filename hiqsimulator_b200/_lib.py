@@ -70,6 +70,8 @@ _SIGNATURES = {
     "hiqk_pauli_apply": (C.c_int, [_vp, C.c_int, _u64, C.POINTER(PauliTerm), C.c_int, _vp, C.c_int, _vp, _u64, _u64, _vp]),
     "hiqk_permute_gather": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.POINTER(Perm), _vp]),
     "hiq_modinv": (C.c_int, [_u64, _u64, C.POINTER(_u64)]),
+    "hiqk_dense_block_shape": (C.c_int, [C.c_int, _dp, _ip]),
+    "hiqk_dense_direct_mixing_bits": (C.c_int, [C.c_int, _dp]),
     "hiqk_microbench": (C.c_int, [C.c_int, C.c_int, _dp]),
     "hiqk_launch_count": (_u64, []),
     "hiqk_debug_set_max_grid": (C.c_int, [C.c_int]),

@@ -23,8 +23,10 @@
 //           stored with one 128-bit store.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <type_traits>
 #include <vector>
 
 #include "hiq_device.cuh"
@@ -54,22 +56,29 @@ __device__ __forceinline__ void load_tuple(double2 (&in)[1 << K], const double2*
 }
 
 // out[b] = sum_c m[b][c] in[c]; every row is handed to `store(b, value)` as soon as it is done.
-template <int K, class Store>
+// KS < K: the matrix is block diagonal in its K - KS high index bits ("select" bits: the qubit multiplexes the
+// gate, it is never mixed — fused controls and diagonal factors produce these, dense_shape() below finds them
+// and moves them to the top).  Row b only meets the 2^KS columns that share its high bits; the skipped terms
+// are exact zeros, so the result equals the full product and the pass drops from 8 * 2^K to 8 * 2^KS flops
+// per amplitude — a QFT cluster (one or two Hadamards among controlled phases) turns from FP64-bound into HBM-bound.
+template <int K, int KS = K, class Store>
 __device__ __forceinline__ void apply_rows(const double2 (&in)[1 << K], const double2* __restrict__ m,
                                            Store store)
 {
      constexpr int D = 1 << K;
+     constexpr int DS = 1 << KS;
      if constexpr (K <= 4) {
 #pragma unroll
           for (int b = 0; b < D; ++b) {
                double2 acc = make_double2(0.0, 0.0);
 #pragma unroll
-               for (int c = 0; c < D; ++c) cmac(acc, m[b * D + c], in[c]);
+               for (int c = (b & ~(DS - 1)); c < (b & ~(DS - 1)) + DS; ++c) cmac(acc, m[b * D + c], in[c]);
                store(b, acc);
           }
      }
      else {
           // 32x32: keep the row loop rolled (a full unroll is 64 KB of SASS)
+          static_assert(K <= 4 || KS == K, "block form is instantiated for K <= 4 only");
 #pragma unroll 2
           for (int b = 0; b < D; ++b) {
                double2 acc = make_double2(0.0, 0.0);
@@ -80,7 +89,7 @@ __device__ __forceinline__ void apply_rows(const double2 (&in)[1 << K], const do
      }
 }
 
-template <int K, int THREADS, int MINB>
+template <int K, int THREADS, int MINB, int KS = K>
 __global__ void __launch_bounds__(THREADS, MINB) dense_direct_kernel(const __grid_constant__ DirectParams<K> p)
 {
      const uint64_t stride = static_cast<uint64_t>(gridDim.x) * THREADS;
@@ -88,14 +97,14 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_kernel(const __gri
           double2* base = p.psi + (insert_zero_bits(f, p.ins) | p.ctrl_mask);
           double2 in[1 << K];
           load_tuple<K>(in, base, p.off);
-          apply_rows<K>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
+          apply_rows<K, KS>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
      }
 }
 
 // DIRECT, staged: same arithmetic as dense_direct_kernel, but every thread's NEXT tuple is copied into
 // its shared-memory column by cp.async while the current tuple is multiplied, so the HBM latency of a
 // tuple hides behind 2^(2K) complex MACs instead of stalling the (register-limited, 4 warps/scheduler) CTA.
-template <int K, int THREADS, int MINB>
+template <int K, int THREADS, int MINB, int KS = K>
 __global__ void __launch_bounds__(THREADS, MINB) dense_direct_staged_kernel(const __grid_constant__ DirectParams<K> p)
 {
      extern __shared__ double2 dyn_smem[];
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_staged_kernel(cons
 #pragma unroll
           for (int c = 0; c < (1 << K); ++c) in[c] = stage[c][threadIdx.x];
           if (f + stride < p.n_free) prefetch(tuple_base(f + stride));
-          apply_rows<K>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
+          apply_rows<K, KS>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
      }
 }
 
@@ -141,7 +150,7 @@ struct DirectPreParams {
      DiagProg prog;
 };
 
-template <int K, int THREADS, int MINB>
+template <int K, int THREADS, int MINB, int KS = K>
 __global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const __grid_constant__ DirectPreParams<K> p)
 {
      // dynamic shared memory: stage[2^K][THREADS] (this thread's NEXT tuple, filled by cp.async while the
@@ -202,7 +211,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const _
                // with this thread's next tuple so its HBM latency hides behind the matrix product
                if (t + 1 < nt) prefetch(p.d.psi + (bidx | p.toff[t + 1]));
                else if (chunk + gridDim.x < n_chunks) prefetch(p.d.psi + bidx_next);
-               apply_rows<K>(in, p.d.m, [&](int b, double2 v) { base[p.d.off[b]] = v; });
+               apply_rows<K, KS>(in, p.d.m, [&](int b, double2 v) { base[p.d.off[b]] = v; });
           }
           bidx = bidx_next;
      }
@@ -392,9 +401,67 @@ static InsertBits make_insert_bits(const int* slots, int k, uint64_t ctrl_mask, 
      return ib;
 }
 
+// Block structure of a gate matrix.  Index bit l is a SELECT bit when m[b][c] == 0 for every pair b, c that
+// differ in bit l: the qubit only chooses which block acts on the other ("mixing") qubits.  shape.order lists the
+// mixing bits first (ascending), then the select bits; shape.ks = number of mixing bits (>= 1).
+struct DenseShape {
+     int ks;
+     int order[kMaxTargets];
+};
+
+static DenseShape dense_shape(int k, const double* matrix)
+{
+     const int d = 1 << k;
+     uint32_t mixes = 0;  // bit l set: some nonzero entry couples indices that differ in bit l
+     for (int b = 0; b < d; ++b)
+          for (int c = 0; c < d; ++c)
+               if (b != c && (matrix[2 * (b * d + c)] != 0.0 || matrix[2 * (b * d + c) + 1] != 0.0)) mixes |= static_cast<uint32_t>(b ^ c);
+     DenseShape sh;
+     sh.ks = 0;
+     for (int l = 0; l < k; ++l)
+          if ((mixes >> l) & 1u) sh.order[sh.ks++] = l;
+     int n = sh.ks;
+     for (int l = 0; l < k; ++l)
+          if (!((mixes >> l) & 1u)) sh.order[n++] = l;
+     if (sh.ks == 0) sh.ks = 1;  // a diagonal matrix: any bit may play the mixing one
+     return sh;
+}
+
+// slots and matrix re-expressed with index bit i' = old bit order[i']
+static void permute_gate(int k, const int* order, const int* slots, const double* matrix, int* slots_out, double* matrix_out)
+{
+     const int d = 1 << k;
+     int map[1 << kMaxTargets];  // new index -> old index
+     for (int x = 0; x < d; ++x) {
+          int o = 0;
+          for (int i = 0; i < k; ++i)
+               if ((x >> i) & 1) o |= 1 << order[i];
+          map[x] = o;
+     }
+     for (int i = 0; i < k; ++i) slots_out[i] = slots[order[i]];
+     for (int b = 0; b < d; ++b)
+          for (int c = 0; c < d; ++c) {
+               matrix_out[2 * (b * d + c)] = matrix[2 * (map[b] * d + map[c])];
+               matrix_out[2 * (b * d + c) + 1] = matrix[2 * (map[b] * d + map[c]) + 1];
+          }
+}
+
+// calls f(std::integral_constant<int, KS>) for the run-time ks in 1..K (K <= 4; K = 5 has the full form only)
+template <int K, class F>
+static int with_ks(int ks, F&& f)
+{
+     if constexpr (K >= 5) return f(std::integral_constant<int, K>{});
+     else {
+          if constexpr (K >= 2) if (ks == 1) return f(std::integral_constant<int, 1>{});
+          if constexpr (K >= 3) if (ks == 2) return f(std::integral_constant<int, 2>{});
+          if constexpr (K >= 4) if (ks == 3) return f(std::integral_constant<int, 3>{});
+          return f(std::integral_constant<int, K>{});
+     }
+}
+
 template <int K>
 static int launch_direct(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
-                         cudaStream_t stream)
+                         cudaStream_t stream, int ks = K)
 {
      DirectParams<K> p;
      p.psi = psi;
@@ -408,29 +475,33 @@ static int launch_direct(double2* psi, int L, const int* slots, const double* ma
      const uint64_t need = (p.n_free + THREADS - 1) / THREADS;
      const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(need, cap));
-     if constexpr (K >= 3 && K <= 4) {
-          // register-limited shapes: stage the next tuple through shared memory (cp.async)
-          if (need > cap) {
-               static bool attr_set = false;
-               if (!attr_set) {
-                    cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         64 * 1024);
-                    cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-                    attr_set = true;
+     return with_ks<K>(ks, [&](auto ks_c) {
+          constexpr int KS = decltype(ks_c)::value;
+          if constexpr (K >= 3 && K <= 4) {
+               // register-limited shapes: stage the next tuple through shared memory (cp.async)
+               if (need > cap) {
+                    static bool attr_set = false;
+                    if (!attr_set) {
+                         cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              64 * 1024);
+                         cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB, KS>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                              100);
+                         attr_set = true;
+                    }
+                    dense_direct_staged_kernel<K, THREADS, MINB, KS><<<grid, THREADS, sizeof(double2) * THREADS << K, stream>>>(p);
+                    count_launch();
+                    return check_launch("dense_direct_staged_kernel");
                }
-               dense_direct_staged_kernel<K, THREADS, MINB><<<grid, THREADS, sizeof(double2) * THREADS << K, stream>>>(p);
-               count_launch();
-               return check_launch("dense_direct_staged_kernel");
           }
-     }
-     dense_direct_kernel<K, THREADS, MINB><<<grid, THREADS, 0, stream>>>(p);
-     count_launch();
-     return check_launch("dense_direct_kernel");
+          dense_direct_kernel<K, THREADS, MINB, KS><<<grid, THREADS, 0, stream>>>(p);
+          count_launch();
+          return check_launch("dense_direct_kernel");
+     });
 }
 
 template <int K>
 static int launch_direct_pre(double2* psi, int L, const int* slots, const double* matrix, const hiqk_diag_op* pre, int n_pre,
-                             cudaStream_t stream)
+                             cudaStream_t stream, int ks = K)
 {
      static DirectPreParams<K> p;  // 10+ KB: keep it off the stack; launches are issued from one host thread per engine
      static std::mutex mu;
@@ -495,19 +566,22 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
      for (int j = je; j < p.prog.n; ++j)
           for (int t = 0; t < (1 << n_t); ++t)
                if (p.prog.usel[j][t]) p.fast = 0;
-     static bool attr_set = false;
-     if (!attr_set) {
-          cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-          cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-          attr_set = true;
-     }
      const size_t smem = sizeof(double2) * THREADS * ((1u << K) + std::max(p.e_npat, 1));
      const uint64_t n_chunks = (p.d.n_free + THREADS - 1) / THREADS;
      const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap));
-     dense_direct_pre_kernel<K, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p);
-     count_launch();
-     return check_launch("dense_direct_pre_kernel");
+     return with_ks<K>(ks, [&](auto ks_c) {
+          constexpr int KS = decltype(ks_c)::value;
+          static bool attr_set = false;
+          if (!attr_set) {
+               cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+               cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+               attr_set = true;
+          }
+          dense_direct_pre_kernel<K, THREADS, MINB, KS><<<grid, THREADS, smem, stream>>>(p);
+          count_launch();
+          return check_launch("dense_direct_pre_kernel");
+     });
 }
 
 template <int K>
@@ -616,6 +690,16 @@ static int launch_dmma(double2* psi, int L, const int* slots, const double* matr
      return check_launch("dense_dmma_kernel");
 }
 
+// HIQ_DENSE_BLOCKS=0 in the environment keeps every DIRECT launch on the full product (A/B measurements)
+static bool dense_blocks_enabled()
+{
+     static const bool on = [] {
+          const char* e = std::getenv("HIQ_DENSE_BLOCKS");
+          return !(e && e[0] == '0');
+     }();
+     return on;
+}
+
 // Kernel choice measured on B200 (profiles/r01_sweep_a_L30.jsonl): the 32x32 product is FP64-bound and
 // fastest on the tensor cores; k <= 4 is HBM-bound and fastest with one tuple per thread unless a
 // target sits in the lowest slots, where the shared-memory tile keeps the accesses coalesced.
@@ -635,7 +719,20 @@ static int dispatch_k(double2* psi, int L, const int* slots, const double* matri
 {
      if (variant == HIQK_DENSE_AUTO) variant = pick_variant(L, K, slots);
      switch (variant) {
-          case HIQK_DENSE_DIRECT: return launch_direct<K>(psi, L, slots, matrix, ctrl_mask, stream);
+          case HIQK_DENSE_DIRECT:
+               if constexpr (K >= 2 && K <= 4) {
+                    if (dense_blocks_enabled()) {
+                         const DenseShape sh = dense_shape(K, matrix);
+                         if (sh.ks < K) {
+                              int pslots[K];
+                              double pm[2 << (2 * K)];
+                              permute_gate(K, sh.order, slots, matrix, pslots, pm);
+                              return launch_direct<K>(psi, L, pslots, pm, ctrl_mask, stream, sh.ks);
+                         }
+                    }
+               }
+               return launch_direct<K>(psi, L, slots, matrix, ctrl_mask, stream);
+          case HIQK_DENSE_DIRECT_FULL: return launch_direct<K>(psi, L, slots, matrix, ctrl_mask, stream);
           case HIQK_DENSE_TILED: return launch_tiled<K>(psi, L, slots, matrix, ctrl_mask, stream);
           case HIQK_DENSE_DMMA:
                if constexpr (K >= 2) return launch_dmma<K>(psi, L, slots, matrix, ctrl_mask, stream);
@@ -650,6 +747,22 @@ extern "C" int hiqk_dense_pick_variant(int L, int k, const int* slots)
 {
      if (!slots || k < 1 || k > hiq::kMaxTargets) return HIQK_DENSE_DIRECT;
      return hiq::pick_variant(L, k, slots);
+}
+
+extern "C" int hiqk_dense_block_shape(int k, const double* matrix, int* order)
+{
+     if (!matrix || k < 1 || k > hiq::kMaxTargets) return hiq::set_error(HIQ_ERR_ARG, "hiqk_dense_block_shape: bad argument"), -1;
+     const hiq::DenseShape sh = hiq::dense_shape(k, matrix);
+     if (order)
+          for (int i = 0; i < k; ++i) order[i] = sh.order[i];
+     return sh.ks;
+}
+
+extern "C" int hiqk_dense_direct_mixing_bits(int k, const double* matrix)
+{
+     if (!matrix || k < 1 || k > hiq::kMaxTargets) return hiq::set_error(HIQ_ERR_ARG, "hiqk_dense_direct_mixing_bits: bad argument"), -1;
+     if (k < 2 || k > 4 || !hiq::dense_blocks_enabled()) return k;
+     return hiq::dense_shape(k, matrix).ks;
 }
 
 extern "C" int hiqk_dense_prediag_supported(int L, int k, const int* slots)
@@ -674,11 +787,23 @@ extern "C" int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slo
      }
      double2* psi = static_cast<double2*>(slab);
      cudaStream_t st = static_cast<cudaStream_t>(stream);
+     int pslots[kMaxTargets];
+     double pm[2 << (2 * 4)];
+     int ks = k;
+     if (k >= 2 && dense_blocks_enabled()) {
+          const DenseShape sh = dense_shape(k, matrix);
+          if (sh.ks < k) {
+               permute_gate(k, sh.order, slots, matrix, pslots, pm);
+               slots = pslots;
+               matrix = pm;
+               ks = sh.ks;
+          }
+     }
      switch (k) {
           case 1: return launch_direct_pre<1>(psi, L, slots, matrix, pre, n_pre, st);
-          case 2: return launch_direct_pre<2>(psi, L, slots, matrix, pre, n_pre, st);
-          case 3: return launch_direct_pre<3>(psi, L, slots, matrix, pre, n_pre, st);
-          default: return launch_direct_pre<4>(psi, L, slots, matrix, pre, n_pre, st);
+          case 2: return launch_direct_pre<2>(psi, L, slots, matrix, pre, n_pre, st, ks);
+          case 3: return launch_direct_pre<3>(psi, L, slots, matrix, pre, n_pre, st, ks);
+          default: return launch_direct_pre<4>(psi, L, slots, matrix, pre, n_pre, st, ks);
      }
 }
 

@@ -484,6 +484,11 @@ void Engine::launch(const Descriptor& d, int variant, const std::vector<hiqk_dia
      for (int r: refs) n_ref += r;
      TimedPass tp{d.kind, d.k, variant, n_ref, nullptr, nullptr};
      if (timing_) {
+          if (d.kind == HIQ_DESC_DENSE && variant == HIQK_DENSE_DIRECT) {
+               // label the reduced product: bits 8.. of the variant = mixing bits when fewer than k
+               const int ks = hiqk_dense_direct_mixing_bits(d.k, reinterpret_cast<const double*>(d.payload.data()));
+               if (ks > 0 && ks < d.k) tp.variant |= ks << 8;
+          }
           tp.start = take_event();
           tp.stop = take_event();
           cudaEventRecord(tp.start, stream_);

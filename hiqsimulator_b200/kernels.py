@@ -12,7 +12,7 @@ import numpy as np
 
 from ._lib import DiagOp, PauliTerm, Perm, check, lib
 
-AUTO, DIRECT, TILED, DMMA = 0, 1, 2, 3
+AUTO, DIRECT, TILED, DMMA, DIRECT_FULL = 0, 1, 2, 3, 4
 
 
 def _slab(t):
@@ -42,6 +42,17 @@ def apply_dense(state, slots, matrix, ctrl_mask=0, variant=AUTO):
     p, L = _slab(state)
     keep, mp = _cplx(matrix)
     check(lib().hiqk_apply_dense(p, L, len(slots), _ints(slots), mp, ctrl_mask, variant, _stream()))
+
+
+def dense_block_shape(matrix):
+    """(number of mixing index bits, bit order with the mixing bits first) of a 2^k x 2^k matrix — host only."""
+    keep, mp = _cplx(matrix)
+    k = int(keep.shape[0]).bit_length() - 1
+    order = (C.c_int * k)()
+    ks = lib().hiqk_dense_block_shape(k, mp, order)
+    if ks < 0:
+        check(ks)
+    return ks, [int(x) for x in order]
 
 
 def apply_diag(state, slots, diag, ctrl_mask=0):

@@ -50,6 +50,7 @@ int hiq_device_count(void);
 #define HIQK_DENSE_DIRECT 1 /* one tuple per thread, registers only              */
 #define HIQK_DENSE_TILED 2  /* shared-memory tile, for targets in the lowest slots */
 #define HIQK_DENSE_DMMA 3   /* FP64 tensor-core path (k >= 2)                    */
+#define HIQK_DENSE_DIRECT_FULL 4 /* DIRECT without the block-structure shortcut (A/B measurements) */
 
 /* Dense k-qubit gate, k = 1..5, in place over a slab of 2^L amplitudes:
  * for every base index I with all target bits 0 and (I & ctrl_mask) == ctrl_mask
@@ -63,6 +64,18 @@ int hiqk_apply_dense(void* slab, int L, int k, const int* slots, const double* m
 
 /* The variant HIQK_DENSE_AUTO resolves to for these targets (so callers can label timings). */
 int hiqk_dense_pick_variant(int L, int k, const int* slots);
+
+/* Block structure the DIRECT kernels exploit (host-only, no device needed): returns the number of MIXING
+ * index bits of `matrix` (2^k x 2^k row-major complex128, host memory) and, if `order` is not NULL, the bit
+ * order that puts them first (order[i] = original bit at new position i).  A bit is a SELECT bit when every
+ * entry coupling two indices that differ in it is exactly zero: the qubit multiplexes the gate on the others
+ * (controls and diagonal factors folded into a fused cluster, reference fusion_mpi.hpp:167-187, produce
+ * these), and row b of the product only meets the 2^mixing columns that share its select bits — the same
+ * result as the full product of the reference kernels at 2^(k - mixing) times fewer flops.  -1 on bad input. */
+int hiqk_dense_block_shape(int k, const double* matrix, int* order);
+/* Mixing bits the DIRECT kernels will really use for this matrix: the block shape for k = 2..4, k otherwise
+ * or when HIQ_DENSE_BLOCKS=0 is set in the environment (so callers can label timings).  Host only. */
+int hiqk_dense_direct_mixing_bits(int k, const double* matrix);
 
 /* Diagonal k-qubit gate: psi[i] *= diag[d], d = target bits of i gathered in
  * matrix-bit order, where (i & ctrl_mask) == ctrl_mask. `diag` is HOST memory, 2^k complex128.

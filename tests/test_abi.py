@@ -42,3 +42,29 @@ def test_compute_fails_loudly_without_gpu():
     M.init_world(0, 1, b"", 0, 0)
     with pytest.raises(RuntimeError):
         M.SimulatorMPI(1, 10, 4)  # no device, no fallback
+
+
+def test_dense_block_shape_is_host_only_and_finds_select_bits():
+    """hiqk_dense_block_shape needs no device: select bits = index bits no nonzero entry mixes; QFT-like
+    clusters (Hadamards among controlled phases, fused as the reference fuses them) have them."""
+    import numpy as np
+    from hiqsimulator_b200 import kernels as K
+    h = np.array([[1, 1], [1, -1]]) / np.sqrt(2)
+    cr = np.diag([1, 1, 1, np.exp(0.3j)])
+    # bits (0, 1, 2, 3): H on bit 2, controlled phases between the others and bit 2 -> only bit 2 mixes
+    m = np.kron(np.eye(2), np.kron(h, np.eye(4)))
+    d = np.ones(16, dtype=complex)
+    for i in range(16):
+        if (i >> 2) & 1 and i & 1:
+            d[i] *= np.exp(0.7j)
+        if (i >> 2) & 1 and (i >> 3) & 1:
+            d[i] *= np.exp(0.2j)
+    m = m @ np.diag(d)
+    ks, order = K.dense_block_shape(m)
+    assert ks == 1 and order[0] == 2 and sorted(order) == [0, 1, 2, 3]
+    ks, order = K.dense_block_shape(np.kron(h, np.kron(np.eye(2), h)))
+    assert ks == 2 and order[:2] == [0, 2]
+    ks, order = K.dense_block_shape(np.kron(h, h))
+    assert ks == 2 and order == [0, 1]
+    ks, order = K.dense_block_shape(cr)  # diagonal: one nominal mixing bit
+    assert ks == 1 and sorted(order) == [0, 1]

@@ -185,6 +185,90 @@ def test_apply_dense_prediag(k, slots, n_pre):
     assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
 
 
+def multiplexed_matrix(k, select_bits, seed):
+    """unitary that is block diagonal in `select_bits`: one Haar block on the other bits per select value"""
+    mix = [l for l in range(k) if l not in select_bits]
+    m = np.zeros((1 << k, 1 << k), dtype=np.complex128)
+    for v in range(1 << len(select_bits)):
+        u = rand_matrix(len(mix), seed + 31 * v) if mix else np.array([[np.exp(1j * (seed + v))]])
+        hi = sum(((v >> i) & 1) << select_bits[i] for i in range(len(select_bits)))
+        for b in range(1 << len(mix)):
+            for c in range(1 << len(mix)):
+                fb = hi | sum(((b >> i) & 1) << mix[i] for i in range(len(mix)))
+                fc = hi | sum(((c >> i) & 1) << mix[i] for i in range(len(mix)))
+                m[fb, fc] = u[b, c]
+    return m
+
+
+BLOCK_CASES = [(2, (3, 9), (0,)), (2, (12, 2), (1,)), (3, (4, 5, 6), (1,)), (3, (13, 6, 2), (0, 2)), (3, (2, 9, 5), (2,)),
+               (4, (5, 2, 9, 12), (0,)), (4, (5, 2, 9, 12), (1, 3)), (4, (10, 11, 12, 13), (0, 1, 2)), (4, (4, 8, 6, 10), (2,)),
+               (4, (13, 3, 7, 2), (0, 3)), (4, (6, 7, 8, 9), (0, 1, 2, 3))]
+
+
+@pytest.mark.parametrize("k,slots,select", BLOCK_CASES)
+@pytest.mark.parametrize("ctrl", [0, "one"])
+def test_apply_dense_block_structure(k, slots, select, ctrl):
+    """fused gates that are block diagonal in some index bits take the reduced product: same result as the
+    full product (DIRECT_FULL) and as the oracle, wherever the select bits sit in the matrix index"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    m = multiplexed_matrix(k, list(select), 7 * k + len(select))
+    ks, order = K.dense_block_shape(m)
+    assert ks == max(1, k - len(select)) and sorted(order) == list(range(k))
+    ref = rand_state(L, 200 + k)
+    cm = _ctrl_mask(L, slots, ctrl, 9)
+    exp = ref.copy()
+    statevec.apply_dense(exp, list(slots), m, cm)
+    for variant in (K.AUTO, K.DIRECT, K.DIRECT_FULL):
+        dev = torch.from_numpy(ref.copy()).cuda()
+        K.apply_dense(dev, list(slots), m, cm, variant)
+        assert np.abs(dev.cpu().numpy() - exp).max() <= TOL, variant
+
+
+@pytest.mark.parametrize("k,slots,select", [c for c in BLOCK_CASES if c[0] >= 2])
+@pytest.mark.parametrize("n_pre", [1, 6])
+def test_apply_dense_prediag_block_structure(k, slots, select, n_pre):
+    """folded diagonals + block-structured matrix: the class-E tables follow the permuted target order"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 15
+    m = multiplexed_matrix(k, list(select), 11 * k + len(select))
+    ref = rand_state(L, 300 + k)
+    ops = _rand_diag_ops(L, n_pre, 500 * k + n_pre)
+    ops[0] = (list(slots[:max(1, k - 1)]), np.exp(1j * np.linspace(0.1, 2.0, 1 << max(1, k - 1))))
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_dense_prediag(dev, list(slots), m, ops)
+    for sl, d in ops:
+        if sl:
+            statevec.apply_diag(ref, sl, d, 0)
+        else:
+            ref *= d[0]
+    statevec.apply_dense(ref, list(slots), m, 0)
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+def test_apply_dense_block_structure_multi_iteration(tiny_grid):
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 17
+    for k, slots, select in [(4, (5, 2, 9, 12), (1, 3)), (3, (13, 6, 2), (0,)), (4, (12, 13, 14, 15), (0, 1, 2))]:
+        m = multiplexed_matrix(k, list(select), 5 * k)
+        ref = rand_state(L, 400 + k)
+        dev = torch.from_numpy(ref.copy()).cuda()
+        K.apply_dense(dev, list(slots), m, 0, K.AUTO)
+        ops = _rand_diag_ops(L, 5, 77 * k)
+        K.apply_dense_prediag(dev, list(slots), m, ops)
+        statevec.apply_dense(ref, list(slots), m, 0)
+        for sl, d in ops:
+            if sl:
+                statevec.apply_diag(ref, sl, d, 0)
+            else:
+                ref *= d[0]
+        statevec.apply_dense(ref, list(slots), m, 0)
+        assert np.abs(dev.cpu().numpy() - ref).max() <= TOL, (k, slots, select)
+
+
 @pytest.fixture
 def tiny_grid():
     """3 CTAs only: every persistent kernel iterates many times per CTA (the path 2^30+ slabs take)"""

@@ -51,6 +51,19 @@ def main():
     rec("dense+E2(ov2)", lambda: K.apply_dense_prediag(state, tg, u4, ops), n_ops=2)
     ops = [([tg[0], tg[1], 3, 15], diag(4))] + [([int(x) for x in rng.choice(hi, size=4, replace=False)], diag(4)) for _ in range(11)]
     rec("dense+E1+S0x11 (qft-like)", lambda: K.apply_dense_prediag(state, tg, u4, ops), n_ops=12)
+    # block-structured matrices (select bits = the high matrix bits here): reduced product vs the full one
+    def blocks(ks):
+        m = np.zeros((16, 16), dtype=np.complex128)
+        for v in range(16 >> ks):
+            zz = rng.normal(size=(1 << ks, 1 << ks)) + 1j * rng.normal(size=(1 << ks, 1 << ks))
+            q, _ = np.linalg.qr(zz)
+            m[v << ks:(v + 1) << ks, v << ks:(v + 1) << ks] = q
+        return m
+    for ks in (1, 2, 3):
+        mb = blocks(ks)
+        rec("dense_mix%d" % ks, lambda: K.apply_dense(state, tg, mb, 0, K.DIRECT), mixing_bits=ks)
+        rec("dense_mix%d_full_product" % ks, lambda: K.apply_dense(state, tg, mb, 0, K.DIRECT_FULL), mixing_bits=ks)
+        rec("dense_mix%d+E1+S0x11 (qft-like)" % ks, lambda: K.apply_dense_prediag(state, tg, mb, ops), n_ops=12, mixing_bits=ks)
     for n in (1, 4, 10, 16):
         ops = [([int(x) for x in rng.choice(np.arange(0, L), size=4, replace=False)], diag(4)) for _ in range(n)]
         rec("diag_batch_x%d" % n, lambda: K.apply_diag_batch(state, ops), n_ops=n)
