@@ -700,17 +700,25 @@ static bool dense_blocks_enabled()
      return on;
 }
 
-// Kernel choice measured on B200 (profiles/r01_sweep_a_L30.jsonl): the 32x32 product is FP64-bound and
-// fastest on the tensor cores; k <= 4 is HBM-bound and fastest with one tuple per thread unless a
-// target sits in the lowest slots, where the shared-memory tile keeps the accesses coalesced.
+// Kernel choice measured on B200 under sustained load (profiles/r01k_sustained_L30.jsonl; a long circuit runs
+// power-capped, the burst figures of profiles/r01_sweep_a_L30.jsonl rank some shapes differently): the 32x32
+// product is FP64-bound and fastest on the tensor cores; k <= 4 is HBM-bound and fastest with one tuple per
+// thread as long as every warp access covers whole 32 B sectors (lowest target slot >= 1, >= 2 for k = 2);
+// a target in slot 0 takes the shared-memory tile (k <= 3) or, for k = 4, the tensor-core kernel, whose
+// A fragments are loaded sector-complete whatever the slots are.
 static int pick_variant(int L, int k, const int* slots)
 {
      int min_slot = 64;
      for (int l = 0; l < k; ++l) min_slot = std::min(min_slot, slots[l]);
      const bool can_tile = tile_bits_for(k, L) >= k + 3 && L >= 10;
-     if (k == 5) return (L - k >= 3) ? HIQK_DENSE_DMMA : HIQK_DENSE_DIRECT;
-     if (k == 4) return (min_slot < 1 && can_tile) ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT;
-     return (min_slot < 2 && can_tile) ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT;
+     const bool can_dmma = L - k >= 3;
+     if (k == 5) return can_dmma ? HIQK_DENSE_DMMA : HIQK_DENSE_DIRECT;
+     if (k == 4) {
+          if (min_slot >= 1) return HIQK_DENSE_DIRECT;
+          return can_dmma ? HIQK_DENSE_DMMA : (can_tile ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT);
+     }
+     if (k == 2) return (min_slot < 2 && can_tile) ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT;
+     return (min_slot < 1 && can_tile) ? HIQK_DENSE_TILED : HIQK_DENSE_DIRECT;
 }
 
 template <int K>

@@ -158,7 +158,8 @@ def test_apply_diag_batch(L, n_ops, seed):
 
 
 @pytest.mark.parametrize("k,slots", [(1, (2,)), (1, (13,)), (2, (3, 9)), (2, (12, 2)), (3, (4, 5, 6)), (3, (13, 6, 2)),
-                                     (4, (5, 2, 9, 12)), (4, (10, 11, 12, 13)), (4, (4, 8, 6, 10))])
+                                     (4, (5, 2, 9, 12)), (4, (10, 11, 12, 13)), (4, (4, 8, 6, 10)),
+                                     (1, (1,)), (3, (1, 6, 9)), (3, (9, 1, 2)), (4, (1, 5, 9, 12)), (4, (4, 3, 2, 1))])
 @pytest.mark.parametrize("n_pre", [1, 4, 16])
 def test_apply_dense_prediag(k, slots, n_pre):
     """one pass == n_pre diagonal passes followed by the dense pass (overlapping and disjoint slots)"""
