@@ -340,6 +340,8 @@ def main():
     vnames = {0: "", 1: "direct", 2: "tiled", 3: "dmma"}
 
     def gname(g):
+        if g[0] == 4:
+            return "swap_q%d%s" % (g[1], "_wait_for_peers" if g[2] == 1 else "")
         if g[0] == 2:
             return "diag_batch" if not args.no_batch else "diag"
         return "%s_k%d_%s%s%s" % (names.get(g[0], "?"), g[1], vnames.get(g[2], ""), ("_mix%d" % g[4]) if g[4] else "",
@@ -377,7 +379,9 @@ def main():
             breakdown.append({"kernel": gname(g), "launches": len(v), "reference_passes": sum(r for _, r in v),
                               "total_ms": round(tot(v), 3), "mean_ms": round(m, 4), "gbs": round(per / (m * 1e-3) / 1e9, 1)})
     swap_gbs = None
-    swap_ms = sum(t[3] for t in timings if t[0] == 4)
+    # the exchange itself; the time a rank waits for its peers to reach the swap (rank skew) is reported apart
+    swap_ms = sum(t[3] for t in timings if t[0] == 4 and t[2] == 0)
+    swap_wait_ms = sum(t[3] for t in timings if t[0] == 4 and t[2] == 1)
     if swap_ms > 0:
         swap_gbs = (stats1["swap_bytes_sent"] - stats0["swap_bytes_sent"]) / (swap_ms * 1e-3) / 1e9
     del be, sim, ext
@@ -451,6 +455,7 @@ def main():
             "circuit_seconds": {"device_only": ms_per_step * 1e-3, "host_schedule_s": shape["host_schedule_s"],
                                 "end_to_end": e2e["seconds_per_step"] if e2e else None},
             "swap_nvlink_gbs_per_gpu": swap_gbs,
+            "swap_wait_for_peers_ms_per_step": swap_wait_ms / args.steps,
             "swap_transport": {"peer_mapped_in_place": int(stats1["swaps_p2p"] - stats0["swaps_p2p"]),
                                "staged_nccl": int(stats1["swaps_staged"] - stats0["swaps_staged"]),
                                "nvlink_peak_gbs_per_dir": 900.0,

@@ -824,12 +824,26 @@ void Engine::swap_qubits(const std::vector<Index>& pairs)
           if (timing_) {
                tp.start = take_event();
                tp.stop = take_event();
+               swap_mark_[0] = take_event();
+               swap_mark_[1] = take_event();
+               swap_marked_ = false;
                cudaEventRecord(tp.start, stream_);
           }
           exchange(gpos, slots);
           if (timing_) {
                cudaEventRecord(tp.stop, stream_);
+               if (swap_marked_) {
+                    // variant 1 = waiting for the slowest peer of the group to arrive (rank skew: ranks whose global
+                    // control bits are 0 skip gates, SimulatorMPI.cpp:735-738), variant 0 = the exchange itself
+                    timed_.push_back(TimedPass{HIQ_DESC_SWAP, tp.k, 1, 0, tp.start, swap_mark_[0]});
+                    tp.start = swap_mark_[1];
+               }
+               else {
+                    event_pool_.push_back(swap_mark_[0]);
+                    event_pool_.push_back(swap_mark_[1]);
+               }
                timed_.push_back(tp);
+               swap_mark_[0] = swap_mark_[1] = nullptr;
           }
      }
      for (size_t i = 0; i < gpos.size(); ++i) std::swap(locals_[slots[i]], globals_[gpos[i]]);
@@ -1006,6 +1020,11 @@ bool Engine::exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& 
           counts.push_back(rank_ < pr ? half : n - half);
      }
      group_barrier(peer_ranks);  // every peer has finished the gates before its slab is touched
+     if (swap_mark_[0]) {
+          cudaEventRecord(swap_mark_[0], stream_);
+          cudaEventRecord(swap_mark_[1], stream_);
+          swap_marked_ = true;
+     }
      cu(hiqk_swap_p2p(slab_.data(), ptrs.data(), static_cast<int>(ptrs.size()), L, q, slots.data(), pats.data(), pattern_of(rank_),
                       begins.data(), counts.data(), stream_));
      group_barrier(peer_ranks);  // ... and nobody moves on while a peer still writes into its slab

@@ -191,6 +191,8 @@ private:
           int kind, k, variant, n_ref;
           cudaEvent_t start, stop;
      };
+     cudaEvent_t swap_mark_[2] = {nullptr, nullptr};  // recorded right after the entry barrier of a timed exchange
+     bool swap_marked_ = false;
      // Diagonal fused gates wait here until the next dense launch (which applies them to the tuples
      // it loads) or the next observation of the slab (one batched pass).  ref_passes[i] = how many
      // passes of the reference's plan op i stands for (ops over the same slots are multiplied on the host).
