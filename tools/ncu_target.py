@@ -38,3 +38,15 @@ for _ in range(args.reps):
     K.apply_diag_batch(state, ops[1:])
 torch.cuda.synchronize()
 print("ok2", K.prob_masked(state))
+# block-structured matrix (two mixing bits, as 15 of the 21 dense passes of QFT-33): reduced product, plain and folded
+m2 = np.zeros((16, 16), dtype=np.complex128)
+for v in range(4):
+    zz = rng.normal(size=(4, 4)) + 1j * rng.normal(size=(4, 4))
+    qq, _ = np.linalg.qr(zz)
+    m2[4 * v:4 * v + 4, 4 * v:4 * v + 4] = qq
+for _ in range(args.reps):
+    K.apply_dense(state, tg, m2, 0, K.DIRECT)
+    K.apply_dense_prediag(state, tg, m2, ops)
+    K.apply_dense(state, [0, 9, 17, 25], u4, 0, K.AUTO)  # slot-0 target: tensor-core kernel
+torch.cuda.synchronize()
+print("ok3", K.prob_masked(state))
