@@ -45,6 +45,7 @@ struct DirectParams {
      InsertBits ins;      // target and control slots, ascending
      uint64_t off[1 << K];
      double2 m[1 << (2 * K)];
+     double msum[K == 4 ? (1 << (2 * K)) : 1];  // Re + Im of every entry (three-multiplication product, K = 4 only)
 };
 
 template <int K>
@@ -61,6 +62,30 @@ __device__ __forceinline__ void load_tuple(double2 (&in)[1 << K], const double2*
 // and moves them to the top).  Row b only meets the 2^KS columns that share its high bits; the skipped terms
 // are exact zeros, so the result equals the full product and the pass drops from 8 * 2^K to 8 * 2^KS flops
 // per amplitude — a QFT cluster (one or two Hadamards among controlled phases) turns from FP64-bound into HBM-bound.
+// Full 16x16 product with three real multiplications per complex one (Re = Ax - By, Im = (A+B)(x+y) - Ax - By):
+// 768 DFMA + 64 DADD per tuple instead of 1024 DFMA.  Under the sustained power cap the k = 4 pass is limited by
+// FP64 issue, so the pass gets faster; the rounding differs from the four-multiplication form by a few ulp of
+// the row norm (amplitudes agree with the reference far inside the 1e-12 tolerance of BASELINE.json).
+template <class Store>
+__device__ __forceinline__ void apply_rows_3m(const double2 (&in)[16], const double2* __restrict__ m, const double* __restrict__ msum,
+                                              Store store)
+{
+     double s[16];
+#pragma unroll
+     for (int c = 0; c < 16; ++c) s[c] = in[c].x + in[c].y;
+#pragma unroll
+     for (int b = 0; b < 16; ++b) {
+          double t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+               t1 = fma(m[b * 16 + c].x, in[c].x, t1);
+               t2 = fma(m[b * 16 + c].y, in[c].y, t2);
+               t3 = fma(msum[b * 16 + c], s[c], t3);
+          }
+          store(b, make_double2(t1 - t2, t3 - t1 - t2));
+     }
+}
+
 template <int K, int KS = K, class Store>
 __device__ __forceinline__ void apply_rows(const double2 (&in)[1 << K], const double2* __restrict__ m,
                                            Store store)
@@ -89,7 +114,7 @@ __device__ __forceinline__ void apply_rows(const double2 (&in)[1 << K], const do
      }
 }
 
-template <int K, int THREADS, int MINB, int KS = K>
+template <int K, int THREADS, int MINB, int KS = K, bool M3 = false>
 __global__ void __launch_bounds__(THREADS, MINB) dense_direct_kernel(const __grid_constant__ DirectParams<K> p)
 {
      const uint64_t stride = static_cast<uint64_t>(gridDim.x) * THREADS;
@@ -97,14 +122,15 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_kernel(const __gri
           double2* base = p.psi + (insert_zero_bits(f, p.ins) | p.ctrl_mask);
           double2 in[1 << K];
           load_tuple<K>(in, base, p.off);
-          apply_rows<K, KS>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
+          if constexpr (M3) apply_rows_3m(in, p.m, p.msum, [&](int b, double2 v) { base[p.off[b]] = v; });
+          else apply_rows<K, KS>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
      }
 }
 
 // DIRECT, staged: same arithmetic as dense_direct_kernel, but every thread's NEXT tuple is copied into
 // its shared-memory column by cp.async while the current tuple is multiplied, so the HBM latency of a
 // tuple hides behind 2^(2K) complex MACs instead of stalling the (register-limited, 4 warps/scheduler) CTA.
-template <int K, int THREADS, int MINB, int KS = K>
+template <int K, int THREADS, int MINB, int KS = K, bool M3 = false>
 __global__ void __launch_bounds__(THREADS, MINB) dense_direct_staged_kernel(const __grid_constant__ DirectParams<K> p)
 {
      extern __shared__ double2 dyn_smem[];
@@ -124,7 +150,8 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_staged_kernel(cons
 #pragma unroll
           for (int c = 0; c < (1 << K); ++c) in[c] = stage[c][threadIdx.x];
           if (f + stride < p.n_free) prefetch(tuple_base(f + stride));
-          apply_rows<K, KS>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
+          if constexpr (M3) apply_rows_3m(in, p.m, p.msum, [&](int b, double2 v) { base[p.off[b]] = v; });
+          else apply_rows<K, KS>(in, p.m, [&](int b, double2 v) { base[p.off[b]] = v; });
      }
 }
 
@@ -150,7 +177,7 @@ struct DirectPreParams {
      DiagProg prog;
 };
 
-template <int K, int THREADS, int MINB, int KS = K>
+template <int K, int THREADS, int MINB, int KS = K, bool M3 = false>
 __global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const __grid_constant__ DirectPreParams<K> p)
 {
      // dynamic shared memory: stage[2^K][THREADS] (this thread's NEXT tuple, filled by cp.async while the
@@ -211,7 +238,8 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const _
                // with this thread's next tuple so its HBM latency hides behind the matrix product
                if (t + 1 < nt) prefetch(p.d.psi + (bidx | p.toff[t + 1]));
                else if (chunk + gridDim.x < n_chunks) prefetch(p.d.psi + bidx_next);
-               apply_rows<K, KS>(in, p.d.m, [&](int b, double2 v) { base[p.d.off[b]] = v; });
+               if constexpr (M3) apply_rows_3m(in, p.d.m, p.d.msum, [&](int b, double2 v) { base[p.d.off[b]] = v; });
+               else apply_rows<K, KS>(in, p.d.m, [&](int b, double2 v) { base[p.d.off[b]] = v; });
           }
           bidx = bidx_next;
      }
@@ -386,6 +414,24 @@ static void fill_common(uint64_t (&off)[1 << K], double2 (&m)[1 << (2 * K)], con
      std::memcpy(m, matrix, sizeof(double2) << (2 * K));
 }
 
+template <int K>
+static void fill_msum(DirectParams<K>& p)
+{
+     if constexpr (K == 4)
+          for (int i = 0; i < (1 << (2 * K)); ++i) p.msum[i] = p.m[i].x + p.m[i].y;
+     else p.msum[0] = 0.0;
+}
+
+// HIQ_DENSE_3M=0 in the environment keeps the full k = 4 product on four multiplications (A/B measurements)
+static bool dense_3m_enabled()
+{
+     static const bool on = [] {
+          const char* e = std::getenv("HIQ_DENSE_3M");
+          return !(e && e[0] == '0');
+     }();
+     return on;
+}
+
 static InsertBits make_insert_bits(const int* slots, int k, uint64_t ctrl_mask, int shift = 0, int min_pos = 0)
 {
      std::vector<int> pos;
@@ -470,33 +516,38 @@ static int launch_direct(double2* psi, int L, const int* slots, const double* ma
      p.ctrl_mask = ctrl_mask;
      p.ins = make_insert_bits(slots, K, ctrl_mask);
      fill_common<K>(p.off, p.m, slots, matrix);
+     fill_msum<K>(p);
      constexpr int THREADS = (K >= 4) ? 128 : 256;
      constexpr int MINB = (K >= 5) ? 2 : (K == 4 ? 4 : 4);
      const uint64_t need = (p.n_free + THREADS - 1) / THREADS;
      const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(need, cap));
-     return with_ks<K>(ks, [&](auto ks_c) {
+     auto go = [&](auto ks_c, auto m3_c) {
           constexpr int KS = decltype(ks_c)::value;
+          constexpr bool M3 = decltype(m3_c)::value;
           if constexpr (K >= 3 && K <= 4) {
                // register-limited shapes: stage the next tuple through shared memory (cp.async)
                if (need > cap) {
                     static bool attr_set = false;
                     if (!attr_set) {
-                         cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB, KS, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                               64 * 1024);
-                         cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB, KS>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                              100);
+                         cudaFuncSetAttribute(dense_direct_staged_kernel<K, THREADS, MINB, KS, M3>,
+                                              cudaFuncAttributePreferredSharedMemoryCarveout, 100);
                          attr_set = true;
                     }
-                    dense_direct_staged_kernel<K, THREADS, MINB, KS><<<grid, THREADS, sizeof(double2) * THREADS << K, stream>>>(p);
+                    dense_direct_staged_kernel<K, THREADS, MINB, KS, M3><<<grid, THREADS, sizeof(double2) * THREADS << K, stream>>>(p);
                     count_launch();
                     return check_launch("dense_direct_staged_kernel");
                }
           }
-          dense_direct_kernel<K, THREADS, MINB, KS><<<grid, THREADS, 0, stream>>>(p);
+          dense_direct_kernel<K, THREADS, MINB, KS, M3><<<grid, THREADS, 0, stream>>>(p);
           count_launch();
           return check_launch("dense_direct_kernel");
-     });
+     };
+     if constexpr (K == 4)
+          if (ks == K && dense_3m_enabled()) return go(std::integral_constant<int, K>{}, std::true_type{});
+     return with_ks<K>(ks, [&](auto ks_c) { return go(ks_c, std::false_type{}); });
 }
 
 template <int K>
@@ -540,6 +591,7 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
      p.d.n_free = 1ull << (L - K - n_t);
      p.d.ctrl_mask = 0;
      fill_common<K>(p.d.off, p.d.m, slots, matrix);
+     fill_msum<K>(p.d);
      // class-E tables: the selector bits every tuple element contributes to each op, grouped into the
      // distinct joint patterns (elements with the same bits for all class-E ops share one factor)
      std::memset(p.e_pat, 0, sizeof(p.e_pat));
@@ -570,18 +622,22 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
      const uint64_t n_chunks = (p.d.n_free + THREADS - 1) / THREADS;
      const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap));
-     return with_ks<K>(ks, [&](auto ks_c) {
+     auto go = [&](auto ks_c, auto m3_c) {
           constexpr int KS = decltype(ks_c)::value;
+          constexpr bool M3 = decltype(m3_c)::value;
           static bool attr_set = false;
           if (!attr_set) {
-               cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-               cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+               cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+               cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS, M3>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
                attr_set = true;
           }
-          dense_direct_pre_kernel<K, THREADS, MINB, KS><<<grid, THREADS, smem, stream>>>(p);
+          dense_direct_pre_kernel<K, THREADS, MINB, KS, M3><<<grid, THREADS, smem, stream>>>(p);
           count_launch();
           return check_launch("dense_direct_pre_kernel");
-     });
+     };
+     if constexpr (K == 4)
+          if (ks == K && dense_3m_enabled()) return go(std::integral_constant<int, K>{}, std::true_type{});
+     return with_ks<K>(ks, [&](auto ks_c) { return go(ks_c, std::false_type{}); });
 }
 
 template <int K>
