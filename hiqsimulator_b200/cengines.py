@@ -16,13 +16,14 @@ from . import ops
 
 
 class GreedyScheduler:
-    def __init__(self, supremacy_circuit=False, num_splits=10 ** 6, cluster_size=4, sched_module=None):
+    def __init__(self, supremacy_circuit=False, num_splits=10 ** 6, cluster_size=4, sched_module=None, use_planner=True):
         if sched_module is None:
             from . import _sched_cpp as sched_module
         self._sched = sched_module
         self._cmd_list = []
         self._was_scheduling = False
         self._supremacy_circuit = supremacy_circuit
+        self._use_planner = use_planner  # False: the Python loop of the reference drives ClusterScheduler / SwapScheduler directly
         self.NUM_SPLITS = num_splits
         self.CLUSTER_SIZE = cluster_size
         self._deallocations_cache = []
@@ -122,11 +123,47 @@ class GreedyScheduler:
             if len(gate) > 5:
                 raise Exception("Can't apply {}-qubits gate (no more that 5 qubits allowed)".format(len(gate)))
 
+    # -- the same loop driven by the C++ planner (`_sched_cpp.GreedyPlanner`, csrc/sched.cpp): one next() per step,
+    #    so every cluster reaches the device while the following one is being searched
+    def _force_scheduling_planned(self):
+        cmds = self._cmd_list
+        gate, gate_ctrl, _ = self._get_commands()
+        planner = self._sched.GreedyPlanner(gate, gate_ctrl, [bool(c.is_z) for c in cmds], self.backend.get_local_qubits_ids(),
+                                            self.backend.get_global_qubits_ids(), self.CLUSTER_SIZE, self.NUM_SPLITS,
+                                            not self._was_scheduling)
+        self._was_scheduling = True
+        while True:
+            kind, data = planner.next()
+            if kind == 0:
+                break
+            if kind == 1:
+                self.backend.set_qubits_perm(list(data))
+                self.log.append(("perm", list(data)))
+            elif kind == 2:
+                cmd = cmds[data[0]]
+                cmd.controls[data[1]], cmd.qubits[0] = cmd.qubits[0], cmd.controls[data[1]]
+            elif kind == 3:
+                self.n_clusters += 1
+                self.log.append(("cluster", [cmds[i].uid for i in data]))
+                for i in data:
+                    self.send([cmds[i]])
+                self.send([ops.Flush()])
+            elif kind == 4:
+                self.n_swaps += 1
+                self.log.append(("swap", list(data)))
+                self.send([ops.MetaSwap(list(data))])
+        self.cluster_seconds += planner.cluster_seconds()
+        self.swap_seconds += planner.swap_seconds()
+        self._cmd_list = []
+
     # -- reference: _greedyscheduler.py:203-242
     def _force_scheduling(self):
         if len(self._cmd_list) == 0:
             return
         self._check_commands()
+        if self._use_planner and not self._supremacy_circuit and hasattr(self._sched, "GreedyPlanner"):
+            self._force_scheduling_planned()
+            return
         if self._supremacy_circuit:
             self._remove_ending_cz()
         if not self._was_scheduling:

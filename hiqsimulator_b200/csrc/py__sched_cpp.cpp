@@ -20,6 +20,22 @@ PYBIND11_MODULE(_sched_cpp, m)
          .def("ScheduleCluster", &ClusterScheduler::ScheduleCluster, py::call_guard<py::gil_scoped_release>())
          .def("candidates", &ClusterScheduler::candidates)
          .def("evaluated", &ClusterScheduler::evaluated);
+     py::class_<GreedyPlanner>(m, "GreedyPlanner",
+                               "stage / cluster loop of the reference's GreedyScheduler as one object: next() -> (kind, ids) with kind "
+                               "0 done, 1 perm, 2 controlled-Z role swap (gate, control position), 3 cluster (gate indices), 4 swap pairs")
+         .def(py::init<std::vector<std::vector<Id>>, std::vector<std::vector<Id>>, std::vector<bool>, std::vector<Id>, std::vector<Id>, int,
+                       int, bool>())
+         .def("next",
+              [](GreedyPlanner& p) {
+                   GreedyPlanner::Step s;
+                   {
+                        py::gil_scoped_release release;
+                        s = p.next();
+                   }
+                   return py::make_tuple(s.kind, s.data);
+              })
+         .def("cluster_seconds", &GreedyPlanner::cluster_seconds)
+         .def("swap_seconds", &GreedyPlanner::swap_seconds);
      m.def("set_mode", &ClusterScheduler::set_mode, "0 = bounded search (default), 1 = replay the reference's enumeration and score every candidate");
      m.def("set_threads", &ClusterScheduler::set_threads, "host threads used to score candidate clusters (0 = auto)");
 }

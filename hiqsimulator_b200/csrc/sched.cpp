@@ -2,6 +2,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <stdexcept>
 #include <thread>
 #include <unordered_set>
@@ -564,6 +565,166 @@ std::vector<int> ClusterScheduler::huge_gate() const
           bad |= all_[i];
      }
      return {};
+}
+
+// ------------------------------------------------------------------------------------ GreedyPlanner
+namespace {
+double seconds_since(std::chrono::steady_clock::time_point t0)
+{
+     return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+bool contains(const std::vector<Id>& v, Id x) { return std::find(v.begin(), v.end(), x) != v.end(); }
+}  // namespace
+
+GreedyPlanner::GreedyPlanner(std::vector<std::vector<Id>> gate, std::vector<std::vector<Id>> gate_ctrl, std::vector<bool> is_z,
+                             std::vector<Id> locals, std::vector<Id> globals, int cluster_size, int num_splits, bool first_stage)
+    : gate_(std::move(gate)), ctrl_(std::move(gate_ctrl)), is_z_(std::move(is_z)), locals_(std::move(locals)),
+      globals_(std::move(globals)), cluster_size_(cluster_size), num_splits_(num_splits), state_(first_stage ? FIRST : STAGE_BEGIN)
+{
+     if (gate_.size() != ctrl_.size() || gate_.size() != is_z_.size()) throw std::runtime_error("GreedyPlanner: ctor(): size mismatch");
+     left_.resize(gate_.size());
+     for (size_t i = 0; i < left_.size(); ++i) left_[i] = static_cast<int>(i);
+     if (left_.empty()) state_ = FINISHED;
+}
+
+void GreedyPlanner::remaining(std::vector<std::vector<Id>>& gate, std::vector<std::vector<Id>>& ctrl) const
+{
+     gate.clear();
+     ctrl.clear();
+     gate.reserve(left_.size());
+     ctrl.reserve(left_.size());
+     for (int i: left_) {
+          gate.push_back(gate_[i]);
+          ctrl.push_back(ctrl_[i]);
+     }
+}
+
+// reference: _greedyscheduler.py:95-112 — a controlled-Z whose target is global hands the target role to its first local control
+void GreedyPlanner::prepare_ctrlz()
+{
+     for (int i: left_) {
+          if (!is_z_[i]) continue;
+          if (gate_[i].size() != 1) throw std::runtime_error("GreedyPlanner: a controlled-Z has exactly one target");
+          if (!contains(globals_, gate_[i][0])) continue;
+          for (size_t c = 0; c < ctrl_[i].size(); ++c)
+               if (contains(locals_, ctrl_[i][c])) {
+                    std::swap(ctrl_[i][c], gate_[i][0]);
+                    Step s;
+                    s.kind = ZSWAP;
+                    s.data = {static_cast<Id>(i), static_cast<Id>(c)};
+                    queue_.push_back(std::move(s));
+                    break;
+               }
+     }
+}
+
+// reference: _greedyscheduler.py:175-193
+bool GreedyPlanner::schedule_swap(std::vector<Id>& g_to_l, std::vector<Id>& l_to_g)
+{
+     const auto t0 = std::chrono::steady_clock::now();
+     std::vector<std::vector<Id>> gate, ctrl;
+     remaining(gate, ctrl);
+     const std::vector<bool> diag(gate.size(), false);
+     const int nl = static_cast<int>(locals_.size());
+     std::vector<Id> want = SwapScheduler(gate, ctrl, diag, num_splits_, nl, true).ScheduleSwap();
+     if (want.empty()) want = SwapScheduler(gate, ctrl, diag, num_splits_, nl, false).ScheduleSwap();
+     swap_s_ += seconds_since(t0);
+     g_to_l.clear();
+     l_to_g.clear();
+     for (Id q: want)  // ascending already; keep distinct ids that are not local
+          if (!contains(locals_, q) && !contains(g_to_l, q)) g_to_l.push_back(q);
+     std::sort(g_to_l.begin(), g_to_l.end());
+     if (!g_to_l.empty()) {
+          std::vector<Id> out;
+          for (Id q: locals_)
+               if (!contains(want, q) && !contains(out, q)) out.push_back(q);
+          std::sort(out.begin(), out.end());
+          if (out.size() < g_to_l.size()) throw std::runtime_error("GreedyPlanner: not enough local qubits to evict");
+          l_to_g.assign(out.begin(), out.begin() + g_to_l.size());
+     }
+     return !g_to_l.empty();
+}
+
+GreedyPlanner::Step GreedyPlanner::next()
+{
+     for (;;) {
+          if (queue_pos_ < queue_.size()) return std::move(queue_[queue_pos_++]);
+          queue_.clear();
+          queue_pos_ = 0;
+          switch (state_) {
+               case FINISHED: return Step{};
+               case FIRST: {
+                    // first scheduling of this engine: choose the local set by relabelling, no data motion
+                    // (reference: _greedyscheduler.py:211-222)
+                    std::vector<Id> g_to_l, l_to_g;
+                    schedule_swap(g_to_l, l_to_g);
+                    std::vector<Id> perm = locals_;
+                    perm.insert(perm.end(), globals_.begin(), globals_.end());
+                    for (size_t i = 0; i < l_to_g.size(); ++i) {
+                         auto a = std::find(perm.begin(), perm.end(), g_to_l[i]);
+                         auto b = std::find(perm.begin(), perm.end(), l_to_g[i]);
+                         if (a == perm.end() || b == perm.end()) throw std::runtime_error("GreedyPlanner: unknown qubit id in the swap choice");
+                         std::iter_swap(a, b);
+                    }
+                    locals_.assign(perm.begin(), perm.begin() + locals_.size());
+                    globals_.assign(perm.end() - globals_.size(), perm.end());
+                    Step s;
+                    s.kind = PERM;
+                    s.data = std::move(perm);
+                    queue_.push_back(std::move(s));
+                    state_ = STAGE_BEGIN;
+                    break;
+               }
+               case STAGE_BEGIN:
+                    prepare_ctrlz();
+                    state_ = CLUSTERS;
+                    break;
+               case CLUSTERS: {
+                    const auto t0 = std::chrono::steady_clock::now();
+                    std::vector<std::vector<Id>> gate, ctrl;
+                    remaining(gate, ctrl);
+                    const std::vector<int> avail =
+                        ClusterScheduler(gate, ctrl, std::vector<bool>(gate.size(), false), locals_, globals_, cluster_size_).ScheduleCluster();
+                    cluster_s_ += seconds_since(t0);
+                    if (!avail.empty()) {
+                         Step s;
+                         s.kind = CLUSTER;
+                         std::vector<char> gone(left_.size(), 0);
+                         for (int a: avail) {
+                              s.data.push_back(left_[a]);
+                              gone[a] = 1;
+                         }
+                         std::vector<int> keep;
+                         keep.reserve(left_.size() - avail.size());
+                         for (size_t i = 0; i < left_.size(); ++i)
+                              if (!gone[i]) keep.push_back(left_[i]);
+                         left_.swap(keep);
+                         queue_.push_back(std::move(s));
+                         break;
+                    }
+                    if (left_.empty()) {
+                         state_ = FINISHED;
+                         break;
+                    }
+                    // nothing more runs with these locals: next stage (reference: _greedyscheduler.py:224-241)
+                    std::vector<Id> g_to_l, l_to_g;
+                    if (!schedule_swap(g_to_l, l_to_g)) throw std::runtime_error("GreedyPlanner: the swap scheduler found nothing to bring in");
+                    Step s;
+                    s.kind = SWAP;
+                    for (size_t i = 0; i < g_to_l.size(); ++i) {
+                         s.data.push_back(g_to_l[i]);
+                         s.data.push_back(l_to_g[i]);
+                         auto g = std::find(globals_.begin(), globals_.end(), g_to_l[i]);
+                         auto l = std::find(locals_.begin(), locals_.end(), l_to_g[i]);
+                         if (g == globals_.end() || l == locals_.end()) throw std::runtime_error("GreedyPlanner: swap choice outside the maps");
+                         std::iter_swap(g, l);
+                    }
+                    queue_.push_back(std::move(s));
+                    state_ = STAGE_BEGIN;
+                    break;
+               }
+          }
+     }
 }
 
 }  // namespace sched

@@ -104,5 +104,43 @@ private:
      size_t n_evaluated_ = 0;
 };
 
+// The stage / cluster loop of the reference's GreedyScheduler (reference:
+// hiq/projectq/cengines/_greedyscheduler.py:95-242) as ONE host object that emits the plan step by step:
+// the initial relabelling, the controlled-Z role swaps, the gate clusters (= one fused-gate descriptor each once
+// the engine has fused them) and the swap plans.  next() does the work of one step only, so the caller can hand
+// every cluster to the device while the following one is being searched.
+class GreedyPlanner {
+public:
+     enum Kind { DONE = 0, PERM = 1, ZSWAP = 2, CLUSTER = 3, SWAP = 4 };
+     struct Step {
+          int kind = DONE;
+          // PERM: the whole permutation (locals then globals) for set_qubits_perm
+          // ZSWAP: {gate index, control position}: that control and the target of the controlled-Z trade roles
+          // CLUSTER: indices (into the constructor's gate list, program order) of the gates of the next cluster
+          // SWAP: [global id, local id, ...] pairs for swap_qubits
+          std::vector<Id> data;
+     };
+     GreedyPlanner(std::vector<std::vector<Id>> gate, std::vector<std::vector<Id>> gate_ctrl, std::vector<bool> is_z,
+                   std::vector<Id> locals, std::vector<Id> globals, int cluster_size, int num_splits, bool first_stage);
+     Step next();
+     double cluster_seconds() const { return cluster_s_; }
+     double swap_seconds() const { return swap_s_; }
+
+private:
+     void prepare_ctrlz();
+     bool schedule_swap(std::vector<Id>& g_to_l, std::vector<Id>& l_to_g);
+     void remaining(std::vector<std::vector<Id>>& gate, std::vector<std::vector<Id>>& ctrl) const;
+
+     std::vector<std::vector<Id>> gate_, ctrl_;
+     std::vector<bool> is_z_;
+     std::vector<int> left_;  // indices of the gates not yet emitted, program order
+     std::vector<Id> locals_, globals_;
+     int cluster_size_, num_splits_;
+     enum State { FIRST, STAGE_BEGIN, CLUSTERS, FINISHED } state_;
+     std::vector<Step> queue_;  // steps decided but not yet handed out (front first)
+     size_t queue_pos_ = 0;
+     double cluster_s_ = 0.0, swap_s_ = 0.0;
+};
+
 }  // namespace sched
 }  // namespace hiq

@@ -146,6 +146,48 @@ def test_swap_scheduler_layered_small_budgets(block):
             assert list(got) == list(exp), (seed, splits, fuse)
 
 
+@pytest.mark.parametrize("kind,n,R,ml,cluster", [("random", 14, 4, 12, 4), ("random", 17, 8, 14, 4), ("random", 12, 2, 11, 3),
+                                                 ("qft", 16, 4, 14, 4), ("qft", 13, 1, 13, 5), ("grover", 9, 2, 9, 4),
+                                                 ("random", 15, 1, 15, 4), ("random", 16, 8, 13, 2)])
+def test_planner_equals_python_loop(kind, n, R, ml, cluster):
+    """`_sched_cpp.GreedyPlanner` (one C++ object emitting perm / controlled-Z role swaps / clusters / swap plans) drives
+    the backend through exactly the command stream of the reference's Python loop (_greedyscheduler.py:203-242)."""
+    from hiqsimulator_b200 import circuits
+    if kind == "random":
+        nq, cmds = circuits.random_circuit(n, 8, seed=n + R)
+    elif kind == "qft":
+        nq, cmds = circuits.qft_circuit(n)
+    else:
+        nq, cmds = circuits.grover_circuit(n, 2)
+    runs = []
+    for use_planner in (True, False):
+        log, be = greedy_log_ex(nq, cmds, R, ml, cluster, use_planner)
+        runs.append((log, be.get_qubits_ids(), [(d["kind"], list(d["slots"]), int(d["ctrl_mask"]), list(d["aux"]),
+                                                 np.asarray(d["payload"]).tobytes()) for d in be._simulator.trace()]))
+    assert runs[0][0] == runs[1][0]          # perm / cluster / swap sequence
+    assert runs[0][1] == runs[1][1]          # final qubit maps
+    assert runs[0][2] == runs[1][2]          # every descriptor the engine emitted (fused matrices bit for bit)
+
+
+def greedy_log_ex(n, cmds, R, max_local, cluster, use_planner):
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    from hiqsimulator_b200 import backends, cengines
+    be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=max_local, max_fused_qubits=cluster,
+                               backend_class=lambda s, ml, mc: M.SimulatorMPI(s, ml, mc, R - 1, R, M.FLAG_DRY_RUN))
+    gs = cengines.GreedyScheduler(cluster_size=cluster, use_planner=use_planner)
+    eng = cengines.HiQMainEngine(be, [gs])
+    eng.allocate_qureg(n)
+    cmds = copy.deepcopy(cmds)
+    for i, c in enumerate(cmds):
+        c.uid = i
+    half = len(cmds) // 2
+    eng.receive(cmds[:half])
+    eng.flush()                 # a second scheduling round starts from the maps the first one left
+    eng.receive(cmds[half:])
+    eng.flush()
+    return [[k, [int(x) for x in v]] for k, v in gs.log], be
+
+
 def greedy_log(n, cmds, R, max_local, sched_module, cluster=4, supremacy=False):
     """Full GreedyScheduler run against a dry-run engine; returns the emitted schedule."""
     from hiqsimulator_b200 import _cppsim_mpi as M
