@@ -137,3 +137,13 @@ def run_shor(eng, N: int, a: int, n: int | None = None, verbose: bool = False):
     y = sum(measurements[2 * n - 1 - i] * 1.0 / (1 << (i + 1)) for i in range(2 * n))
     r = Fraction(y).limit_denominator(N - 1).denominator
     return r, measurements
+
+
+def inverse_circuit(cmds):
+    """The circuit that undoes `cmds`: reversed order, conjugate-transposed matrices (same targets / controls)."""
+    out = []
+    for c in reversed(cmds):
+        m = np.asarray(c.matrix)
+        out.append(Gate(m.conj().T.copy(), list(c.qubits), list(c.controls), name=getattr(c, "name", "") + "^-1",
+                        is_z=bool(getattr(c, "is_z", False))))
+    return out

@@ -114,3 +114,15 @@ def test_set_qubits_perm_is_relabel_only():
     e.set_qubits_perm(ids)
     assert e.get_local_qubits_ids() == [2, 1, 4, 5] and e.get_global_qubits_ids() == [0, 3]
     assert len(e.trace()) == n  # no data motion
+
+
+def test_fullsize_property_checks_hold_on_the_oracle():
+    """the size-independent checks of tests/test_fullsize_gpu.py, run here against the numpy oracle at 12 qubits:
+    the closed form (bit-reversed QFT output), the marginals and the circuit-then-inverse identity are properties
+    of the reference pipeline, not of the CUDA engine"""
+    import test_fullsize_gpu as F
+    from oracle import statevec
+    worst, marg, p_after = F.check_qft_closed_form(statevec.SimulatorMPI, 12, 256)
+    assert worst <= 1e-12 and marg <= 1e-12 and abs(p_after - 1.0) <= 1e-12
+    d_amp, d_p = F.check_circuit_then_inverse(statevec.SimulatorMPI, 10, 6)
+    assert d_amp <= 1e-12 and d_p <= 1e-12
