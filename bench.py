@@ -458,6 +458,7 @@ def main():
             "swap_wait_for_peers_ms_per_step": swap_wait_ms / args.steps,
             "swap_transport": {"peer_mapped_in_place": int(stats1["swaps_p2p"] - stats0["swaps_p2p"]),
                                "staged_nccl": int(stats1["swaps_staged"] - stats0["swaps_staged"]),
+                               "packed_peer_read": int(stats1.get("swaps_packed", 0) - stats0.get("swaps_packed", 0)),
                                "nvlink_peak_gbs_per_dir": 900.0,
                                "frac_of_nvlink": (swap_gbs / 900.0) if swap_gbs else None},
             "kernel_breakdown": breakdown,

@@ -310,6 +310,7 @@ int hiq_get_stats(hiq_engine* e, hiq_stats* out)
      out->swap_bytes_sent = s.swap_bytes_sent;
      out->swaps_p2p = s.swaps_p2p;
      out->swaps_staged = s.swaps_staged;
+     out->swaps_packed = s.swaps_packed;
      out->h2d_bytes = s.h2d_bytes;
      out->d2h_bytes = s.d2h_bytes;
      out->gate_launches = s.gate_launches;

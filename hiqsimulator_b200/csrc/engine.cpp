@@ -74,7 +74,10 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
           if (const char* m = std::getenv("HIQ_SWAP_MODE")) {
                if (!std::strcmp(m, "staged") || !std::strcmp(m, "nccl")) swap_mode_ = 1;
                else if (!std::strcmp(m, "p2p")) swap_mode_ = 2;
+               else if (!std::strcmp(m, "packed")) swap_mode_ = 3;
           }
+          if (const char* m = std::getenv("HIQ_SWAP_PACKED")) packed_enabled_ = m[0] == '1';
+          if (const char* m = std::getenv("HIQ_SWAP_PACKED_BELOW")) packed_below_slot_ = std::atoi(m);
           if (const char* m = std::getenv("HIQ_SWAP_P2P_MIN_SLOT")) min_p2p_slot_ = std::atoi(m);
           cu(check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           cu(check_cuda(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
@@ -98,6 +101,9 @@ Engine::~Engine()
           if (d_vals_) cudaFree(d_vals_);
           if (d_blocks_) cudaFree(d_blocks_);
           if (swap_buf_) cudaFree(swap_buf_);
+          for (double2* p: packed_peer_stage_)
+               if (p) cudaIpcCloseMemHandle(p);
+          if (packed_stage_) cudaFree(packed_stage_);
           slab_.release();
           for (auto& t: timed_) {
                cudaEventDestroy(t.start);
@@ -856,6 +862,9 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
      //                no extra HBM passes; its accesses are runs of 2^(lowest swapped slot) amplitudes
      //   staged       pack -> NCCL send/recv -> unpack pipeline; contiguous messages whatever the slots
      const int lowest = *std::min_element(slots.begin(), slots.end());
+     const bool want_packed = swap_mode_ == 3 || (swap_mode_ == 0 && packed_enabled_ && lowest < packed_below_slot_);
+     if (want_packed && !packed_failed_ && exchange_packed(gpos, slots)) return;
+     if (swap_mode_ == 3) fail(std::string("SwapQubits(): packed exchange unavailable: ") + hiq_last_error());
      const bool want_p2p = swap_mode_ == 2 || (swap_mode_ == 0 && lowest >= min_p2p_slot_);
      if (want_p2p && !p2p_broken_ && exchange_p2p(gpos, slots)) return;
      if (swap_mode_ == 2) fail(std::string("SwapQubits(): peer-mapped exchange unavailable: ") + hiq_last_error());
@@ -1030,6 +1039,114 @@ bool Engine::exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& 
      group_barrier(peer_ranks);  // ... and nobody moves on while a peer still writes into its slab
      stats_.swap_bytes_sent += static_cast<double>(peer_ranks.size()) * n * sizeof(double2);
      ++stats_.swaps_p2p;
+     return true;
+}
+
+bool Engine::ensure_packed_staging(size_t bytes)
+{
+     // Collective over the world (every rank takes part in every swap): allocate my staging buffer, publish its
+     // CUDA IPC handle with one all-gather, open the peers' buffers.  The outcome is agreed on by all ranks.
+     if (packed_stage_ && packed_stage_bytes_ >= bytes) return true;
+     double failed = 0.0;
+     std::string why;
+     cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
+     for (double2*& p: packed_peer_stage_)
+          if (p) {
+               cudaIpcCloseMemHandle(p);
+               p = nullptr;
+          }
+     if (packed_stage_) {
+          cudaFree(packed_stage_);
+          packed_stage_ = nullptr;
+          packed_stage_bytes_ = 0;
+     }
+     packed_peer_stage_.assign(world_, nullptr);
+     cudaIpcMemHandle_t mine;
+     std::memset(&mine, 0, sizeof(mine));
+     if (cudaMalloc(&packed_stage_, bytes) != cudaSuccess || cudaIpcGetMemHandle(&mine, packed_stage_) != cudaSuccess) {
+          failed = 1.0;
+          why = std::string("staging buffer: ") + cudaGetErrorString(cudaGetLastError());
+     }
+     static_assert(sizeof(cudaIpcMemHandle_t) % sizeof(double) == 0, "handle travels as doubles");
+     constexpr size_t HD = sizeof(cudaIpcMemHandle_t) / sizeof(double);
+     double* d_handles = nullptr;
+     std::vector<cudaIpcMemHandle_t> all(world_);
+     cu(check_cuda(cudaMalloc(&d_handles, world_ * sizeof(cudaIpcMemHandle_t)), "cudaMalloc handles"));
+     cu(check_cuda(cudaMemcpyAsync(d_handles + HD * rank_, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync"));
+     cu(comm_p_->allgather(d_handles + HD * rank_, d_handles, HD, stream_));
+     cu(check_cuda(cudaMemcpyAsync(all.data(), d_handles, world_ * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, stream_),
+                   "cudaMemcpyAsync"));
+     cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
+     cudaFree(d_handles);
+     cu(comm_p_->allreduce_sum(&failed, 1, stream_));  // somebody could not allocate: nobody opens anything
+     if (failed == 0.0) {
+          for (int r = 0; r < world_ && failed == 0.0; ++r) {
+               if (r == rank_) continue;
+               void* p = nullptr;
+               if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    failed = 1.0;
+                    why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(cudaGetLastError());
+               }
+               packed_peer_stage_[r] = static_cast<double2*>(p);
+          }
+          cu(comm_p_->allreduce_sum(&failed, 1, stream_));
+     }
+     if (failed != 0.0) {
+          packed_failed_ = true;
+          set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not set up the packed exchange" : why);
+          return false;
+     }
+     packed_stage_bytes_ = bytes;
+     return true;
+}
+
+bool Engine::exchange_packed(const std::vector<int>& gpos, const std::vector<int>& slots)
+{
+     // Same transposition as exchange_staged(), but the wire is a peer read: piece i is packed into my staging
+     // buffer (contiguous, HBM speed whatever the slots are), a stream-ordered barrier tells the group that every
+     // buffer is ready, and each rank unpacks straight from its PEERS' staging buffers — contiguous NVLink loads
+     // instead of the 16-64 B runs the in-place kernel makes when a swapped slot is low.  Two buffers: my pack of
+     // piece i+2 follows my barrier i+1, which completes only after every peer has queued past its unpack of piece i.
+     const int L = static_cast<int>(locals_.size());
+     const int q = static_cast<int>(gpos.size());
+     std::vector<int> order(q);
+     for (int i = 0; i < q; ++i) order[i] = i;
+     std::sort(order.begin(), order.end(), [&](int a, int b) { return slots[a] < slots[b]; });
+     const uint64_t chunk = 1ull << (L - q);
+     const int n_peers = (1 << q) - 1;
+     const uint64_t piece = std::min(chunk, kSwapPieceAmps);
+     const int max_peers = std::min(world_ - 1, 7);
+     if (!ensure_packed_staging(2ull * max_peers * kSwapPieceAmps * sizeof(double2))) return false;
+     std::vector<int> peer_ranks;
+     std::vector<uint64_t> pats;
+     for (int x = 1; x < (1 << q); ++x) {  // peer k of rank r is r ^ bits(x): the same k names me in the peer's list
+          int pr = rank_;
+          for (int i = 0; i < q; ++i)
+               if ((x >> i) & 1) pr ^= 1 << gpos[i];
+          uint64_t pat = 0;
+          for (int j = 0; j < q; ++j)
+               if ((pr >> gpos[order[j]]) & 1) pat |= 1ull << j;
+          peer_ranks.push_back(pr);
+          pats.push_back(pat);
+     }
+     const uint64_t n_pieces = chunk / piece;
+     for (uint64_t i = 0; i < n_pieces; ++i) {
+          const size_t buf = static_cast<size_t>(i % 2) * n_peers * piece;
+          for (int k = 0; k < n_peers; ++k)
+               cu(hiqk_swap_pack(slab_.data(), L, q, slots.data(), pats[k], i * piece, piece, packed_stage_ + buf + k * piece, stream_));
+          group_barrier(peer_ranks);
+          if (i == 0 && swap_mark_[0]) {
+               cudaEventRecord(swap_mark_[0], stream_);
+               cudaEventRecord(swap_mark_[1], stream_);
+               swap_marked_ = true;
+          }
+          for (int k = 0; k < n_peers; ++k)
+               cu(hiqk_swap_unpack(slab_.data(), L, q, slots.data(), pats[k], i * piece, piece,
+                                   packed_peer_stage_[peer_ranks[k]] + buf + k * piece, stream_));
+     }
+     group_barrier(peer_ranks);  // nobody repacks or frees while a peer still reads
+     stats_.swap_bytes_sent += static_cast<double>(n_peers) * chunk * sizeof(double2);
+     ++stats_.swaps_packed;
      return true;
 }
 

@@ -43,7 +43,7 @@ struct EngineStats {
      uint64_t dense_passes = 0, diag_passes = 0, scale_passes = 0, skipped_passes = 0;
      double runs_s = 0, swaps_s = 0, measures_s = 0, allocs_s = 0, deallocs_s = 0;
      double swap_bytes_sent = 0;
-     uint64_t swaps_p2p = 0, swaps_staged = 0;
+     uint64_t swaps_p2p = 0, swaps_staged = 0, swaps_packed = 0;
      double h2d_bytes = 0, d2h_bytes = 0;
      uint64_t gate_launches = 0;  // device launches that carried the dense/diag/scale passes above
 };
@@ -180,7 +180,17 @@ private:
      };
      std::vector<PeerView> peer_views_;
      uint64_t epoch_ = 0;
-     int swap_mode_ = 0;        // 0 auto, 1 staged NCCL only, 2 peer-mapped only
+     int swap_mode_ = 0;        // 0 auto, 1 staged NCCL only, 2 peer-mapped only, 3 packed peer-read only
+     // packed peer-read exchange (low swapped slots): pack into a staging buffer that the group peers have opened
+     // through CUDA IPC, barrier, unpack straight from the PEER's staging buffer (contiguous NVLink loads)
+     bool packed_enabled_ = false;      // HIQ_SWAP_PACKED=1 (opt-in until validated on a multi-GPU box)
+     int packed_below_slot_ = 3;        // auto mode: used when the lowest swapped slot is below this
+     bool packed_failed_ = false;
+     double2* packed_stage_ = nullptr;  // [2 buffers][peers][piece]
+     size_t packed_stage_bytes_ = 0;
+     std::vector<double2*> packed_peer_stage_;  // by world rank; opened IPC mappings of the peers' staging buffers
+     bool ensure_packed_staging(size_t bytes);
+     bool exchange_packed(const std::vector<int>& gpos, const std::vector<int>& slots);
      bool p2p_broken_ = false;  // the handshake failed once: stay on the staged path
      int min_p2p_slot_ = 0;     // lowest swapped slot for which the in-place kernel is used in auto mode
      int dense_variant_ = 0;

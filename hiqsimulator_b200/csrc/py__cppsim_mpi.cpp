@@ -298,6 +298,7 @@ public:
           d["swap_bytes_sent"] = s.swap_bytes_sent;
           d["swaps_p2p"] = s.swaps_p2p;
           d["swaps_staged"] = s.swaps_staged;
+          d["swaps_packed"] = s.swaps_packed;
           d["h2d_bytes"] = s.h2d_bytes;
           d["d2h_bytes"] = s.d2h_bytes;
           d["gate_launches"] = s.gate_launches;

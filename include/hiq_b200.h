@@ -328,6 +328,7 @@ typedef struct hiq_stats {
      uint64_t swaps_p2p, swaps_staged; /* exchanges done in place over peer-mapped slabs / through the staged NCCL pipeline */
      double h2d_bytes, d2h_bytes; /* host<->device traffic issued by the engine (descriptor payloads, results) */
      uint64_t gate_launches;      /* device launches that carried the dense/diag/scale passes (<= their sum) */
+     uint64_t swaps_packed;       /* exchanges done by packing + reading the peers' staging buffers (opt-in, HIQ_SWAP_PACKED=1) */
 } hiq_stats;
 int hiq_get_stats(hiq_engine* e, hiq_stats* out);
 

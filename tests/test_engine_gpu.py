@@ -128,6 +128,27 @@ def test_engine_matches_golden_multi_gpu(name):
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
+@pytest.mark.parametrize("mode", ["packed", "staged"])
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("r1_")][:4])
+def test_engine_matches_golden_multi_gpu_swap_transports(name, mode):
+    """the same golden runs with the exchange forced onto the packed peer-read transport (opt-in, low swapped slots)
+    and onto the staged NCCL pipeline: every transport performs the same transposition"""
+    R = int(name[1])
+    if os.environ.get("HIQ_TEST_SWAP_TRANSPORTS") != "1":
+        pytest.skip("forced swap transports run on request (HIQ_TEST_SWAP_TRANSPORTS=1): the packed one is opt-in")
+    if _gpu_count() < R:
+        pytest.skip("needs %d GPUs" % R)
+    import socket
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, HIQ_SWAP_MODE=mode))
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+
+
 # ---------------------------------------------------------------------------------------------
 # Known answers of the reference's own test-suite, restated without ProjectQ
 # (reference: hiq/projectq/backends/_sim/_simulator_mpi_test.py)

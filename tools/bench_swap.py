@@ -53,7 +53,7 @@ def main():
             worst = max(all_ms)
             print(json.dumps({"mode": mode, "n_gpus": size, "L": L, "q": q, "slots": name, "ms": worst,
                               "nvlink_gbs_per_gpu_per_dir": nbytes / worst / 1e6, "frac_of_900": nbytes / worst / 1e6 / 900.0,
-                              "swaps_p2p": st["swaps_p2p"], "swaps_staged": st["swaps_staged"]}), flush=True)
+                              "swaps_p2p": st["swaps_p2p"], "swaps_staged": st["swaps_staged"], "swaps_packed": st.get("swaps_packed", 0)}), flush=True)
     p = sim.get_probability([False], [0])
     if rank == 0:
         print(json.dumps({"check_prob_q0_is_half": p}), flush=True)
