@@ -245,6 +245,91 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const _
      }
 }
 
+// DIRECT with diagonals folded in, block form (KS < K), register-pipelined — EXPERIMENTAL, opt-in (HIQ_DENSE_BLOCKLOOP=1).
+// The reduced product never mixes the 2^(K-KS) blocks of a tuple, so a thread only needs one block (2^KS elements)
+// live at a time: the next block is loaded into registers while the current one is multiplied and stored, nothing is
+// staged through shared memory (the staged kernel spends a quarter of its stalls on the shared-memory queue,
+// profiles/r01n_ncu_full_blocks_L30.md) and the register budget allows more resident warps.  Same diagonal program,
+// chunking and factor tables as dense_direct_pre_kernel; results are identical.
+template <int K, int KS, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_blocks_kernel(const __grid_constant__ DirectPreParams<K> p)
+{
+     static_assert(KS < K, "block form only");
+     constexpr int D = 1 << K;
+     constexpr int DS = 1 << KS;
+     constexpr int NB = 1 << (K - KS);
+     extern __shared__ double2 dyn_smem[];
+     double2 (*sT)[THREADS] = reinterpret_cast<double2 (*)[THREADS]>(dyn_smem);  // this thread's class-E factors
+     __shared__ DiagShared sh;
+     uint32_t selt[kMaxDiagOps / 4];
+     diag_prog_init<THREADS>(p.prog, sh, insert_zero_bits(threadIdx.x, p.d.ins), selt);
+     const uint64_t n_chunks = (p.d.n_free + THREADS - 1) / THREADS;
+     const int nt = 1 << p.n_t;
+     const int je = p.prog.n_s0 + p.prog.n_s1;
+     const bool valid = threadIdx.x < p.d.n_free;
+     auto build_patterns = [&](double2 s, int t) {
+          for (int e = 0; e < p.e_npat; ++e) {
+               double2 f = s;
+               for (int j = je; j < p.prog.n; ++j)
+                    f = cmul(f, sh.lut[j][sh.selh[j] | diag_selt(selt, j) | p.prog.usel[j][t] | p.e_pat[j][e]]);
+               sT[e][threadIdx.x] = f;
+          }
+     };
+     auto chunk_index = [&](uint64_t chunk) { return insert_zero_bits(chunk * THREADS + threadIdx.x, p.d.ins); };
+     auto load_block = [&](double2 (&dst)[DS], const double2* base, int blk) {
+#pragma unroll
+          for (int j = 0; j < DS; ++j) dst[j] = ldg_stream(base + p.d.off[blk * DS + j]);
+     };
+     uint64_t chunk = blockIdx.x;
+     uint64_t bidx = chunk < n_chunks ? chunk_index(chunk) : 0;
+     double2 cur[DS], nxt[DS];
+     if (chunk < n_chunks && valid) load_block(cur, p.d.psi + bidx, 0);
+     for (; chunk < n_chunks; chunk += gridDim.x) {
+          diag_prog_chunk(p.prog, sh, insert_zero_bits(chunk * THREADS, p.d.ins));
+          if (!valid) continue;
+          const double2 s0 = diag_prog_s0(p.prog, sh, selt);
+          if (p.fast && p.prog.n_e) build_patterns(s0, 0);
+          const bool more_chunks = chunk + gridDim.x < n_chunks;
+          const uint64_t bidx_next = more_chunks ? chunk_index(chunk + gridDim.x) : 0;
+#pragma unroll 1
+          for (int t = 0; t < nt; ++t) {
+               double2* base = p.d.psi + (bidx | p.toff[t]);
+               double2 s = s0;
+               if (!p.fast) {
+                    s = diag_prog_s1(p.prog, sh, selt, t, s0);
+                    if (p.prog.n_e) build_patterns(s, t);
+               }
+#pragma unroll
+               for (int blk = 0; blk < NB; ++blk) {
+                    // the block after this one (next block of the tuple, else block 0 of the thread's next tuple)
+                    if (blk + 1 < NB) load_block(nxt, base, blk + 1);
+                    else if (t + 1 < nt) load_block(nxt, p.d.psi + (bidx | p.toff[t + 1]), 0);
+                    else if (more_chunks) load_block(nxt, p.d.psi + bidx_next, 0);
+                    double2 in[DS];
+                    if (p.prog.n_e == 0) {
+#pragma unroll
+                         for (int j = 0; j < DS; ++j) in[j] = cmul(cur[j], s);
+                    }
+                    else {
+#pragma unroll
+                         for (int j = 0; j < DS; ++j) in[j] = cmul(cur[j], sT[p.e_cmap[blk * DS + j]][threadIdx.x]);
+                    }
+#pragma unroll
+                    for (int r = 0; r < DS; ++r) {
+                         const int b = blk * DS + r;
+                         double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+                         for (int j = 0; j < DS; ++j) cmac(acc, p.d.m[b * D + blk * DS + j], in[j]);
+                         base[p.d.off[b]] = acc;
+                    }
+#pragma unroll
+                    for (int j = 0; j < DS; ++j) cur[j] = nxt[j];
+               }
+          }
+          bidx = bidx_next;
+     }
+}
+
 // ---------------------------------------------------------------------------------------------
 // TILED
 // ---------------------------------------------------------------------------------------------
@@ -420,6 +505,17 @@ static void fill_msum(DirectParams<K>& p)
      if constexpr (K == 4)
           for (int i = 0; i < (1 << (2 * K)); ++i) p.msum[i] = p.m[i].x + p.m[i].y;
      else p.msum[0] = 0.0;
+}
+
+// HIQ_DENSE_BLOCKLOOP=1 routes folded-diagonal launches of block-structured gates to the register-pipelined
+// block kernel (experimental: to be measured against the staged form before it becomes the default)
+static bool dense_blockloop_enabled()
+{
+     static const bool on = [] {
+          const char* e = std::getenv("HIQ_DENSE_BLOCKLOOP");
+          return e && e[0] == '1';
+     }();
+     return on;
 }
 
 // HIQ_DENSE_3M=0 in the environment keeps the full k = 4 product on four multiplications (A/B measurements)
@@ -625,6 +721,18 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
      auto go = [&](auto ks_c, auto m3_c) {
           constexpr int KS = decltype(ks_c)::value;
           constexpr bool M3 = decltype(m3_c)::value;
+          if constexpr (KS < K) {
+               if (dense_blockloop_enabled()) {
+                    // experimental register-pipelined block form (opt-in): no tuple staging, more resident warps
+                    constexpr int MINB2 = (K >= 3) ? (KS >= 3 ? 4 : 6) : 4;
+                    const size_t smem2 = sizeof(double2) * THREADS * std::max(p.e_npat, 1);
+                    const uint64_t cap2 = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB2 * 8);
+                    const unsigned grid2 = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap2));
+                    dense_direct_pre_blocks_kernel<K, KS, THREADS, MINB2><<<grid2, THREADS, smem2, stream>>>(p);
+                    count_launch();
+                    return check_launch("dense_direct_pre_blocks_kernel");
+               }
+          }
           static bool attr_set = false;
           if (!attr_set) {
                cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);

@@ -633,3 +633,20 @@ def test_permute_gather_rejects_bad_arguments():
         K.permute_gather(d, [s], 0, K.PERM_ADD, [0, 1], 2, 1, 0)
     with pytest.raises(HiqError, match="missing the slab"):
         K.permute_gather(d, [s, None], 0, K.PERM_ADD, [0, 8], 0, 1, 0)
+
+
+def test_experimental_blockloop_kernel_parity():
+    """HIQ_DENSE_BLOCKLOOP=1 (register-pipelined block form of the folded-diagonal launch, csrc/apply_dense.cu): the
+    prediag parity cases again, in a child process that has the switch set.  Runs on request only
+    (HIQ_TEST_EXPERIMENTAL=1) until the kernel has been measured and made the default."""
+    import os
+    import subprocess
+    import sys
+    if os.environ.get("HIQ_TEST_EXPERIMENTAL") != "1":
+        pytest.skip("experimental kernel: set HIQ_TEST_EXPERIMENTAL=1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    env = dict(os.environ, HIQ_DENSE_BLOCKLOOP="1")
+    env.pop("HIQ_TEST_EXPERIMENTAL")
+    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_kernels_gpu.py"), "-m", "gpu", "-q", "-p", "no:cacheprovider",
+                          "-k", "prediag"], capture_output=True, text=True, timeout=600, env=env, cwd=os.path.dirname(here))
+    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
