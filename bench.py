@@ -450,7 +450,11 @@ def main():
                                    "diagonal fused gates folded into the next dense launch / batched per pass",
                        "swaps": shape["swaps"],
                        "swap_qubits": shape["swap_qubits"], "l2_policy": "inputs larger than L2 (slab >> 126 MB), no flush",
-                       "timing": "CUDA events on the engine stream, max over ranks"},
+                       "timing": "CUDA events on the engine stream, max over ranks",
+                       "series": "BASELINE.json configs: N=1 is QFT-33 (33q@1; its diagonal fused gates are folded into "
+                                 "neighbouring launches, so effective GB/s exceeds the physical rate), N>=2 are random-34/35/35 "
+                                 "(one HBM pass per fused gate); the like-for-like single-GPU figure of the random series is "
+                                 "`bench.py --circuit random --qubits 33` (or 30: profiles/r01o_bench_n1_random30.json)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "circuit_seconds": {"device_only": ms_per_step * 1e-3, "host_schedule_s": shape["host_schedule_s"],
                                 "end_to_end": e2e["seconds_per_step"] if e2e else None},
