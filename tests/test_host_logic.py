@@ -126,3 +126,67 @@ def test_fullsize_property_checks_hold_on_the_oracle():
     assert worst <= 1e-12 and marg <= 1e-12 and abs(p_after - 1.0) <= 1e-12
     d_amp, d_p = F.check_circuit_then_inverse(statevec.SimulatorMPI, 10, 6)
     assert d_amp <= 1e-12 and d_p <= 1e-12
+
+
+@pytest.mark.parametrize("L,gpos,slots,piece_bits", [(8, [0], [0], 5), (8, [0], [5], 7), (9, [1, 0], [0, 1], 4), (9, [0, 2], [6, 1], 5),
+                                                      (10, [0, 1, 2], [0, 1, 2], 4), (10, [2, 0, 1], [7, 0, 3], 6)])
+def test_packed_exchange_scheme(L, gpos, slots, piece_bits):
+    """Index logic of Engine::exchange_packed (csrc/engine.cpp), restated with numpy: every rank packs piece i for peer k
+    into staging[(i % 2) * n_peers + k], and unpacks peer k's data from the PEER's staging at the same (i % 2, k) —
+    peer k of rank r is r ^ bits(x_k), so k also names r in that peer's list.  The result must be the transposition of
+    global-index bit (L + gpos_j) with bit slots[j], whatever the piece size."""
+    g = 3
+    R = 1 << g
+    q = len(gpos)
+    rng = np.random.default_rng(L + sum(slots))
+    full = rng.normal(size=R << L) + 1j * rng.normal(size=R << L)
+    vec = [full[r << L:(r + 1) << L].copy() for r in range(R)]
+    order = sorted(range(q), key=lambda j: slots[j])
+    srt = sorted(slots)
+    idx = np.arange(1 << L)
+    free = np.zeros(1 << L, dtype=np.int64)  # free index of every local index (swapped slots removed)
+    pos = 0
+    for b in range(L):
+        if b in slots:
+            continue
+        free |= ((idx >> b) & 1) << pos
+        pos += 1
+
+    def select(pat, begin, count):
+        sel = (free >= begin) & (free < begin + count)
+        for j, s in enumerate(srt):
+            sel &= ((idx >> s) & 1) == ((pat >> j) & 1)
+        return sel
+
+    def peers_of(r):
+        out = []
+        for x in range(1, 1 << q):
+            pr = r
+            for i in range(q):
+                if (x >> i) & 1:
+                    pr ^= 1 << gpos[i]
+            pat = sum(((pr >> gpos[order[j]]) & 1) << j for j in range(q))
+            out.append((pr, pat))
+        return out
+
+    chunk = 1 << (L - q)
+    piece = min(chunk, 1 << piece_bits)
+    n_peers = (1 << q) - 1
+    staging = [np.zeros(2 * n_peers * piece, dtype=np.complex128) for _ in range(R)]
+    for i in range(chunk // piece):
+        buf = (i % 2) * n_peers * piece
+        for r in range(R):  # pack, then the group barrier
+            for k, (pr, pat) in enumerate(peers_of(r)):
+                staging[r][buf + k * piece: buf + (k + 1) * piece] = vec[r][select(pat, i * piece, piece)]
+        for r in range(R):  # unpack from the peers' staging buffers
+            for k, (pr, pat) in enumerate(peers_of(r)):
+                assert peers_of(pr)[k][0] == r
+                vec[r][select(pat, i * piece, piece)] = staging[pr][buf + k * piece: buf + (k + 1) * piece]
+    got = np.concatenate(vec)
+    gidx = np.arange(R << L, dtype=np.int64)
+    src = gidx.copy()
+    for j in range(q):
+        hi, lo = L + gpos[j], slots[j]
+        bh, bl = (src >> hi) & 1, (src >> lo) & 1
+        src = src & ~((1 << hi) | (1 << lo)) | (bl << hi) | (bh << lo)
+    assert np.array_equal(got, full[src])
