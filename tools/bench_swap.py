@@ -32,6 +32,10 @@ def main():
     for q in range(1, g + 1):
         cases += [(q, "top", list(range(L - q, L))), (q, "mid", list(range(12, 12 + q))), (q, "slot3+", list(range(3, 3 + q))),
                   (q, "bottom", list(range(0, q)))]
+        # one low slot, the others in the middle: where the in-place exchange starts to lose (crossover for the packed one)
+        cases += [(q, "slot%d+mid" % low, [low] + list(range(12, 12 + q - 1))) for low in (1, 2)]
+        if q > 1:
+            cases.append((q, "slot0+mid", [0] + list(range(12, 12 + q - 1))))
     for q, name, slots in cases:
         times = []
         for rep in range(args.reps + 1):
