@@ -66,6 +66,7 @@ _SIGNATURES = {
     "hiqk_swap_unpack": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _u64, _u64, _u64, _vp, _vp]),
     "hiqk_swap_p2p": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _ip, C.POINTER(_u64), _u64, C.POINTER(_u64),
                                C.POINTER(_u64), _vp]),
+    "hiqk_swap_move": (C.c_int, [_vp, C.c_int, C.c_int, _ip, C.c_int, C.POINTER(_u64), _u64, _u64, C.POINTER(_vp), C.c_int, _vp]),
     "hiqk_pauli_expect": (C.c_int, [_vp, C.c_int, _u64, C.POINTER(PauliTerm), C.c_int, _vp, _u64, _u64, _vp, _vp, _vp]),
     "hiqk_pauli_apply": (C.c_int, [_vp, C.c_int, _u64, C.POINTER(PauliTerm), C.c_int, _vp, C.c_int, _vp, _u64, _u64, _vp]),
     "hiqk_permute_gather": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, C.POINTER(Perm), _vp]),

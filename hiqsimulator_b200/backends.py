@@ -11,7 +11,6 @@ import random
 
 import numpy as np
 
-from . import _cppsim_mpi as _M
 from . import ops
 
 
@@ -19,7 +18,12 @@ class SimulatorMPI:
     def __init__(self, gate_fusion=False, rnd_seed=None, num_local_qubits=33, max_fused_qubits=4, backend_class=None):
         if rnd_seed is None:
             rnd_seed = random.randint(0, 4294967295)
-        cls = backend_class or _M.SimulatorMPI
+        if backend_class is None:
+            # the B200 engine; imported here so that a caller who brings its own engine class (the compiled reference in
+            # bench.py's reference arm, the numpy oracle in the tests) never loads this repository's native modules
+            from . import _cppsim_mpi as _M
+            backend_class = _M.SimulatorMPI
+        cls = backend_class
         self._simulator = cls(rnd_seed, num_local_qubits, max_fused_qubits)
         self._gate_fusion = gate_fusion
         self.main_engine = None

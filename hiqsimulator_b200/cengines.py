@@ -16,7 +16,8 @@ from . import ops
 
 
 class GreedyScheduler:
-    def __init__(self, supremacy_circuit=False, num_splits=10 ** 6, cluster_size=4, sched_module=None, use_planner=True):
+    def __init__(self, supremacy_circuit=False, num_splits=10 ** 6, cluster_size=4, sched_module=None, use_planner=True,
+                 prefetch=True):
         if sched_module is None:
             from . import _sched_cpp as sched_module
         self._sched = sched_module
@@ -24,6 +25,7 @@ class GreedyScheduler:
         self._was_scheduling = False
         self._supremacy_circuit = supremacy_circuit
         self._use_planner = use_planner  # False: the Python loop of the reference drives ClusterScheduler / SwapScheduler directly
+        self._prefetch = prefetch        # planner steps are computed ahead of the device on a host thread
         self.NUM_SPLITS = num_splits
         self.CLUSTER_SIZE = cluster_size
         self._deallocations_cache = []
@@ -132,8 +134,33 @@ class GreedyScheduler:
                                             self.backend.get_global_qubits_ids(), self.CLUSTER_SIZE, self.NUM_SPLITS,
                                             not self._was_scheduling)
         self._was_scheduling = True
+        if self._prefetch:
+            # the planner runs ahead on a host thread (next() releases the GIL): while the device works through the
+            # clusters of a stage, the search for the next stage's local set is already under way, so neither the
+            # swap search nor the cluster search sits between two launches.  Steps are consumed in emission order.
+            import queue
+            import threading
+            steps = queue.Queue(maxsize=256)
+
+            def produce():
+                try:
+                    while True:
+                        step = planner.next()
+                        steps.put(step)
+                        if step[0] == 0:
+                            return
+                except BaseException as e:  # surfaces in the consumer
+                    steps.put((-1, e))
+            worker = threading.Thread(target=produce, name="hiq-planner", daemon=True)
+            worker.start()
+            next_step = steps.get
+        else:
+            worker = None
+            next_step = planner.next
         while True:
-            kind, data = planner.next()
+            kind, data = next_step()
+            if kind == -1:
+                raise data
             if kind == 0:
                 break
             if kind == 1:
@@ -152,6 +179,8 @@ class GreedyScheduler:
                 self.n_swaps += 1
                 self.log.append(("swap", list(data)))
                 self.send([ops.MetaSwap(list(data))])
+        if worker is not None:
+            worker.join()
         self.cluster_seconds += planner.cluster_seconds()
         self.swap_seconds += planner.swap_seconds()
         self._cmd_list = []

@@ -314,6 +314,11 @@ int hiq_get_stats(hiq_engine* e, hiq_stats* out)
      out->h2d_bytes = s.h2d_bytes;
      out->d2h_bytes = s.d2h_bytes;
      out->gate_launches = s.gate_launches;
+     out->ctor_s = s.ctor_s;
+     out->slab_grow_s = s.slab_grow_s;
+     out->peer_map_s = s.peer_map_s;
+     out->tile_launches = s.tile_launches;
+     out->tile_steps = s.tile_steps;
      return HIQ_OK;
 }
 

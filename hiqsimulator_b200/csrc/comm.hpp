@@ -40,6 +40,18 @@ public:
      // peer-mapping handshake tags its messages with (all ranks create their engines in the same order)
      uint64_t next_epoch() { return ++epoch_; }
 
+     // Staging of the packed exchange (engine.cpp, Engine::exchange_packed): one buffer per process, opened by the peers
+     // through CUDA IPC.  Process-wide like the communicator: an engine per circuit must not pay cudaMalloc + handle
+     // exchange + cudaIpcOpenMemHandle again.
+     struct PackedStaging {
+          double2* mine = nullptr;
+          size_t bytes = 0;
+          size_t wanted = 0;            // the request that produced this buffer (it may have been halved to fit)
+          std::vector<double2*> peers;  // by world rank
+          bool failed = false;
+     };
+     PackedStaging& packed() { return packed_; }
+
      // host-value collectives (values staged through a small device buffer on `stream`)
      int allreduce_sum(double* vals, int n, cudaStream_t stream);
      int broadcast_bytes(void* host, size_t bytes, int root, cudaStream_t stream);
@@ -53,6 +65,7 @@ private:
      double* stage_ = nullptr;  // 4 KiB device staging
      FdChannel fds_;
      uint64_t epoch_ = 0;
+     PackedStaging packed_;
 };
 
 }  // namespace hiq

@@ -58,6 +58,7 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
       timing_((flags & HIQ_FLAG_TIMING) && !(flags & HIQ_FLAG_DRY_RUN)),
       batching_(!(flags & HIQ_FLAG_NO_BATCH))
 {
+     const auto t_ctor = Clock::now();
      if (world_size < 1 || (world_size & (world_size - 1)) || rank < 0 || rank >= world_size)
           fail("ctor(): world size must be a power of two and 0 <= rank < world size");
      if (max_local < 1 || max_local > 40 || max_cluster < 1) fail("ctor(): bad max_local / max_cluster_size");
@@ -78,6 +79,8 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
           }
           if (const char* m = std::getenv("HIQ_SWAP_PACKED")) packed_enabled_ = m[0] == '1';
           if (const char* m = std::getenv("HIQ_SWAP_PACKED_BELOW")) packed_below_slot_ = std::atoi(m);
+          if (const char* m = std::getenv("HIQ_SWAP_PACKED_PULL")) packed_push_ = m[0] != '1';
+          if (const char* m = std::getenv("HIQ_SWAP_PACKED_PIECE")) packed_piece_cap_ = std::strtoull(m, nullptr, 10);
           if (const char* m = std::getenv("HIQ_SWAP_P2P_MIN_SLOT")) min_p2p_slot_ = std::atoi(m);
           cu(check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           cu(check_cuda(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
@@ -90,6 +93,7 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
           cu(hiqk_fill(slab_.data(), 0, 1, rank_ == 0 ? 1.0 : 0.0, 0.0, stream_));
      }
      ++stats_.total_stages;
+     stats_.ctor_s = seconds_since(t_ctor);
 }
 
 Engine::~Engine()
@@ -101,9 +105,6 @@ Engine::~Engine()
           if (d_vals_) cudaFree(d_vals_);
           if (d_blocks_) cudaFree(d_blocks_);
           if (swap_buf_) cudaFree(swap_buf_);
-          for (double2* p: packed_peer_stage_)
-               if (p) cudaIpcCloseMemHandle(p);
-          if (packed_stage_) cudaFree(packed_stage_);
           slab_.release();
           for (auto& t: timed_) {
                cudaEventDestroy(t.start);
@@ -151,6 +152,9 @@ uint64_t Engine::ids_to_bits(const std::vector<Index>& ids, const std::vector<In
 void Engine::allocate_local(Index id)
 {
      const uint64_t old = 1ull << locals_.size();
+     // queued launches (held dense gate, batched diagonals) were planned for the slab as it is NOW: they go out
+     // before the register grows — afterwards locals_.size() would describe a slab whose upper half is not mapped yet
+     flush_pending();
      locals_.push_back(id);
      if (tracing_) {
           Descriptor d;
@@ -159,8 +163,9 @@ void Engine::allocate_local(Index id)
           trace_.push_back(d);
      }
      if (dry_run_) return;
-     flush_pending();
+     const auto t_grow = Clock::now();
      cu(slab_.ensure(2 * old));
+     stats_.slab_grow_s += seconds_since(t_grow);
      cu(check_cuda(cudaMemsetAsync(slab_.data() + old, 0, old * sizeof(double2), stream_), "cudaMemsetAsync"));
 }
 
@@ -863,7 +868,7 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
      //   staged       pack -> NCCL send/recv -> unpack pipeline; contiguous messages whatever the slots
      const int lowest = *std::min_element(slots.begin(), slots.end());
      const bool want_packed = swap_mode_ == 3 || (swap_mode_ == 0 && packed_enabled_ && lowest < packed_below_slot_);
-     if (want_packed && !packed_failed_ && exchange_packed(gpos, slots)) return;
+     if (want_packed && !comm_p_->packed().failed && exchange_packed(gpos, slots)) return;
      if (swap_mode_ == 3) fail(std::string("SwapQubits(): packed exchange unavailable: ") + hiq_last_error());
      const bool want_p2p = swap_mode_ == 2 || (swap_mode_ == 0 && lowest >= min_p2p_slot_);
      if (want_p2p && !p2p_broken_ && exchange_p2p(gpos, slots)) return;
@@ -981,7 +986,9 @@ bool Engine::ensure_peer_views(const std::vector<int>& peer_ranks)
      for (int pr: peer_ranks)
           if (!stale && (peer_views_[pr].sent < slab_.n_chunks() || peer_views_[pr].slab.n_chunks() < slab_.n_chunks())) stale = true;
      if (stale) {
+          const auto t_map = Clock::now();
           double failed = map_peers(peer_ranks) ? 0.0 : 1.0;
+          stats_.peer_map_s += seconds_since(t_map);
           const std::string why = failed != 0.0 ? hiq_last_error() : "";
           cu(comm_p_->allreduce_sum(&failed, 1, stream_));
           if (failed != 0.0) {
@@ -1042,30 +1049,59 @@ bool Engine::exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& 
      return true;
 }
 
-bool Engine::ensure_packed_staging(size_t bytes)
+bool Engine::ensure_packed_staging(size_t want_bytes, size_t min_bytes)
 {
-     // Collective over the world (every rank takes part in every swap): allocate my staging buffer, publish its
-     // CUDA IPC handle with one all-gather, open the peers' buffers.  The outcome is agreed on by all ranks.
-     if (packed_stage_ && packed_stage_bytes_ >= bytes) return true;
-     double failed = 0.0;
-     std::string why;
+     // Collective over the world (every rank takes part in every swap, with the same arguments): allocate my staging
+     // buffer, publish its CUDA IPC handle with one all-gather, open the peers' buffers.  The outcome — including the
+     // size, halved until every rank could allocate it — is agreed on by all ranks.  The buffers belong to the process
+     // (Comm::packed()), so the engines a caller creates one after the other share them.
+     Comm::PackedStaging& S = comm_p_->packed();
+     if (S.failed) {
+          set_error(HIQ_ERR_RUNTIME, "the packed exchange could not be set up in this process group");
+          return false;
+     }
+     if (S.mine && want_bytes <= S.wanted && S.bytes >= min_bytes) return true;
      cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
-     for (double2*& p: packed_peer_stage_)
+     cu(check_cuda(cudaStreamSynchronize(comm_stream_), "cudaStreamSynchronize"));
+     for (double2*& p: S.peers)
           if (p) {
                cudaIpcCloseMemHandle(p);
                p = nullptr;
           }
-     if (packed_stage_) {
-          cudaFree(packed_stage_);
-          packed_stage_ = nullptr;
-          packed_stage_bytes_ = 0;
+     if (S.mine) {
+          cudaFree(S.mine);
+          S.mine = nullptr;
+          S.bytes = 0;
      }
-     packed_peer_stage_.assign(world_, nullptr);
+     S.peers.assign(world_, nullptr);
+     std::string why;
+     size_t bytes = want_bytes;
+     for (;;) {
+          double failed = 0.0;
+          if (cudaMalloc(&S.mine, bytes) != cudaSuccess) {
+               cudaGetLastError();
+               S.mine = nullptr;
+               failed = 1.0;
+          }
+          cu(comm_p_->allreduce_sum(&failed, 1, stream_));
+          if (failed == 0.0) break;
+          if (S.mine) {
+               cudaFree(S.mine);
+               S.mine = nullptr;
+          }
+          bytes /= 2;
+          if (bytes < min_bytes) {
+               S.failed = true;
+               set_error(HIQ_ERR_RUNTIME, "no device memory for the staging buffer of the packed exchange");
+               return false;
+          }
+     }
+     double failed = 0.0;
      cudaIpcMemHandle_t mine;
      std::memset(&mine, 0, sizeof(mine));
-     if (cudaMalloc(&packed_stage_, bytes) != cudaSuccess || cudaIpcGetMemHandle(&mine, packed_stage_) != cudaSuccess) {
+     if (cudaIpcGetMemHandle(&mine, S.mine) != cudaSuccess) {
           failed = 1.0;
-          why = std::string("staging buffer: ") + cudaGetErrorString(cudaGetLastError());
+          why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError());
      }
      static_assert(sizeof(cudaIpcMemHandle_t) % sizeof(double) == 0, "handle travels as doubles");
      constexpr size_t HD = sizeof(cudaIpcMemHandle_t) / sizeof(double);
@@ -1078,7 +1114,7 @@ bool Engine::ensure_packed_staging(size_t bytes)
                    "cudaMemcpyAsync"));
      cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
      cudaFree(d_handles);
-     cu(comm_p_->allreduce_sum(&failed, 1, stream_));  // somebody could not allocate: nobody opens anything
+     cu(comm_p_->allreduce_sum(&failed, 1, stream_));  // somebody has no handle: nobody opens anything
      if (failed == 0.0) {
           for (int r = 0; r < world_ && failed == 0.0; ++r) {
                if (r == rank_) continue;
@@ -1087,36 +1123,50 @@ bool Engine::ensure_packed_staging(size_t bytes)
                     failed = 1.0;
                     why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(cudaGetLastError());
                }
-               packed_peer_stage_[r] = static_cast<double2*>(p);
+               S.peers[r] = static_cast<double2*>(p);
           }
           cu(comm_p_->allreduce_sum(&failed, 1, stream_));
      }
      if (failed != 0.0) {
-          packed_failed_ = true;
+          S.failed = true;
           set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not set up the packed exchange" : why);
           return false;
      }
-     packed_stage_bytes_ = bytes;
+     S.bytes = bytes;
+     S.wanted = want_bytes;
      return true;
 }
 
 bool Engine::exchange_packed(const std::vector<int>& gpos, const std::vector<int>& slots)
 {
-     // Same transposition as exchange_staged(), but the wire is a peer read: piece i is packed into my staging
-     // buffer (contiguous, HBM speed whatever the slots are), a stream-ordered barrier tells the group that every
-     // buffer is ready, and each rank unpacks straight from its PEERS' staging buffers — contiguous NVLink loads
-     // instead of the 16-64 B runs the in-place kernel makes when a swapped slot is low.  Two buffers: my pack of
-     // piece i+2 follows my barrier i+1, which completes only after every peer has queued past its unpack of piece i.
+     // Same transposition as exchange_staged(), but the wire carries contiguous full-line traffic whatever the swapped
+     // slots are (the in-place kernel makes 16-64 B runs when a slot is below 3, and NVLink moves 32 B sectors).
+     //   push (default)  piece i is gathered from my slab straight into the PEERS' staging buffers (posted NVLink
+     //                   writes), a stream-ordered barrier tells the group the pieces have landed, and every rank
+     //                   scatters its own staging buffer into its slab (local, HBM speed)
+     //   pull            piece i is gathered into MY staging buffer (local), barrier, the peers scatter from it (NVLink reads)
+     // Pipeline over two streams: the gathers and the barriers run on the engine stream, the scatters on the second one,
+     // so the scatter of piece i overlaps the gather of piece i + 1.  Two staging buffers; barrier i also certifies
+     // that everybody has scattered piece i - 1, which is what frees the buffer piece i + 1 goes into.
      const int L = static_cast<int>(locals_.size());
      const int q = static_cast<int>(gpos.size());
+     if (q > 3) {
+          set_error(HIQ_ERR_RUNTIME, "more than 3 swapped pairs");
+          return false;
+     }
      std::vector<int> order(q);
      for (int i = 0; i < q; ++i) order[i] = i;
      std::sort(order.begin(), order.end(), [&](int a, int b) { return slots[a] < slots[b]; });
      const uint64_t chunk = 1ull << (L - q);
      const int n_peers = (1 << q) - 1;
-     const uint64_t piece = std::min(chunk, kSwapPieceAmps);
-     const int max_peers = std::min(world_ - 1, 7);
-     if (!ensure_packed_staging(2ull * max_peers * kSwapPieceAmps * sizeof(double2))) return false;
+     constexpr size_t kStagingMax = 8ull << 30;
+     const size_t full = 2ull * n_peers * chunk * sizeof(double2);
+     const size_t floor_bytes = 2ull * n_peers * std::min<uint64_t>(chunk, 1ull << 16) * sizeof(double2);
+     if (!ensure_packed_staging(std::min(full, kStagingMax), floor_bytes)) return false;
+     Comm::PackedStaging& S = comm_p_->packed();
+     uint64_t piece = chunk;
+     while (2ull * n_peers * piece * sizeof(double2) > S.bytes) piece >>= 1;
+     while (packed_piece_cap_ && piece > packed_piece_cap_ && piece > 1) piece >>= 1;
      std::vector<int> peer_ranks;
      std::vector<uint64_t> pats;
      for (int x = 1; x < (1 << q); ++x) {  // peer k of rank r is r ^ bits(x): the same k names me in the peer's list
@@ -1129,22 +1179,39 @@ bool Engine::exchange_packed(const std::vector<int>& gpos, const std::vector<int
           peer_ranks.push_back(pr);
           pats.push_back(pat);
      }
-     const uint64_t n_pieces = chunk / piece;
-     for (uint64_t i = 0; i < n_pieces; ++i) {
-          const size_t buf = static_cast<size_t>(i % 2) * n_peers * piece;
-          for (int k = 0; k < n_peers; ++k)
-               cu(hiqk_swap_pack(slab_.data(), L, q, slots.data(), pats[k], i * piece, piece, packed_stage_ + buf + k * piece, stream_));
-          group_barrier(peer_ranks);
-          if (i == 0 && swap_mark_[0]) {
-               cudaEventRecord(swap_mark_[0], stream_);
-               cudaEventRecord(swap_mark_[1], stream_);
-               swap_marked_ = true;
-          }
-          for (int k = 0; k < n_peers; ++k)
-               cu(hiqk_swap_unpack(slab_.data(), L, q, slots.data(), pats[k], i * piece, piece,
-                                   packed_peer_stage_[peer_ranks[k]] + buf + k * piece, stream_));
+     if (!swap_events_[0]) {
+          for (auto& ev: swap_events_) cu(check_cuda(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming), "cudaEventCreate"));
      }
-     group_barrier(peer_ranks);  // nobody repacks or frees while a peer still reads
+     cudaEvent_t* gathered = &swap_events_[0];   // [2] piece gathered and certified by the barrier (engine stream)
+     cudaEvent_t* scattered = &swap_events_[2];  // [2] piece scattered into my slab (second stream)
+     if (swap_mark_[0]) {
+          // nothing here waits for a peer before moving data: the first gather goes into a staging buffer, not into a slab
+          cudaEventRecord(swap_mark_[0], stream_);
+          cudaEventRecord(swap_mark_[1], stream_);
+          swap_marked_ = true;
+     }
+     const uint64_t n_pieces = chunk / piece;
+     std::vector<void*> mine(n_peers), theirs(n_peers);
+     for (uint64_t i = 0; i < n_pieces; ++i) {
+          const int b = static_cast<int>(i % 2);
+          for (int k = 0; k < n_peers; ++k) {
+               const size_t off = (static_cast<size_t>(b) * n_peers + k) * piece;
+               mine[k] = S.mine + off;
+               theirs[k] = S.peers[peer_ranks[k]] + off;
+          }
+          cu(hiqk_swap_move(slab_.data(), L, q, slots.data(), n_peers, pats.data(), i * piece, piece,
+                            packed_push_ ? theirs.data() : mine.data(), 1, stream_));
+          if (i >= 1) cu(check_cuda(cudaStreamWaitEvent(stream_, scattered[(i - 1) % 2], 0), "cudaStreamWaitEvent"));
+          group_barrier(peer_ranks);
+          cu(check_cuda(cudaEventRecord(gathered[b], stream_), "cudaEventRecord"));
+          cu(check_cuda(cudaStreamWaitEvent(comm_stream_, gathered[b], 0), "cudaStreamWaitEvent"));
+          cu(hiqk_swap_move(slab_.data(), L, q, slots.data(), n_peers, pats.data(), i * piece, piece,
+                            packed_push_ ? mine.data() : theirs.data(), 0, comm_stream_));
+          cu(check_cuda(cudaEventRecord(scattered[b], comm_stream_), "cudaEventRecord"));
+     }
+     // the slab is complete, and nobody starts the next exchange (or frees anything) while a peer still reads a buffer
+     cu(check_cuda(cudaStreamWaitEvent(stream_, scattered[(n_pieces - 1) % 2], 0), "cudaStreamWaitEvent"));
+     group_barrier(peer_ranks);
      stats_.swap_bytes_sent += static_cast<double>(n_peers) * chunk * sizeof(double2);
      ++stats_.swaps_packed;
      return true;

@@ -46,6 +46,8 @@ struct EngineStats {
      uint64_t swaps_p2p = 0, swaps_staged = 0, swaps_packed = 0;
      double h2d_bytes = 0, d2h_bytes = 0;
      uint64_t gate_launches = 0;  // device launches that carried the dense/diag/scale passes above
+     double ctor_s = 0, slab_grow_s = 0, peer_map_s = 0;  // host seconds: constructor, mapping physical memory, peer-slab handshakes
+     uint64_t tile_launches = 0, tile_steps = 0;           // multi-gate tile-resident launches and the dense gates they carried
 };
 
 class Engine {
@@ -183,13 +185,11 @@ private:
      int swap_mode_ = 0;        // 0 auto, 1 staged NCCL only, 2 peer-mapped only, 3 packed peer-read only
      // packed peer-read exchange (low swapped slots): pack into a staging buffer that the group peers have opened
      // through CUDA IPC, barrier, unpack straight from the PEER's staging buffer (contiguous NVLink loads)
-     bool packed_enabled_ = false;      // HIQ_SWAP_PACKED=1 (opt-in until validated on a multi-GPU box)
+     bool packed_enabled_ = false;      // HIQ_SWAP_PACKED=1
      int packed_below_slot_ = 3;        // auto mode: used when the lowest swapped slot is below this
-     bool packed_failed_ = false;
-     double2* packed_stage_ = nullptr;  // [2 buffers][peers][piece]
-     size_t packed_stage_bytes_ = 0;
-     std::vector<double2*> packed_peer_stage_;  // by world rank; opened IPC mappings of the peers' staging buffers
-     bool ensure_packed_staging(size_t bytes);
+     uint64_t packed_piece_cap_ = 0;    // HIQ_SWAP_PACKED_PIECE: largest piece in amplitudes (tests drive the multi-piece pipeline with it)
+     bool packed_push_ = true;          // pieces are written into the peers' staging (HIQ_SWAP_PACKED_PULL=1: peers read mine)
+     bool ensure_packed_staging(size_t want_bytes, size_t min_bytes);  // process-wide buffers live in Comm::packed()
      bool exchange_packed(const std::vector<int>& gpos, const std::vector<int>& slots);
      bool p2p_broken_ = false;  // the handshake failed once: stay on the staged path
      int min_p2p_slot_ = 0;     // lowest swapped slot for which the in-place kernel is used in auto mode

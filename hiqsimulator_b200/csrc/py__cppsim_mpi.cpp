@@ -302,6 +302,11 @@ public:
           d["h2d_bytes"] = s.h2d_bytes;
           d["d2h_bytes"] = s.d2h_bytes;
           d["gate_launches"] = s.gate_launches;
+          d["ctor_s"] = s.ctor_s;
+          d["slab_grow_s"] = s.slab_grow_s;
+          d["peer_map_s"] = s.peer_map_s;
+          d["tile_launches"] = s.tile_launches;
+          d["tile_steps"] = s.tile_steps;
           return d;
      }
      py::list trace()

@@ -171,6 +171,15 @@ def swap_unpack(state, slots, pat, begin, count, buf):
     check(lib().hiqk_swap_unpack(p, L, len(slots), _ints(slots), pat, begin, count, C.c_void_p(buf.data_ptr()), _stream()))
 
 
+def swap_move(state, slots, peer_pats, begin, count, bufs, pack):
+    """all peers' pieces in one launch: gather into bufs[k] (pack) or scatter from them (unpack)"""
+    p, L = _slab(state)
+    n = len(bufs)
+    ptrs = (C.c_void_p * n)(*[b.data_ptr() for b in bufs])
+    pats = (C.c_uint64 * n)(*[int(x) for x in peer_pats])
+    check(lib().hiqk_swap_move(p, L, len(slots), _ints(slots), n, pats, begin, count, ptrs, 1 if pack else 0, _stream()))
+
+
 def swap_p2p(local, peers, slots, peer_pats, my_pat, begins, counts):
     """in-place exchange of `local` with the peer slabs (torch tensors; on one GPU they simply are other buffers)"""
     p, L = _slab(local)

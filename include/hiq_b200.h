@@ -163,6 +163,15 @@ int hiqk_swap_unpack(void* slab, int L, int q, const int* slots, uint64_t pat, u
 int hiqk_swap_p2p(void* local, void* const* peer_slabs, int n_peers, int L, int q, const int* slots,
                   const uint64_t* peer_pats, uint64_t my_pat, const uint64_t* begin, const uint64_t* count, void* stream);
 
+/* Packed exchange, all peers of a swap group in one launch: for every peer k and free index f in [begin, begin+count)
+ *   pack != 0:  bufs[k][f - begin] = slab[deposit(f) | spread(peer_pats[k])]      (gather; bufs may be peer memory)
+ *   pack == 0:  slab[deposit(f) | spread(peer_pats[k])] = bufs[k][f - begin]      (scatter)
+ * Same index convention as hiqk_swap_pack; four independent 128-bit accesses in flight per thread.  The engine uses it
+ * when a swapped slot is low: contiguous full-line NVLink traffic instead of 16-64 B runs (reference data movement:
+ * swapping.hpp:33-68 pack, SwapperMT.cpp:48-86 unpack). */
+int hiqk_swap_move(void* slab, int L, int q, const int* slots, int n_peers, const uint64_t* peer_pats, uint64_t begin,
+                   uint64_t count, void* const* bufs, int pack, void* stream);
+
 /* ---- Pauli-operator passes ------------------------------------------------------------------
  * The reference wrapper calls get_expectation_value / apply_qubit_operator on its C++ simulator
  * (reference: hiq/projectq/backends/_sim/_simulator_mpi.py:180-183, 220-223) although the reference
@@ -328,7 +337,9 @@ typedef struct hiq_stats {
      uint64_t swaps_p2p, swaps_staged; /* exchanges done in place over peer-mapped slabs / through the staged NCCL pipeline */
      double h2d_bytes, d2h_bytes; /* host<->device traffic issued by the engine (descriptor payloads, results) */
      uint64_t gate_launches;      /* device launches that carried the dense/diag/scale passes (<= their sum) */
-     uint64_t swaps_packed;       /* exchanges done by packing + reading the peers' staging buffers (opt-in, HIQ_SWAP_PACKED=1) */
+     uint64_t swaps_packed;       /* exchanges done by packing + reading the peers' staging buffers (low swapped slots) */
+     double ctor_s, slab_grow_s, peer_map_s; /* host seconds: constructor, mapping physical memory into the slab, peer-slab handshakes */
+     uint64_t tile_launches, tile_steps;     /* multi-gate tile-resident launches and the dense fused gates they carried */
 } hiq_stats;
 int hiq_get_stats(hiq_engine* e, hiq_stats* out);
 

@@ -11,7 +11,8 @@
   reductions and measurement outcomes of the reference are obtained without MPI.
 
 Script format: ``[("ctor", seed, max_local, max_cluster), (method, *args), ...]``.
-Pseudo methods: ``("cheat_local",)`` returns ``(id2pos, np.ndarray)``.
+Pseudo methods: ``("cheat_local",)`` returns ``(id2pos, np.ndarray)``; ``("timed", method, *args)`` returns the wall
+seconds the call took on that rank (bench.py's CPU swap baseline).
 Every op yields its return value, or ``("error", message)`` if it raised.
 """
 from __future__ import annotations
@@ -24,6 +25,7 @@ import subprocess
 import sys
 import sysconfig
 import tempfile
+import time
 
 import numpy as np
 
@@ -79,6 +81,10 @@ def execute_script(script):
             if name == "ctor":
                 sim = mod.SimulatorMPI(*args)
                 out.append(None)
+            elif name == "timed":  # ("timed", method, *args) -> wall seconds of that call on this rank
+                t0 = time.perf_counter()
+                getattr(sim, args[0])(*args[1:])
+                out.append(time.perf_counter() - t0)
             else:
                 out.append(_to_py(getattr(sim, name)(*args)))
         except RuntimeError as e:  # the reference throws std::runtime_error
@@ -109,6 +115,8 @@ def run_script(script, world_size: int = 1, omp_threads: int | None = None, time
                 if shm:
                     env["HIQ_REF_SHM"] = shm
                 env["OMP_NUM_THREADS"] = str(omp_threads if omp_threads else 1)
+                if world_size > 1:
+                    env.pop("OMP_PROC_BIND", None)  # every rank would bind its team to the same cores
                 env["PYTHONPATH"] = os.path.dirname(_HERE) + os.pathsep + env.get("PYTHONPATH", "")
                 procs.append(subprocess.Popen(
                     [sys.executable, "-m", "oracle.ref", spath, os.path.join(tmp, "out%d.pkl" % r)],

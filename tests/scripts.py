@@ -424,3 +424,33 @@ def replay_traces(traces, R, info=None):
                 sl = int(d["aux"][0])
                 vec[r] = np.zeros(1 << L, dtype=np.complex128) if sl < 0 else wf[sl << L:(sl + 1) << L].copy()
     return np.concatenate(vec)
+
+
+# ------------------------------------------------------------------ scheduled circuits as scripts
+def scheduled_script(kind, n, R, cluster=4, seed=1, depth=20):
+    """The bench's pipeline (circuit generator -> GreedyScheduler -> backend) recorded as a script: the post-scheduler
+    command stream (initial relabelling, gates, flushes, swaps) for `R` ranks, planned against a dry-run engine, ending
+    with the slot maps and a look at the state.  Identical on every rank; runs on the compiled reference (one process
+    per rank), the numpy oracle and the CUDA engine."""
+    import bench
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    from hiqsimulator_b200 import circuits, ops
+    g = R.bit_length() - 1
+    L = n - g
+    cmds = circuits.qft_circuit(n)[1] if kind == "qft" else circuits.random_circuit(n, depth=depth)[1]
+    stream, shape, _ = bench.schedule_circuit(n, L, cmds, lambda s, ml, mc: M.SimulatorMPI(s, ml, mc, 0, R, M.FLAG_DRY_RUN), cluster=cluster)
+    script = [("ctor", seed, L, cluster), ("allocate_qureg", list(range(n)), 0)]
+    for c in stream:
+        if isinstance(c, tuple):
+            script.append(("set_qubits_perm", list(c[1])))
+        elif c.kind == ops.FLUSH:
+            script.append(("run",))
+        elif c.kind == ops.METASWAP:
+            script.append(("run",))
+            script.append(("swap_qubits", list(c.qubits)))
+        elif c.kind == ops.GATE:
+            script.append(("apply_controlled_gate", c.matrix.tolist(), list(c.qubits), list(c.controls)))
+        else:
+            raise AssertionError("unexpected command in a scheduled stream: %r" % (c,))
+    script += [("run",), ("get_qubits_ids",), ("cheat_local",)]
+    return script, shape

@@ -107,6 +107,38 @@ def test_engine_batched_diagonals_match_oracle(nq, seed, flags):
         M.init_world(0, 1, b"", 0, 0)
 
 
+@pytest.mark.parametrize("nq", [9, 17, 21])
+def test_engine_allocate_with_launches_queued(nq):
+    """a held dense launch and queued diagonal passes are in flight when a qubit is allocated: they belong to the slab
+    as it was (2^nq amplitudes) and must go out before it grows (nq = 9: the kernel choice changes with the size,
+    nq >= 17: the upper half of the grown slab is not mapped until the allocation maps it)"""
+    M = _M()
+    rng = np.random.default_rng(90 + nq)
+    script = [("ctor", 3, nq + 2, 4), ("allocate_qureg", list(range(nq)), 0)]
+    for q in range(nq):
+        script.append(("apply_controlled_gate", G.H.tolist(), [q], []))
+        if q % 3 == 2:
+            script.append(("run",))
+    script.append(("run",))
+    for step in range(2):
+        # dense gate (held back by the engine), then diagonal gates that commute with it and some that do not
+        ids = [0, 3, 5] if step == 0 else [1, 2, nq]
+        script.append(("apply_controlled_gate", G.haar_unitary(8, rng).tolist(), ids, []))
+        script.append(("run",))
+        for t, c in ((4, 6), (3, 7), (2, 8)):
+            script.append(("apply_controlled_gate", G.R(0.3 + t).tolist(), [t], [c]))
+            script.append(("run",))
+        script.append(("allocate_qubit", nq + step))
+        script.append(("apply_controlled_gate", G.H.tolist(), [nq + step], []))
+        script.append(("apply_controlled_gate", G.X.tolist(), [0], [nq + step]))
+        script.append(("run",))
+    script.append(("get_qubits_ids",))
+    script.append(("cheat_local",))
+    exp = scripts.run_on_oracle(script, 1)
+    got = scripts.run_on_sim(M.SimulatorMPI, script)
+    scripts.assert_outputs_match(script, got, exp)
+
+
 def _gpu_count():
     import torch
     return torch.cuda.device_count()
@@ -128,14 +160,13 @@ def test_engine_matches_golden_multi_gpu(name):
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
-@pytest.mark.parametrize("mode", ["packed", "staged"])
-@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("r1_")][:4])
+@pytest.mark.parametrize("mode", ["p2p", "packed", "packed_pull", "staged"])
+@pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("r1_")])
 def test_engine_matches_golden_multi_gpu_swap_transports(name, mode):
-    """the same golden runs with the exchange forced onto the packed peer-read transport (opt-in, low swapped slots)
-    and onto the staged NCCL pipeline: every transport performs the same transposition"""
+    """the same golden runs with the exchange forced onto each transport — in place over peer-mapped slabs, packed
+    (pieces pushed into the peers' staging buffers / pulled from them) and the staged NCCL pipeline: every transport
+    performs the same transposition"""
     R = int(name[1])
-    if os.environ.get("HIQ_TEST_SWAP_TRANSPORTS") != "1":
-        pytest.skip("forced swap transports run on request (HIQ_TEST_SWAP_TRANSPORTS=1): the packed one is opt-in")
     if _gpu_count() < R:
         pytest.skip("needs %d GPUs" % R)
     import socket
@@ -145,7 +176,12 @@ def test_engine_matches_golden_multi_gpu_swap_transports(name, mode):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, HIQ_SWAP_MODE=mode))
+    env = dict(os.environ, HIQ_SWAP_MODE=mode.split("_")[0])
+    if mode.startswith("packed"):
+        env["HIQ_SWAP_PACKED_PIECE"] = "16"  # many pieces even on these small slabs: the two-buffer pipeline is exercised
+    if mode == "packed_pull":
+        env["HIQ_SWAP_PACKED_PULL"] = "1"
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 

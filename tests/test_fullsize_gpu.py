@@ -90,7 +90,9 @@ def test_qft_closed_form_at_full_size(n):
     assert worst <= TOL and marg <= TOL and abs(p_after - 1.0) <= TOL, (worst, marg, p_after)
 
 
-def test_random_circuit_then_inverse_at_full_size():
-    _need_gib(30)
-    d_amp, d_p = check_circuit_then_inverse(None, 30, 20)  # BASELINE.json config 2: 30 qubits, depth 20
+@pytest.mark.parametrize("n", [30, 33])
+def test_random_circuit_then_inverse_at_full_size(n):
+    _need_gib(n)
+    # BASELINE.json configs[1]: 30 qubits, depth 20; north_star: "a 33-qubit random circuit on 1 B200"
+    d_amp, d_p = check_circuit_then_inverse(None, n, 20)
     assert d_amp <= TOL and d_p <= TOL, (d_amp, d_p)

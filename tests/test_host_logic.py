@@ -190,3 +190,40 @@ def test_packed_exchange_scheme(L, gpos, slots, piece_bits):
         bh, bl = (src >> hi) & 1, (src >> lo) & 1
         src = src & ~((1 << hi) | (1 << lo)) | (bl << hi) | (bh << lo)
     assert np.array_equal(got, full[src])
+
+
+@pytest.mark.parametrize("kind,n,R", [("random", 13, 2), ("random", 14, 4), ("qft", 13, 8), ("random", 12, 1)])
+def test_scheduled_script_dry_run_equals_compiled_reference(kind, n, R):
+    """the script tests/test_fullsize_multigpu.py diffs on the GPUs (bench pipeline -> scheduled stream), here on dry-run
+    engines: descriptor traces replayed with the oracle kernels == the compiled reference run as R processes"""
+    from oracle import ref
+    if not ref.have_ref():
+        pytest.skip("oracle/_ref is not built")
+    script, shape = scripts.scheduled_script(kind, n, R)
+    res = scripts.merge_rank_outputs(ref.run_script(script, R, 1))
+    engines = _dry_engines(script, R)
+    ids = None
+    for op in script[1:-1]:
+        for e in engines:
+            got = getattr(e, op[0])(*op[1:])
+            if op[0] == "get_qubits_ids":
+                ids = list(got)
+    state = scripts.replay_traces([e.trace() for e in engines], R)
+    assert ids == list(res[-2])
+    assert np.abs(state - res[-1][1]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("R", [1, 4])
+def test_bench_parity_checks_pinned_on_the_oracle(R):
+    """bench.py's `parity` object (QFT closed form via get_amplitude, marginals, post-measurement state, random circuit
+    followed by its inverse) evaluated on the numpy oracle: the checks themselves hold at 1e-12 on a correct engine"""
+    import bench
+    from hiqsimulator_b200 import backends
+    from oracle import statevec
+    n = 12
+    L = n - (R.bit_length() - 1)
+    res = bench.parity_checks(n, L, lambda: backends.SimulatorMPI(gate_fusion=True, rnd_seed=5, num_local_qubits=L, max_fused_qubits=4,
+                                                                  backend_class=lambda s, ml, mc: statevec.SimulatorMPI(s, ml, mc, R)),
+                              samples=256)
+    assert res["ok"], res
+    assert res["qft_closed_form"]["max_abs_err"] <= 1e-12 and res["random_then_inverse"]["abs_amp0_minus_1"] <= 1e-12

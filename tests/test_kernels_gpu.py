@@ -429,6 +429,43 @@ def test_swap_pack_unpack(slots):
         dev = torch.from_numpy(ref.copy()).cuda()
 
 
+@pytest.mark.parametrize("slots", [(0,), (2, 0), (1, 9), (0, 1, 2), (11, 4, 1)])
+@pytest.mark.parametrize("piece", [None, 300])
+def test_swap_move_all_peers(slots, piece):
+    """hiqk_swap_move: every peer's piece gathered / scattered by one launch == numpy selection (bit-exact), whole range
+    and an odd sub-range"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 14
+    q = len(slots)
+    ref = rand_state(L, 52)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    n = 1 << (L - q)
+    begin, count = (0, n) if piece is None else (37, piece)
+    srt = sorted(slots)
+    i = np.arange(1 << L)
+    pats = list(range(1, 1 << q))  # this GPU has pattern 0; peer k has pattern k + 1
+
+    def select(pat):
+        sel = np.ones(1 << L, dtype=bool)
+        for b, s in enumerate(srt):
+            sel &= ((i >> s) & 1) == ((pat >> b) & 1)
+        return sel
+    bufs = [torch.zeros(count, dtype=torch.complex128, device="cuda") for _ in pats]
+    K.swap_move(dev, list(slots), pats, begin, count, bufs, True)
+    for pat, buf in zip(pats, bufs):
+        assert np.array_equal(buf.cpu().numpy(), ref[select(pat)][begin:begin + count])
+    # scatter different data back into the same positions
+    new = [torch.from_numpy(rand_state(L, 60 + pat)[:count].copy()).cuda() for pat in pats]
+    K.swap_move(dev, list(slots), pats, begin, count, new, False)
+    got = dev.cpu().numpy()
+    exp = ref.copy()
+    for pat, buf in zip(pats, new):
+        pos = np.nonzero(select(pat))[0][begin:begin + count]
+        exp[pos] = buf.cpu().numpy()
+    assert np.array_equal(got, exp)
+
+
 @pytest.mark.parametrize("slots", [(13,), (0,), (5, 12), (1, 0), (11, 3, 7), (0, 1, 2), (12, 13, 11)])
 @pytest.mark.parametrize("grid", [0, 2])
 def test_swap_p2p_in_place(slots, grid):

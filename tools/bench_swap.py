@@ -27,7 +27,7 @@ def main():
     sim = M.SimulatorMPI(1, L, 4)
     sim.allocate_qureg(list(range(n)), 2.0 ** (-n / 2))
     sim.synchronize()
-    mode = os.environ.get("HIQ_SWAP_MODE", "auto")
+    mode = os.environ.get("HIQ_SWAP_MODE", "auto") + ("_pull" if os.environ.get("HIQ_SWAP_PACKED_PULL") == "1" else "")
     cases = []
     for q in range(1, g + 1):
         cases += [(q, "top", list(range(L - q, L))), (q, "mid", list(range(12, 12 + q))), (q, "slot3+", list(range(3, 3 + q))),
