@@ -399,8 +399,13 @@ def cpu_leg_subprocess(args, kind, n):
 # parity checks (outside every timed region; all ranks take part, the numbers are identical on every rank)
 # ---------------------------------------------------------------------------------------------
 def release(be, eng=None):
-    be.main_engine = None  # break the engine <-> backend cycle: the slab must go before the next engine maps its own
-    del eng, be
+    """Breaks the engine <-> backend <-> scheduler cycles and drops the simulator so that its slab is unmapped NOW (the next
+    engine maps its own 128 GiB); callers rebind their own names to None as well."""
+    be.main_engine = None
+    if eng is not None:
+        eng.scheduler.backend = eng.scheduler.next_engine = None
+        eng.backend = None
+    be._simulator = None
     gc.collect()
 
 
@@ -433,6 +438,7 @@ def parity_checks(n, L, fresh_backend, samples=2048, skip_random=False):
                               "post_measurement_prob_err": abs(p_after - 1.0), "swaps": int(st["total_swaps"]),
                               "seconds": round(time.perf_counter() - t0, 2)}
     release(be, eng)
+    be = eng = None
     ok = worst <= TOL and marg <= TOL and abs(p_after - 1.0) <= TOL
     # (2) random circuit followed by its inverse
     if not skip_random:
@@ -452,6 +458,7 @@ def parity_checks(n, L, fresh_backend, samples=2048, skip_random=False):
                                       "abs_p0_minus_1": abs(p0 - 1.0), "swaps": int(st["total_swaps"]),
                                       "seconds": round(time.perf_counter() - t0, 2)}
         release(be, eng)
+        be = eng = None
         ok = ok and abs(amp - 1.0) <= TOL and abs(p0 - 1.0) <= TOL
     out["ok"] = bool(ok)
     return out
@@ -513,7 +520,7 @@ def main():
     if args.impl == "reference":
         reference_arm(args)
         return
-    if args.circuit in ("shor", "grover"):
+    if args.circuit == "shor":
         import bench_extra
         bench_extra.main(args)
         return
@@ -571,6 +578,7 @@ def main():
     if swap_ms > 0:
         swap_gbs = ds["swap_bytes_sent"] / (swap_ms * 1e-3) / 1e9
     release(be)
+    be = None
     torch.cuda.empty_cache()
 
     # ---- N = 1: the 33-qubit QFT of BASELINE.json configs[2] as a second measurement
@@ -595,6 +603,7 @@ def main():
                          "physical = launches x 32 B x 2^L / t",
                  "roofline": qroof, "kernel_breakdown": qbreak}
         release(be)
+        be = None
         torch.cuda.empty_cache()
 
     # ---- e2e: the full reference-facing pipeline, every step from host inputs to measured bits
@@ -636,6 +645,7 @@ def main():
                     parts[k] += v
             e2e_passes = st["dense_passes"] + st["diag_passes"] + st["scale_passes"]
             release(be2, eng)
+            be2 = eng = gs = None
         tt, (ww,) = reduce_max_sum(sum(per_step), [32.0 * (1 << L) * e2e_passes * len(per_step)])
         e2e = {"value": ww / tt / 1e9, "unit": UNIT,
                "h2d_bytes_per_step": int(h2d / len(per_step)), "d2h_bytes_per_step": int(d2h / len(per_step)),
@@ -669,7 +679,9 @@ def main():
                                    "diagonal fused gates ride along the next dense launch; consecutive dense gates whose targets fit one "
                                    "shared-memory tile share a launch",
                        "swaps": shape["swaps"],
-                       "swap_qubits": shape["swap_qubits"], "l2_policy": "inputs larger than L2 (slab >> 126 MB), no flush",
+                       "swap_qubits": shape["swap_qubits"],
+                       "l2_policy": "inputs larger than L2 (slab >> 126 MB), no flush" if 16.0 * (1 << L) > 4 * 126e6 else
+                                    "slab of %.0f MiB is L2-resident: a parity-size configuration, not a bandwidth measurement" % (16.0 * (1 << L) / 2 ** 20),
                        "timing": "CUDA events on the engine stream, max over ranks",
                        "series": "one family for every N: random-33 / 34 / 35 / 35 at N = 1 / 2 / 4 / 8 (BASELINE.json configs[1]/[3] generator); "
                                  "the N=1 line carries the 33-qubit QFT of configs[2] under `qft33`"},
@@ -695,7 +707,7 @@ def roofline_of(timings, L, args):
         folded = kind_id == 1 and n_ref > 1
         # dense DIRECT launches of block-structured matrices carry their mixing bits in variant bits 8..
         groups.setdefault((kind_id, k if kind_id != 2 else 0, variant & 0xff, folded, variant >> 8), []).append((ms, n_ref))
-    names = {1: "dense", 2: "diag_batch", 3: "scale", 4: "swap", 7: "tile"}
+    names = {1: "dense", 2: "diag_batch", 3: "scale", 4: "swap", 12: "tile"}
     vnames = {0: "", 1: "direct", 2: "tiled", 3: "dmma"}
 
     def gname(g):
@@ -703,12 +715,12 @@ def roofline_of(timings, L, args):
             return "swap_q%d%s" % (g[1], "_wait_for_peers" if g[2] == 1 else "")
         if g[0] == 2:
             return "diag_batch" if not args.no_batch else "diag"
-        if g[0] == 7:
+        if g[0] == 12:
             return "tile_program_%dgates" % g[1]
         return "%s_k%d_%s%s%s" % (names.get(g[0], "?"), g[1], vnames.get(g[2], ""), ("_mix%d" % g[4]) if g[4] else "",
                                   "+prediag" if g[3] else "")
     peak, peak_src = measured_peaks()
-    gate_groups = {g: v for g, v in groups.items() if g[0] in (1, 2, 3, 7)}
+    gate_groups = {g: v for g, v in groups.items() if g[0] in (1, 2, 3, 12)}
     roofline = None
     breakdown = []
     if gate_groups:

@@ -32,6 +32,11 @@ class DiagOp(C.Structure):
     _fields_ = [("k", C.c_int), ("slots", C.c_int * 5), ("lut", C.c_double * 64)]
 
 
+class TileStep(C.Structure):
+    """hiqk_tile_step of include/hiq_b200.h"""
+    _fields_ = [("k", C.c_int), ("slots", C.c_int * 5), ("matrix", C.POINTER(C.c_double)), ("pre", C.POINTER(DiagOp)), ("n_pre", C.c_int)]
+
+
 class PauliTerm(C.Structure):
     """hiqk_pauli_term of include/hiq_b200.h"""
     _fields_ = [("zmask", C.c_uint64), ("re", C.c_double), ("im", C.c_double)]
@@ -66,6 +71,8 @@ _SIGNATURES = {
     "hiqk_swap_unpack": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _u64, _u64, _u64, _vp, _vp]),
     "hiqk_swap_p2p": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _ip, C.POINTER(_u64), _u64, C.POINTER(_u64),
                                C.POINTER(_u64), _vp]),
+    "hiqk_tile_program_fits": (C.c_int, [C.c_int, C.c_int, C.POINTER(TileStep)]),
+    "hiqk_apply_tile_program": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(TileStep), _vp]),
     "hiqk_swap_move": (C.c_int, [_vp, C.c_int, C.c_int, _ip, C.c_int, C.POINTER(_u64), _u64, _u64, C.POINTER(_vp), C.c_int, _vp]),
     "hiqk_pauli_expect": (C.c_int, [_vp, C.c_int, _u64, C.POINTER(PauliTerm), C.c_int, _vp, _u64, _u64, _vp, _vp, _vp]),
     "hiqk_pauli_apply": (C.c_int, [_vp, C.c_int, _u64, C.POINTER(PauliTerm), C.c_int, _vp, C.c_int, _vp, _u64, _u64, _vp]),

@@ -29,6 +29,7 @@
 #include <type_traits>
 #include <vector>
 
+#include "dense_rows.cuh"
 #include "hiq_device.cuh"
 #include "hiq_host.hpp"
 
@@ -54,64 +55,6 @@ __device__ __forceinline__ void load_tuple(double2 (&in)[1 << K], const double2*
 {
 #pragma unroll
      for (int c = 0; c < (1 << K); ++c) in[c] = ldg_stream(base + off[c]);
-}
-
-// out[b] = sum_c m[b][c] in[c]; every row is handed to `store(b, value)` as soon as it is done.
-// KS < K: the matrix is block diagonal in its K - KS high index bits ("select" bits: the qubit multiplexes the
-// gate, it is never mixed — fused controls and diagonal factors produce these, dense_shape() below finds them
-// and moves them to the top).  Row b only meets the 2^KS columns that share its high bits; the skipped terms
-// are exact zeros, so the result equals the full product and the pass drops from 8 * 2^K to 8 * 2^KS flops
-// per amplitude — a QFT cluster (one or two Hadamards among controlled phases) turns from FP64-bound into HBM-bound.
-// Full 16x16 product with three real multiplications per complex one (Re = Ax - By, Im = (A+B)(x+y) - Ax - By):
-// 768 DFMA + 64 DADD per tuple instead of 1024 DFMA.  Under the sustained power cap the k = 4 pass is limited by
-// FP64 issue, so the pass gets faster; the rounding differs from the four-multiplication form by a few ulp of
-// the row norm (amplitudes agree with the reference far inside the 1e-12 tolerance of BASELINE.json).
-template <class Store>
-__device__ __forceinline__ void apply_rows_3m(const double2 (&in)[16], const double2* __restrict__ m, const double* __restrict__ msum,
-                                              Store store)
-{
-     double s[16];
-#pragma unroll
-     for (int c = 0; c < 16; ++c) s[c] = in[c].x + in[c].y;
-#pragma unroll
-     for (int b = 0; b < 16; ++b) {
-          double t1 = 0.0, t2 = 0.0, t3 = 0.0;
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-               t1 = fma(m[b * 16 + c].x, in[c].x, t1);
-               t2 = fma(m[b * 16 + c].y, in[c].y, t2);
-               t3 = fma(msum[b * 16 + c], s[c], t3);
-          }
-          store(b, make_double2(t1 - t2, t3 - t1 - t2));
-     }
-}
-
-template <int K, int KS = K, class Store>
-__device__ __forceinline__ void apply_rows(const double2 (&in)[1 << K], const double2* __restrict__ m,
-                                           Store store)
-{
-     constexpr int D = 1 << K;
-     constexpr int DS = 1 << KS;
-     if constexpr (K <= 4) {
-#pragma unroll
-          for (int b = 0; b < D; ++b) {
-               double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-               for (int c = (b & ~(DS - 1)); c < (b & ~(DS - 1)) + DS; ++c) cmac(acc, m[b * D + c], in[c]);
-               store(b, acc);
-          }
-     }
-     else {
-          // 32x32: keep the row loop rolled (a full unroll is 64 KB of SASS)
-          static_assert(K <= 4 || KS == K, "block form is instantiated for K <= 4 only");
-#pragma unroll 2
-          for (int b = 0; b < D; ++b) {
-               double2 acc = make_double2(0.0, 0.0);
-#pragma unroll
-               for (int c = 0; c < D; ++c) cmac(acc, m[b * D + c], in[c]);
-               store(b, acc);
-          }
-     }
 }
 
 template <int K, int THREADS, int MINB, int KS = K, bool M3 = false>
@@ -245,7 +188,7 @@ __global__ void __launch_bounds__(THREADS, MINB) dense_direct_pre_kernel(const _
      }
 }
 
-// DIRECT with diagonals folded in, block form (KS < K), register-pipelined — EXPERIMENTAL, opt-in (HIQ_DENSE_BLOCKLOOP=1).
+// DIRECT with diagonals folded in, block form (KS < K), register-pipelined.
 // The reduced product never mixes the 2^(K-KS) blocks of a tuple, so a thread only needs one block (2^KS elements)
 // live at a time: the next block is loaded into registers while the current one is multiplied and stored, nothing is
 // staged through shared memory (the staged kernel spends a quarter of its stalls on the shared-memory queue,
@@ -507,17 +450,6 @@ static void fill_msum(DirectParams<K>& p)
      else p.msum[0] = 0.0;
 }
 
-// HIQ_DENSE_BLOCKLOOP=1 routes folded-diagonal launches of block-structured gates to the register-pipelined
-// block kernel (experimental: to be measured against the staged form before it becomes the default)
-static bool dense_blockloop_enabled()
-{
-     static const bool on = [] {
-          const char* e = std::getenv("HIQ_DENSE_BLOCKLOOP");
-          return e && e[0] == '1';
-     }();
-     return on;
-}
-
 // HIQ_DENSE_3M=0 in the environment keeps the full k = 4 product on four multiplications (A/B measurements)
 static bool dense_3m_enabled()
 {
@@ -722,17 +654,17 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
           constexpr int KS = decltype(ks_c)::value;
           constexpr bool M3 = decltype(m3_c)::value;
           if constexpr (KS < K) {
-               if (dense_blockloop_enabled()) {
-                    // experimental register-pipelined block form (opt-in): no tuple staging, more resident warps
-                    constexpr int MINB2 = (K >= 3) ? (KS >= 3 ? 4 : 6) : 4;
-                    const size_t smem2 = sizeof(double2) * THREADS * std::max(p.e_npat, 1);
-                    const uint64_t cap2 = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB2 * 8);
-                    const unsigned grid2 = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap2));
-                    dense_direct_pre_blocks_kernel<K, KS, THREADS, MINB2><<<grid2, THREADS, smem2, stream>>>(p);
-                    count_launch();
-                    return check_launch("dense_direct_pre_blocks_kernel");
-               }
+               // block-structured gate: register-pipelined block form — no tuple staging, more resident warps (measured on
+               // B200, profiles/r02a_prediag_{staged,blockloop}_L30.jsonl: 6.46 -> 5.84 ms for the QFT-like launch at L = 30)
+               constexpr int MINB2 = (K >= 3) ? (KS >= 3 ? 4 : 6) : 4;
+               const size_t smem2 = sizeof(double2) * THREADS * std::max(p.e_npat, 1);
+               const uint64_t cap2 = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB2 * 8);
+               const unsigned grid2 = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap2));
+               dense_direct_pre_blocks_kernel<K, KS, THREADS, MINB2><<<grid2, THREADS, smem2, stream>>>(p);
+               count_launch();
+               return check_launch("dense_direct_pre_blocks_kernel");
           }
+          else {
           static bool attr_set = false;
           if (!attr_set) {
                cudaFuncSetAttribute(dense_direct_pre_kernel<K, THREADS, MINB, KS, M3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
@@ -742,6 +674,7 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
           dense_direct_pre_kernel<K, THREADS, MINB, KS, M3><<<grid, THREADS, smem, stream>>>(p);
           count_launch();
           return check_launch("dense_direct_pre_kernel");
+          }
      };
      if constexpr (K == 4)
           if (ks == K && dense_3m_enabled()) return go(std::integral_constant<int, K>{}, std::true_type{});

@@ -82,6 +82,12 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
           if (const char* m = std::getenv("HIQ_SWAP_PACKED_PULL")) packed_push_ = m[0] != '1';
           if (const char* m = std::getenv("HIQ_SWAP_PACKED_PIECE")) packed_piece_cap_ = std::strtoull(m, nullptr, 10);
           if (const char* m = std::getenv("HIQ_SWAP_P2P_MIN_SLOT")) min_p2p_slot_ = std::atoi(m);
+     }
+     if (const char* m = std::getenv("HIQ_TILE")) tile_enabled_ = m[0] != '0';
+     if (const char* m = std::getenv("HIQ_TILE_MAX_FULL")) tile_max_full_ = std::atoi(m);
+     if (const char* m = std::getenv("HIQ_TILE_MAX_STEPS")) tile_max_steps_ = std::max(1, std::min(HIQK_TILE_MAX_STEPS, std::atoi(m)));
+     if (const char* m = std::getenv("HIQ_TILE_SINGLE")) tile_single_ = m[0] == '1';
+     if (!dry_run_) {
           cu(check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           cu(check_cuda(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           comm_p_ = Comm::shared(rank, world_size, nccl_id, device_);
@@ -120,8 +126,8 @@ Engine::~Engine()
 
 void Engine::synchronize()
 {
+     flush_pending();  // on a dry-run engine: closes the launch accounting (stats), nothing is launched
      if (dry_run_) return;
-     flush_pending();
      cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
 }
 
@@ -406,9 +412,8 @@ bool merge_or_append(std::vector<hiqk_diag_op>& q, std::vector<int>& refs, const
 void Engine::execute(const Descriptor& d)
 {
      if (tracing_) trace_.push_back(d);
-     if (dry_run_) return;
      const int L = static_cast<int>(locals_.size());
-     stats_.h2d_bytes += static_cast<double>(d.payload.size() * sizeof(cplx));
+     if (!dry_run_) stats_.h2d_bytes += static_cast<double>(d.payload.size() * sizeof(cplx));
      int variant = 0;
      if (d.kind == HIQ_DESC_DENSE) variant = dense_variant_ ? dense_variant_ : hiqk_dense_pick_variant(L, d.k, d.slots);
      if (batching_) {
@@ -418,22 +423,55 @@ void Engine::execute(const Descriptor& d)
                queue_diagonal(d);
                return;
           }
-          if (d.kind == HIQ_DESC_DENSE && d.ctrl_mask == 0 && variant == HIQK_DENSE_DIRECT &&
-              hiqk_dense_prediag_supported(L, d.k, d.slots)) {
-               launch_held();                         // the previous dense launch goes out now
-               flush_pending(HIQK_MAX_DIAG_OPS);      // more diagonals than one launch carries: batched passes first
-               held_ = true;
-               held_d_ = d;
-               held_variant_ = variant;
-               held_ops_.swap(pending_);              // they precede this gate: applied to the tuples it loads
-               held_ref_.swap(pending_ref_);
-               pending_.clear();
-               pending_ref_.clear();
-               return;
+          if (d.kind == HIQ_DESC_DENSE && d.ctrl_mask == 0 && d.k <= 4 && dense_variant_ == 0) {
+               const bool direct = variant == HIQK_DENSE_DIRECT && hiqk_dense_prediag_supported(L, d.k, d.slots);
+               HeldGate cand;
+               cand.d = d;
+               cand.variant = variant;
+               cand.direct = direct;
+               cand.full = hiqk_dense_direct_mixing_bits(d.k, reinterpret_cast<const double*>(d.payload.data())) >= 4;
+               // the diagonals queued so far precede this gate; more than one launch carries go out as batched passes first
+               const size_t cap = tile_enabled_ ? HIQK_TILE_MAX_OPS : HIQK_MAX_DIAG_OPS;
+               if (pending_.size() > cap) flush_pending(cap);
+               if (tile_enabled_ && !group_.empty() && group_accepts(cand, pending_)) {
+                    cand.ops.swap(pending_);
+                    cand.refs.swap(pending_ref_);
+                    group_.push_back(std::move(cand));
+                    return;
+               }
+               launch_group();  // the gates held so far go out now
+               if (pending_.size() > cap) flush_pending(cap);
+               if (direct || (tile_enabled_ && group_accepts(cand, pending_))) {
+                    cand.ops.swap(pending_);  // applied to the tuples this gate loads
+                    cand.refs.swap(pending_ref_);
+                    group_.push_back(std::move(cand));
+                    return;
+               }
           }
      }
      flush_pending();
      launch(d, variant, {}, {});
+}
+
+bool Engine::group_accepts(const HeldGate& cand, const std::vector<hiqk_diag_op>& cand_ops) const
+{
+     // may `cand` (with the diagonals that precede it) join the gates held so far in one tile-resident pass?
+     const int L = static_cast<int>(locals_.size());
+     if (group_.size() + 1 > static_cast<size_t>(tile_max_steps_)) return false;
+     int n_full = cand.full ? 1 : 0;
+     for (const HeldGate& g: group_) n_full += g.full ? 1 : 0;
+     if (n_full > tile_max_full_ && group_.size() + 1 > 1) return false;
+     std::vector<hiqk_tile_step> steps(group_.size() + 1);
+     auto fill = [](hiqk_tile_step& st, const HeldGate& g, const std::vector<hiqk_diag_op>& ops) {
+          st.k = g.d.k;
+          for (int l = 0; l < 5; ++l) st.slots[l] = g.d.slots[l];
+          st.matrix = reinterpret_cast<const double*>(g.d.payload.data());
+          st.pre = ops.data();
+          st.n_pre = static_cast<int>(ops.size());
+     };
+     for (size_t i = 0; i < group_.size(); ++i) fill(steps[i], group_[i], group_[i].ops);
+     fill(steps.back(), cand, cand_ops);
+     return hiqk_tile_program_fits(L, static_cast<int>(steps.size()), steps.data()) != 0;
 }
 
 void Engine::queue_diagonal(const Descriptor& d)
@@ -443,30 +481,80 @@ void Engine::queue_diagonal(const Descriptor& d)
      op.k = d.kind == HIQ_DESC_SCALE ? 0 : d.k;
      for (int l = 0; l < op.k; ++l) op.slots[l] = d.slots[l];
      std::memcpy(op.lut, d.payload.data(), sizeof(cplx) << op.k);
-     if (held_) {
+     if (!group_.empty()) {
+          HeldGate& h = group_.back();
           uint64_t tm = 0;
-          for (int l = 0; l < held_d_.k; ++l) tm |= 1ull << held_d_.slots[l];
-          // commutes with the held dense gate: joins its launch as a per-tuple scalar
-          if ((slot_mask(op) & tm) == 0 && merge_or_append(held_ops_, held_ref_, op, HIQK_MAX_DIAG_OPS)) return;
+          for (int l = 0; l < h.d.k; ++l) tm |= 1ull << h.d.slots[l];
+          // commutes with the most recent held gate: joins its launch as a per-tuple scalar
+          if ((slot_mask(op) & tm) == 0) {
+               const size_t cap = group_.size() > 1 || !h.direct ? HIQK_TILE_MAX_OPS : HIQK_MAX_DIAG_OPS;
+               std::vector<hiqk_diag_op> ops = h.ops;
+               std::vector<int> refs = h.refs;
+               if (merge_or_append(ops, refs, op, cap)) {
+                    bool ok = true;
+                    if (group_.size() > 1 || !h.direct) {  // the run must still fit its tile program (table pool)
+                         HeldGate last = std::move(group_.back());
+                         group_.pop_back();
+                         ok = group_accepts(last, ops);
+                         group_.push_back(std::move(last));
+                    }
+                    if (ok) {
+                         group_.back().ops.swap(ops);
+                         group_.back().refs.swap(refs);
+                         return;
+                    }
+               }
+          }
      }
      merge_or_append(pending_, pending_ref_, op, static_cast<size_t>(-1));
 }
 
-void Engine::launch_held()
+void Engine::launch_group()
 {
-     if (!held_) return;
-     held_ = false;
-     launch(held_d_, held_variant_, held_ops_, held_ref_);
-     held_ops_.clear();
-     held_ref_.clear();
+     if (group_.empty()) return;
+     std::vector<HeldGate> g;
+     g.swap(group_);
+     if (g.size() == 1 && g[0].direct && !tile_single_) {
+          launch(g[0].d, g[0].variant, g[0].ops, g[0].refs);
+          return;
+     }
+     if (g.size() == 1 && g[0].ops.empty() && !tile_single_) {
+          launch(g[0].d, g[0].variant, {}, {});
+          return;
+     }
+     const int L = static_cast<int>(locals_.size());
+     std::vector<hiqk_tile_step> steps(g.size());
+     int n_ref = 0;
+     for (size_t i = 0; i < g.size(); ++i) {
+          steps[i].k = g[i].d.k;
+          for (int l = 0; l < 5; ++l) steps[i].slots[l] = g[i].d.slots[l];
+          steps[i].matrix = reinterpret_cast<const double*>(g[i].d.payload.data());
+          steps[i].pre = g[i].ops.data();
+          steps[i].n_pre = static_cast<int>(g[i].ops.size());
+          n_ref += 1;
+          for (int r: g[i].refs) n_ref += r;
+     }
+     TimedPass tp{HIQ_DESC_TILE, static_cast<int>(g.size()), 0, n_ref, nullptr, nullptr};
+     if (timing_) {
+          tp.start = take_event();
+          tp.stop = take_event();
+          cudaEventRecord(tp.start, stream_);
+     }
+     if (!dry_run_) cu(hiqk_apply_tile_program(slab_.data(), L, static_cast<int>(steps.size()), steps.data(), stream_));
+     ++stats_.gate_launches;
+     ++stats_.tile_launches;
+     stats_.tile_steps += g.size();
+     if (timing_) {
+          cudaEventRecord(tp.stop, stream_);
+          timed_.push_back(tp);
+     }
 }
 
 void Engine::flush_pending(size_t keep)
 {
-     // the held dense launch first (queued diagonals that touch its targets come after it), then
+     // the held gates first (queued diagonals that touch the last one's targets come after it), then
      // batched diagonal launches (full batches first) until at most `keep` ops remain queued
-     if (dry_run_) return;
-     launch_held();
+     launch_group();
      while (pending_.size() > keep) {
           const size_t take = std::min<size_t>(pending_.size(), HIQK_MAX_DIAG_OPS);
           int n_ref = 0;
@@ -477,7 +565,8 @@ void Engine::flush_pending(size_t keep)
                tp.stop = take_event();
                cudaEventRecord(tp.start, stream_);
           }
-          cu(hiqk_apply_diag_batch(slab_.data(), static_cast<int>(locals_.size()), pending_.data(), static_cast<int>(take), stream_));
+          if (!dry_run_)
+               cu(hiqk_apply_diag_batch(slab_.data(), static_cast<int>(locals_.size()), pending_.data(), static_cast<int>(take), stream_));
           ++stats_.gate_launches;
           if (timing_) {
                cudaEventRecord(tp.stop, stream_);
@@ -504,6 +593,8 @@ void Engine::launch(const Descriptor& d, int variant, const std::vector<hiqk_dia
           tp.stop = take_event();
           cudaEventRecord(tp.start, stream_);
      }
+     ++stats_.gate_launches;
+     if (dry_run_) return;
      switch (d.kind) {
           case HIQ_DESC_DENSE:
                if (!ops.empty())
@@ -520,7 +611,6 @@ void Engine::launch(const Descriptor& d, int variant, const std::vector<hiqk_dia
           case HIQ_DESC_SCALE: cu(hiqk_scale(slab_.data(), L, d.payload[0].real(), d.payload[0].imag(), stream_)); break;
           default: break;
      }
-     ++stats_.gate_launches;
      if (timing_) {
           cudaEventRecord(tp.stop, stream_);
           timed_.push_back(tp);
@@ -783,9 +873,7 @@ void Engine::copy_slab_from_host(const void* src, uint64_t n_amps)
 {
      need_device("set_local_slab()");
      if (n_amps != (1ull << locals_.size())) fail("set_local_slab(): size must equal 2^(local qubits)");
-     held_ = false;  // the whole slab is overwritten
-     held_ops_.clear();
-     held_ref_.clear();
+     group_.clear();  // the whole slab is overwritten
      pending_.clear();
      pending_ref_.clear();
      cu(check_cuda(cudaMemcpyAsync(slab_.data(), src, n_amps * sizeof(double2), cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync"));

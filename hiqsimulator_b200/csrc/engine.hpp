@@ -151,7 +151,6 @@ private:
      void normalize(double norm, uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv);
      void execute(const Descriptor& d);
      void launch(const Descriptor& d, int variant, const std::vector<hiqk_diag_op>& ops, const std::vector<int>& refs);
-     void launch_held();
      void queue_diagonal(const Descriptor& d);
      void flush_pending(size_t keep = 0);
      void ensure_scratch();
@@ -208,14 +207,27 @@ private:
      // passes of the reference's plan op i stands for (ops over the same slots are multiplied on the host).
      std::vector<hiqk_diag_op> pending_;
      std::vector<int> pending_ref_;
-     // The most recent dense launch is held back until the next dense gate (or the next observation):
-     // diagonal gates that arrive meanwhile and avoid its targets commute with it and join its launch as
-     // per-tuple scalars; the ones that touch its targets wait in pending_ for the next dense launch.
-     bool held_ = false;
-     Descriptor held_d_;
-     int held_variant_ = 0;
-     std::vector<hiqk_diag_op> held_ops_;
-     std::vector<int> held_ref_;
+     // Dense launches are held back until the next dense gate that cannot share their pass (or the next observation):
+     //  * diagonal gates that arrive meanwhile and avoid the most recent held gate's targets commute with it and join its
+     //    launch as per-tuple scalars; the ones that touch its targets wait in pending_ for the next dense gate;
+     //  * consecutive dense gates whose targets (plus four low slots) fit one shared-memory tile form a RUN that goes out as
+     //    one tile-resident launch (csrc/tile_program.cu): one HBM pass for the whole run.  The plan itself — clusters,
+     //    swaps, their order — is the reference's; only the number of sweeps over the slab changes.
+     struct HeldGate {
+          Descriptor d;
+          int variant = 0;
+          bool direct = false;  // the one-gate DIRECT launch can carry its diagonals itself
+          bool full = false;    // full 16 x 16 product (no block structure): FP64-bound
+          std::vector<hiqk_diag_op> ops;  // diagonal factors applied before this gate
+          std::vector<int> refs;          // passes of the reference's plan each of them stands for
+     };
+     std::vector<HeldGate> group_;
+     bool tile_enabled_ = true;   // HIQ_TILE=0: one launch per dense gate (round-1 behaviour)
+     int tile_max_steps_ = HIQK_TILE_MAX_STEPS;
+     int tile_max_full_ = 1;      // full products per run (HIQ_TILE_MAX_FULL): two of them in one pass are FP64-bound
+     bool tile_single_ = false;   // HIQ_TILE_SINGLE=1: single gates take the tile kernel too (A/B measurements)
+     bool group_accepts(const HeldGate& cand, const std::vector<hiqk_diag_op>& cand_ops) const;
+     void launch_group();
      std::vector<TimedPass> timed_;
      std::vector<cudaEvent_t> event_pool_;
      cudaEvent_t take_event();

@@ -10,7 +10,7 @@ import math
 
 import numpy as np
 
-from ._lib import DiagOp, PauliTerm, Perm, check, lib
+from ._lib import DiagOp, PauliTerm, Perm, TileStep, check, lib
 
 AUTO, DIRECT, TILED, DMMA, DIRECT_FULL = 0, 1, 2, 3, 4
 
@@ -88,6 +88,36 @@ def apply_dense_prediag(state, slots, matrix, pre):
     keep, mp = _cplx(matrix)
     arr = _diag_ops(pre)
     check(lib().hiqk_apply_dense_prediag(p, L, len(slots), _ints(slots), mp, arr, len(pre), _stream()))
+
+
+def _tile_steps(steps):
+    """steps: [(slots, matrix, [(slots, diag), ...]), ...] -> (ctypes array of hiqk_tile_step, objects to keep alive)"""
+    arr = (TileStep * len(steps))()
+    keep = []
+    for st, (slots, matrix, pre) in zip(arr, steps):
+        m, mp = _cplx(matrix)
+        ops = _diag_ops(pre) if pre else None
+        keep += [m, ops]
+        st.k = len(slots)
+        for l, sl in enumerate(slots):
+            st.slots[l] = int(sl)
+        st.matrix = mp
+        st.pre = ops if ops is not None else C.POINTER(DiagOp)()
+        st.n_pre = len(pre) if pre else 0
+    return arr, keep
+
+
+def tile_program_fits(L, steps) -> int:
+    """tile size in bits (11 / 12) when the run of gates can share one pass, 0 when it cannot — host only"""
+    arr, keep = _tile_steps(steps)
+    return int(lib().hiqk_tile_program_fits(L, len(steps), arr))
+
+
+def apply_tile_program(state, steps):
+    """One pass: for every step in order, psi <- M_s * prod_j D_sj * psi (tile-resident gate program)"""
+    p, L = _slab(state)
+    arr, keep = _tile_steps(steps)
+    check(lib().hiqk_apply_tile_program(p, L, len(steps), arr, _stream()))
 
 
 def dense_prediag_supported(L, slots) -> bool:

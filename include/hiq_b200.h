@@ -138,6 +138,24 @@ int hiqk_collapse(void* slab, int L, uint64_t mask, uint64_t val, double scale, 
 /* psi[i] = (re, im) for i in [begin, begin+count)   (FillVector, SimulatorMPI.cpp:136-146) */
 int hiqk_fill(void* slab, uint64_t begin, uint64_t count, double re, double im, void* stream);
 
+/* Tile-resident gate program: up to HIQK_TILE_MAX_STEPS consecutive dense fused gates of the plan (1..4 targets, no
+ * control mask), each preceded by up to HIQK_TILE_MAX_OPS diagonal factors, applied in ONE pass over the slab: a CTA
+ * keeps a tile of 2^11 or 2^12 amplitudes (>= 4 low slots x every combination of the higher targets of the run) in
+ * shared memory while the gates go by.  Same result as hiqk_apply_dense_prediag called once per gate (reference: one
+ * kernelK / kernel_core_diag sweep per fused cluster, SimulatorMPI.cpp:470-515).  hiqk_tile_program_fits returns the tile
+ * size in bits (11 / 12) when the run can be taken, 0 when it cannot (targets too spread out, too many tables). */
+#define HIQK_TILE_MAX_STEPS 4
+#define HIQK_TILE_MAX_OPS 16
+typedef struct hiqk_tile_step {
+     int k;
+     int slots[5];               /* matrix index bit l <-> slab slot slots[l] */
+     const double* matrix;       /* 2^k x 2^k complex128, row-major, interleaved re/im */
+     const hiqk_diag_op* pre;    /* diagonal factors applied before this gate (after the previous gate of the run) */
+     int n_pre;
+} hiqk_tile_step;
+int hiqk_tile_program_fits(int L, int n_steps, const hiqk_tile_step* steps);
+int hiqk_apply_tile_program(void* slab, int L, int n_steps, const hiqk_tile_step* steps, void* stream);
+
 /* Remove bit `slot` from the index space keeping the half where that bit == keep:
  * dst[j] = src[insert_bit(j, slot, keep)], j < 2^(L-1).  dst may alias the start of src
  * (the launcher stages through `scratch`, `scratch_amps` amplitudes, in index order).
@@ -258,6 +276,7 @@ typedef struct hiq_engine hiq_engine;
 /* aux = [HIQK_PERM_*, a, N, ctrl mask over the global index, this rank takes part (0/1), pos_0 .. pos_{k-1}, inverse table] */
 #define HIQ_DESC_PERMUTE 10
 #define HIQ_DESC_LOAD 11 /* set_wavefunction: aux = [slice of the host vector this rank copies, -1 = zeros] */
+#define HIQ_DESC_TILE 12 /* timing records only: one tile-resident launch that carried k dense gates of the plan */
 
 typedef struct hiq_descriptor {
      int kind;           /* HIQ_DESC_* */

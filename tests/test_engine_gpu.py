@@ -139,6 +139,35 @@ def test_engine_allocate_with_launches_queued(nq):
     scripts.assert_outputs_match(script, got, exp)
 
 
+@pytest.mark.parametrize("env", [{"HIQ_TILE": "0"}, {"HIQ_TILE_MAX_FULL": "2"}, {"HIQ_TILE_MAX_FULL": "4", "HIQ_TILE_SINGLE": "1"},
+                                 {"HIQ_TILE_MAX_STEPS": "2"}])
+@pytest.mark.parametrize("kind,nq", [("random", 14), ("qft", 16), ("random", 19), ("qft", 21)])
+def test_engine_tile_runs_match_oracle(kind, nq, env):
+    """the bench pipeline (scheduled circuit) with every grouping policy of the tile-resident launches — off, two / four
+    full products per run, single gates through the tile kernel, short runs: same state as the numpy oracle, and the
+    grouping never changes the plan (slot maps equal)"""
+    M = _M()
+    script, shape = scripts.scheduled_script(kind, nq, 1)
+    exp = scripts.run_on_oracle(script, 1)
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        keep = []
+        got = scripts.run_on_sim(M.SimulatorMPI, script, keep)
+        st = keep[0].stats()
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+    scripts.assert_outputs_match(script, got, exp)
+    if env.get("HIQ_TILE") == "0":
+        assert st["tile_launches"] == 0
+    elif nq >= 16:
+        assert st["tile_launches"] >= 1 and st["tile_steps"] > st["tile_launches"]
+
+
 def _gpu_count():
     import torch
     return torch.cuda.device_count()

@@ -249,6 +249,85 @@ def test_apply_dense_prediag_block_structure(k, slots, select, n_pre):
     assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
 
 
+def _tile_reference(ref, steps):
+    for slots, m, pre in steps:
+        for sl, d in pre:
+            if sl:
+                statevec.apply_diag(ref, sl, d, 0)
+            else:
+                ref *= d[0]
+        statevec.apply_dense(ref, list(slots), m, 0)
+
+
+TILE_RUNS = [
+    # (L, [(k, slots, select bits of the matrix or None = dense, number of diagonal ops)], expected tile bits)
+    (15, [(4, (11, 12, 13, 14), None, 0)], 11),
+    (15, [(4, (11, 12, 13, 14), (2, 3), 3), (4, (9, 10, 13, 14), (0, 1), 5), (4, (9, 10, 11, 12), (2, 3), 12)], 11),   # 6 high slots
+    (16, [(4, (12, 13, 14, 15), (0, 1), 2), (4, (10, 11, 12, 13), (2, 3), 4), (4, (8, 9, 10, 11), (2, 3), 6)], 12),     # QFT-like chain
+    (16, [(4, (7, 8, 9, 10), (2, 3), 2), (4, (5, 6, 7, 8), (2, 3), 3), (4, (3, 4, 5, 6), (2, 3), 4), (4, (1, 2, 3, 4), (2, 3), 5)], 11),
+    (14, [(3, (0, 1, 2), (1, 2), 6), (4, (1, 2, 3, 4), None, 2)], 11),                                                  # slot-0 targets
+    (15, [(4, (0, 5, 9, 13), None, 1), (4, (2, 6, 9, 12), None, 2)], 11),                                               # two full products
+    (17, [(2, (3, 16), None, 1), (1, (14,), None, 0), (3, (15, 0, 7), (1,), 4), (4, (12, 13, 14, 15), (0,), 7)], 11),
+    (16, [(4, (0, 1, 14, 15), None, 12), (4, (2, 3, 12, 13), None, 9)], 12),
+]
+
+
+@pytest.mark.parametrize("case", range(len(TILE_RUNS)))
+def test_tile_program_matches_oracle(case):
+    """a run of dense gates, each preceded by diagonal factors, in ONE tile-resident pass == the reference's
+    one-sweep-per-fused-gate sequence (numpy oracle), every target / select / class-E configuration"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L, run, tile_bits = TILE_RUNS[case]
+    rng = np.random.default_rng(900 + case)
+    steps = []
+    for i, (k, slots, select, n_pre) in enumerate(run):
+        m = rand_matrix(k, 17 * case + i) if select is None else multiplexed_matrix(k, list(select), 13 * case + i)
+        ops = _rand_diag_ops(L, n_pre, 1000 * case + i)
+        ops = [(sl[:4], d[:1 << len(sl[:4])]) for sl, d in ops]  # tables of at most 16 entries (cluster size 4)
+        if n_pre:  # one op entirely inside the targets, one overlapping them partly
+            ops[0] = (list(slots[:max(1, k - 1)]), np.exp(1j * np.linspace(0.1, 2.0, 1 << max(1, k - 1))))
+        if n_pre > 1:
+            other = [s for s in range(L) if s not in slots]
+            ops[1] = ([slots[0], other[0], other[-1]], np.exp(1j * np.linspace(0.3, 3.0, 8)))
+        steps.append((slots, m, ops))
+    assert K.tile_program_fits(L, steps) == tile_bits
+    ref = rand_state(L, 800 + case)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_tile_program(dev, steps)
+    _tile_reference(ref, steps)
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+def test_tile_program_multi_iteration(tiny_grid):
+    """more tiles than CTAs: every CTA walks several tiles (per-tile selectors, tile reuse)"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L = 18
+    steps = []
+    for i, slots in enumerate([(13, 14, 15, 16), (11, 12, 13, 14), (9, 10, 11, 12)]):
+        ops = _rand_diag_ops(L, 5, 40 + i)
+        ops = [(sl[:4], d[:1 << len(sl[:4])]) for sl, d in ops]
+        ops[0] = ([slots[1], 17, 2], np.exp(1j * np.linspace(0.2, 2.5, 8)))
+        steps.append((slots, multiplexed_matrix(4, [2, 3], 50 + i), ops))
+    ref = rand_state(L, 77)
+    dev = torch.from_numpy(ref.copy()).cuda()
+    K.apply_tile_program(dev, steps)
+    K.apply_tile_program(dev, steps[:2])
+    _tile_reference(ref, steps)
+    _tile_reference(ref, steps[:2])
+    assert np.abs(dev.cpu().numpy() - ref).max() <= TOL
+
+
+def test_tile_program_rejects_what_does_not_fit():
+    from hiqsimulator_b200 import kernels as K
+    m = rand_matrix(4, 1)
+    wide = [((20, 21, 22, 23), m, []), ((10, 11, 12, 13), m, []), ((15, 16, 17, 18), m, [])]  # 12 high slots
+    assert K.tile_program_fits(26, wide) == 0
+    assert K.tile_program_fits(26, wide[:2]) == 12
+    assert K.tile_program_fits(10, [((0, 1, 2, 3), m, [])]) == 0  # slab smaller than a tile
+
+
 def test_apply_dense_block_structure_multi_iteration(tiny_grid):
     torch = _torch()
     from hiqsimulator_b200 import kernels as K
@@ -672,18 +751,3 @@ def test_permute_gather_rejects_bad_arguments():
         K.permute_gather(d, [s, None], 0, K.PERM_ADD, [0, 8], 0, 1, 0)
 
 
-def test_experimental_blockloop_kernel_parity():
-    """HIQ_DENSE_BLOCKLOOP=1 (register-pipelined block form of the folded-diagonal launch, csrc/apply_dense.cu): the
-    prediag parity cases again, in a child process that has the switch set.  Runs on request only
-    (HIQ_TEST_EXPERIMENTAL=1) until the kernel has been measured and made the default."""
-    import os
-    import subprocess
-    import sys
-    if os.environ.get("HIQ_TEST_EXPERIMENTAL") != "1":
-        pytest.skip("experimental kernel: set HIQ_TEST_EXPERIMENTAL=1")
-    here = os.path.dirname(os.path.abspath(__file__))
-    env = dict(os.environ, HIQ_DENSE_BLOCKLOOP="1")
-    env.pop("HIQ_TEST_EXPERIMENTAL")
-    res = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_kernels_gpu.py"), "-m", "gpu", "-q", "-p", "no:cacheprovider",
-                          "-k", "prediag"], capture_output=True, text=True, timeout=600, env=env, cwd=os.path.dirname(here))
-    assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-2000:]
