@@ -116,6 +116,9 @@ class SimulatorMPI:
                 self._simulator.emulate_math_multiply_by_constant_modN(cmd.math[1], cmd.math[2], list(cmd.quregs[0]), ctrls)
             else:
                 raise Exception("unknown math gate %r" % (cmd.math,))
+        elif cmd.kind == ops.TIME_EVOLUTION:  # reference: the TimeEvolution branch, _simulator_mpi.py:469-475
+            t, op = cmd.math
+            self._simulator.emulate_time_evolution(self._terms(op, len(cmd.qubits)), t, list(cmd.qubits), list(cmd.controls))
         elif cmd.kind == ops.GATE and len(cmd.matrix) <= 2 ** 5:
             if not 2 ** len(cmd.qubits) == len(cmd.matrix):
                 raise Exception("Simulator: Error applying {} gate: {}-qubit gate applied to {} qubits.".format(

@@ -227,6 +227,17 @@ int hiq_apply_qubit_operator(hiq_engine* e, const int* term_offsets, const int* 
      });
 }
 
+int hiq_emulate_time_evolution(hiq_engine* e, const int* term_offsets, const int* factor_index, const char* factor_pauli,
+                               const double* coefs_re_im, int n_terms, double time, const int64_t* ids, int n_ids,
+                               const int64_t* ctrls, int n_ctrls)
+{
+     NEED(e);
+     return guarded([&] {
+          e->impl.emulate_time_evolution(pauli_terms(term_offsets, factor_index, factor_pauli, coefs_re_im, n_terms), time,
+                                         vec_ids(ids, n_ids), vec_ids(ctrls, n_ctrls));
+     });
+}
+
 int hiq_set_wavefunction(hiq_engine* e, const double* amps_re_im, uint64_t n_amps, const int64_t* ids, int n_ids)
 {
      NEED(e);

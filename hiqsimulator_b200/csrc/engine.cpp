@@ -4,6 +4,7 @@
 #include <cmath>
 #include <unistd.h>
 
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <sstream>
@@ -533,6 +534,19 @@ void Engine::launch_group()
           steps[i].n_pre = static_cast<int>(g[i].ops.size());
           n_ref += 1;
           for (int r: g[i].refs) n_ref += r;
+     }
+     if (std::getenv("HIQ_TILE_DEBUG")) {
+          std::fprintf(stderr, "tile run (T=%d):", hiqk_tile_program_fits(L, static_cast<int>(steps.size()), steps.data()));
+          for (size_t i = 0; i < g.size(); ++i) {
+               uint64_t tm = 0;
+               for (int l = 0; l < g[i].d.k; ++l) tm |= 1ull << g[i].d.slots[l];
+               int n_e = 0;
+               for (const hiqk_diag_op& o: g[i].ops) n_e += (slot_mask(o) & tm) ? 1 : 0;
+               std::fprintf(stderr, "  [k=%d ks=%d slots", g[i].d.k, hiqk_dense_direct_mixing_bits(g[i].d.k, steps[i].matrix));
+               for (int l = 0; l < g[i].d.k; ++l) std::fprintf(stderr, " %d", g[i].d.slots[l]);
+               std::fprintf(stderr, " | ops %zu, on targets %d]", g[i].ops.size(), n_e);
+          }
+          std::fprintf(stderr, "\n");
      }
      TimedPass tp{HIQ_DESC_TILE, static_cast<int>(g.size()), 0, n_ref, nullptr, nullptr};
      if (timing_) {

@@ -108,6 +108,8 @@ public:
      };
      double get_expectation_value(const std::vector<PauliTerm>& terms, const std::vector<Index>& ids);
      void apply_qubit_operator(const std::vector<PauliTerm>& terms, const std::vector<Index>& ids);
+     void emulate_time_evolution(const std::vector<PauliTerm>& terms, double time, const std::vector<Index>& ids,
+                                 const std::vector<Index>& ctrls);
      void set_wavefunction(const cplx* amps, uint64_t n_amps, const std::vector<Index>& ordering);
      // kind = HIQK_PERM_*; fwd_table (TABLE only) = f(v) for every value of the concatenated registers
      void emulate_math(int kind, uint64_t a, uint64_t N, const std::vector<uint64_t>& fwd_table, const std::vector<Index>& reg_ids,

@@ -328,6 +328,36 @@ extern "C" int hiqk_pauli_apply(void* slab, int L, uint64_t xmask, const hiqk_pa
      return check_launch("pauli_apply_kernel");
 }
 
+// y[j] += a * x[j] for every j with (j & mask) == val  (x may alias y: y *= 1 + a).  The Taylor accumulation and the
+// control handling of emulate_time_evolution (ProjectQ simulator.hpp: output_state[j] += update[j] when the control
+// bits of j are set; reference call site: _simulator_mpi.py:469-475).
+namespace hiq {
+__global__ void __launch_bounds__(kOpThreads) axpy_masked_kernel(double2* y, const double2* x, uint64_t n, uint64_t mask, uint64_t val,
+                                                                 double2 a)
+{
+     const uint64_t stride = static_cast<uint64_t>(gridDim.x) * kOpThreads;
+     for (uint64_t j = static_cast<uint64_t>(blockIdx.x) * kOpThreads + threadIdx.x; j < n; j += stride) {
+          if ((j & mask) != val) continue;
+          const double2 xv = ldg_stream(x + j);
+          double2 yv = y[j];
+          yv.x = fma(a.x, xv.x, fma(-a.y, xv.y, yv.x));
+          yv.y = fma(a.x, xv.y, fma(a.y, xv.x, yv.y));
+          y[j] = yv;
+     }
+}
+}  // namespace hiq
+
+extern "C" int hiqk_axpy_masked(void* y, const void* x, int L, uint64_t mask, uint64_t val, double a_re, double a_im, void* stream)
+{
+     if (!y || !x || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_axpy_masked: bad argument");
+     if ((L < 64 && (mask >> L)) || (val & ~mask)) return set_error(HIQ_ERR_ARG, "hiqk_axpy_masked: mask / value outside the slab");
+     const uint64_t n = 1ull << L;
+     axpy_masked_kernel<<<op_grid(n, 4), kOpThreads, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<double2*>(y), static_cast<const double2*>(x),
+                                                                                               n, mask, val, make_double2(a_re, a_im));
+     count_launch();
+     return check_launch("axpy_masked_kernel");
+}
+
 extern "C" int hiq_modinv(uint64_t a, uint64_t N, uint64_t* out)
 {
      // a^-1 mod N by the extended Euclidean algorithm; fails when gcd(a, N) != 1

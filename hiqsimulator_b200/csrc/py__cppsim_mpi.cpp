@@ -200,6 +200,13 @@ public:
           check(hiq_apply_qubit_operator(e_, f.offsets.data(), f.index.data(), f.pauli.data(), f.coefs.data(), static_cast<int>(td.size()),
                                          ids.data(), static_cast<int>(ids.size())));
      }
+     void emulate_time_evolution(const TermsDict& td, double time, const std::vector<int64_t>& ids, const std::vector<int64_t>& ctrls)
+     {
+          FlatTerms f(td);
+          py::gil_scoped_release nogil;
+          check(hiq_emulate_time_evolution(e_, f.offsets.data(), f.index.data(), f.pauli.data(), f.coefs.data(), static_cast<int>(td.size()),
+                                           time, ids.data(), static_cast<int>(ids.size()), ctrls.data(), static_cast<int>(ctrls.size())));
+     }
      void set_wavefunction(py::array_t<cplx, py::array::c_style | py::array::forcecast> wf, const std::vector<int64_t>& ids)
      {
           check(hiq_set_wavefunction(e_, reinterpret_cast<const double*>(wf.data()), static_cast<uint64_t>(wf.size()), ids.data(),
@@ -403,6 +410,7 @@ PYBIND11_MODULE(_cppsim_mpi, m)
          .def("emulate_math_multiply_by_constant_modN", &SimulatorB200::emulate_math_multiply_by_constant_modN)
          .def("get_expectation_value", &SimulatorB200::get_expectation_value)
          .def("apply_qubit_operator", &SimulatorB200::apply_qubit_operator)
+         .def("emulate_time_evolution", &SimulatorB200::emulate_time_evolution)
          .def("set_wavefunction", &SimulatorB200::set_wavefunction)
          .def("cheat", &SimulatorB200::cheat)
          .def("get_amplitude", &SimulatorB200::get_amplitude)

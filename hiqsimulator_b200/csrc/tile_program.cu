@@ -34,7 +34,9 @@ namespace hiq {
 constexpr int kTileMaxSteps = HIQK_TILE_MAX_STEPS;
 constexpr int kTileMaxOps = HIQK_TILE_MAX_OPS;  // diagonal ops per gate
 constexpr int kTileLutEntries = 512;            // table pool shared by all ops of a launch (8 KB of shared memory)
-constexpr int kTileCtxWords = 1 + (kTileMaxOps + 3) / 4;
+// per-thread context in shared memory, computed once per launch: the physical tile position of the thread's tuple of
+// every gate (u32) and, per diagonal op, the selector bits its tuple base contributes (u8)
+constexpr int kTileCtxBytes = kTileMaxSteps * (4 + kTileMaxOps);
 
 struct TileStepDesc {
      int ks;                          // mixing bits, 1..4 (4 = full product, three-multiplication form)
@@ -70,40 +72,29 @@ __device__ __forceinline__ uint32_t tile_phys(uint32_t j, const uint32_t (&mask)
      return j ^ ((__popc(j & mask[0]) & 1u) | ((__popc(j & mask[1]) & 1u) << 1) | ((__popc(j & mask[2]) & 1u) << 2));
 }
 
-__device__ __forceinline__ uint32_t ctx_sel(const uint32_t (&w)[kTileCtxWords - 1], int j)
-{
-     // j is uniform across the CTA: a select on registers, no local memory
-     uint32_t v = w[0];
-#pragma unroll
-     for (int i = 1; i < kTileCtxWords - 1; ++i)
-          if ((j >> 2) == i) v = w[i];
-     return (v >> (8 * (j & 3))) & 0xffu;
-}
-
 template <int S, int THREADS>
 __device__ __forceinline__ void tile_step(const TileParams& p, double2* __restrict__ tile, const double2* __restrict__ lut,
-                                          const uint32_t* __restrict__ ctx, const uint32_t (&selh)[kTileMaxSteps][kTileMaxOps])
+                                          const uint32_t* __restrict__ ctx_pb, const uint8_t* __restrict__ ctx_sel,
+                                          const uint32_t (&selh)[kTileMaxSteps][kTileMaxOps])
 {
      const TileStepDesc& d = p.step[S];
      const int tid = threadIdx.x;
-     const uint32_t pb = ctx[(S * kTileCtxWords) * THREADS + tid];
-     uint32_t w[kTileCtxWords - 1];
-#pragma unroll
-     for (int i = 0; i < kTileCtxWords - 1; ++i) w[i] = ctx[(S * kTileCtxWords + 1 + i) * THREADS + tid];
+     const uint32_t pb = ctx_pb[S * THREADS + tid];
+     const uint8_t* my_sel = ctx_sel + (S * kTileMaxOps) * THREADS + tid;  // op j: my_sel[j * THREADS]
      double2 in[16];
 #pragma unroll
      for (int c = 0; c < 16; ++c) in[c] = tile[pb ^ d.ploff[c]];
      if (d.n_ops) {
           const int n_s = d.n_ops - d.n_e;
           double2 sc = make_double2(1.0, 0.0);
-          for (int j = 0; j < n_s; ++j) sc = cmul(sc, lut[d.lut_off[j] + (selh[S][j] | ctx_sel(w, j))]);
+          for (int j = 0; j < n_s; ++j) sc = cmul(sc, lut[d.lut_off[j] + (selh[S][j] | my_sel[j * THREADS])]);
           if (d.n_e == 0) {
 #pragma unroll
                for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], sc);
           }
           else {
                for (int j = n_s; j < d.n_ops; ++j) {
-                    const uint32_t sel0 = selh[S][j] | ctx_sel(w, j);
+                    const uint32_t sel0 = selh[S][j] | my_sel[j * THREADS];
 #pragma unroll
                     for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], lut[d.lut_off[j] + (sel0 | d.esel[j][c])]);
                }
@@ -130,7 +121,8 @@ __global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : 4) tile_program_ke
      extern __shared__ double2 dyn_smem[];
      double2* tile = dyn_smem;                                         // 2^T amplitudes
      double2* lut = dyn_smem + (1 << T);                               // table pool
-     uint32_t* ctx = reinterpret_cast<uint32_t*>(lut + kTileLutEntries);  // [gate][word][thread]
+     uint32_t* ctx_pb = reinterpret_cast<uint32_t*>(lut + kTileLutEntries);   // [gate][thread]
+     uint8_t* ctx_sel = reinterpret_cast<uint8_t*>(ctx_pb + kTileMaxSteps * THREADS);  // [gate][op][thread]
      __shared__ uint32_t selh[kTileMaxSteps][kTileMaxOps];
      const int tid = threadIdx.x;
      for (int i = tid; i < p.n_lut; i += THREADS) lut[i] = p.lut[i];
@@ -149,19 +141,13 @@ __global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : 4) tile_program_ke
                const uint32_t low = base & ((1u << d.tpos[i]) - 1u);
                base = ((base >> d.tpos[i]) << (d.tpos[i] + 1)) | low;
           }
-          ctx[(s * kTileCtxWords) * THREADS + tid] = tile_phys(base, p.swz_mask);
-          for (int wi = 0; wi < kTileCtxWords - 1; ++wi) {
-               uint32_t v = 0;
-               for (int bi = 0; bi < 4; ++bi) {
-                    const int j = 4 * wi + bi;
-                    if (j >= d.n_ops) break;
-                    uint32_t sel = 0;
+          ctx_pb[s * THREADS + tid] = tile_phys(base, p.swz_mask);
+          for (int j = 0; j < d.n_ops; ++j) {
+               uint32_t sel = 0;
 #pragma unroll
-                    for (int l = 0; l < 5; ++l)
-                         if (d.lpos[j][l] != 0xFF) sel |= ((base >> d.lpos[j][l]) & 1u) << l;
-                    v |= sel << (8 * bi);
-               }
-               ctx[(s * kTileCtxWords + 1 + wi) * THREADS + tid] = v;
+               for (int l = 0; l < 5; ++l)
+                    if (d.lpos[j][l] != 0xFF) sel |= ((base >> d.lpos[j][l]) & 1u) << l;
+               ctx_sel[(s * kTileMaxOps + j) * THREADS + tid] = static_cast<uint8_t>(sel);
           }
      }
      __syncthreads();
@@ -181,18 +167,18 @@ __global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : 4) tile_program_ke
           }
           cp_async_wait_all();
           __syncthreads();
-          tile_step<0, THREADS>(p, tile, lut, ctx, selh);
+          tile_step<0, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
           __syncthreads();
           if (p.n_steps > 1) {
-               tile_step<1, THREADS>(p, tile, lut, ctx, selh);
+               tile_step<1, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
                __syncthreads();
           }
           if (p.n_steps > 2) {
-               tile_step<2, THREADS>(p, tile, lut, ctx, selh);
+               tile_step<2, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
                __syncthreads();
           }
           if (p.n_steps > 3) {
-               tile_step<3, THREADS>(p, tile, lut, ctx, selh);
+               tile_step<3, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
                __syncthreads();
           }
 #pragma unroll
@@ -534,7 +520,7 @@ int ring_acquire(LutRing*& ring, int& slot)
 
 size_t tile_smem_bytes(int T)
 {
-     return sizeof(double2) * ((1u << T) + kTileLutEntries) + sizeof(uint32_t) * kTileMaxSteps * kTileCtxWords * (1u << (T - 4));
+     return sizeof(double2) * ((1u << T) + kTileLutEntries) + static_cast<size_t>(kTileCtxBytes) * (1u << (T - 4));
 }
 
 }  // namespace

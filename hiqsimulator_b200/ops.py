@@ -11,7 +11,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 
-GATE, ALLOCATE, ALLOCATE_QUREG, DEALLOCATE, MEASURE, FLUSH, METASWAP, MATH = range(8)
+GATE, ALLOCATE, ALLOCATE_QUREG, DEALLOCATE, MEASURE, FLUSH, METASWAP, MATH, TIME_EVOLUTION = range(9)
 
 
 @dataclass
@@ -24,13 +24,13 @@ class Command:
     init: complex = 0                               # ALLOCATE_QUREG initial amplitude
     is_z: bool = False                              # ZGate (target/control roles may be exchanged)
     quregs: list = field(default_factory=list)      # MATH: one id list per register
-    math: tuple = ()                                # MATH: ("add", a) | ("add_mod", a, N) | ("mul_mod", a, N) | ("fn", callable)
+    math: tuple = ()                                # MATH: ("add", a) | ("add_mod", a, N) | ("mul_mod", a, N) | ("fn", callable); TIME_EVOLUTION: (time, terms)
 
     @property
     def fast_forwarding(self) -> bool:
         """ProjectQ FastForwardingGate family: Measure, Flush, Deallocate, MetaSwap.  Math gates are emulated on
         the whole state (reference call site: _simulator_mpi.py:459-468), so everything pending runs first."""
-        return self.kind in (MEASURE, FLUSH, DEALLOCATE, METASWAP, MATH)
+        return self.kind in (MEASURE, FLUSH, DEALLOCATE, METASWAP, MATH, TIME_EVOLUTION)
 
 
 def Gate(matrix, qubits, controls=(), name="", is_z=False):
@@ -76,6 +76,15 @@ def AddConstantModN(a, N, qureg, controls=()):
 def MultiplyByConstantModN(a, N, qureg, controls=()):
     return Command(MATH, [q for q in qureg], list(controls), name="MultiplyByConstantModN", quregs=[list(qureg)],
                    math=("mul_mod", int(a), int(N)))
+
+
+def TimeEvolution(time, hamiltonian, qureg, controls=()):
+    """ProjectQ's TimeEvolution(time, hamiltonian) | qureg: exp(-i time H), H = list of (term, coefficient) with term =
+    sequence of (index into qureg, 'X'|'Y'|'Z') (a QubitOperator's .terms.items()).  Emulated on the whole state
+    (reference call site: _simulator_mpi.py:469-475)."""
+    terms = hamiltonian.terms.items() if hasattr(hamiltonian, "terms") else hamiltonian
+    return Command(TIME_EVOLUTION, list(qureg), list(controls), name="TimeEvolution",
+                   math=(float(time), [(list(t), c) for t, c in terms]))
 
 
 def BasicMath(fn, quregs, controls=()):

@@ -190,6 +190,10 @@ int hiqk_swap_p2p(void* local, void* const* peer_slabs, int n_peers, int L, int 
 int hiqk_swap_move(void* slab, int L, int q, const int* slots, int n_peers, const uint64_t* peer_pats, uint64_t begin,
                    uint64_t count, void* const* bufs, int pack, void* stream);
 
+/* y[j] += (a_re + i a_im) * x[j] for every j < 2^L with (j & mask) == val; x may alias y.  Taylor accumulation of
+ * emulate_time_evolution. */
+int hiqk_axpy_masked(void* y, const void* x, int L, uint64_t mask, uint64_t val, double a_re, double a_im, void* stream);
+
 /* ---- Pauli-operator passes ------------------------------------------------------------------
  * The reference wrapper calls get_expectation_value / apply_qubit_operator on its C++ simulator
  * (reference: hiq/projectq/backends/_sim/_simulator_mpi.py:180-183, 220-223) although the reference
@@ -328,6 +332,14 @@ int hiq_get_expectation_value(hiq_engine* e, const int* term_offsets, const int*
                               const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids, double* out);
 int hiq_apply_qubit_operator(hiq_engine* e, const int* term_offsets, const int* factor_index, const char* factor_pauli,
                              const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids);
+/* psi <- exp(-i t H) psi on the part of the register whose control qubits are 1, H = the Pauli operator (same encoding as
+ * above, real or complex coefficients).  ProjectQ's algorithm: s = |t| * (sum of |coefficients| of the non-identity terms)
+ * + 1 slices, each a Taylor series summed until the norm of a term drops below 1e-12; the identity terms enter as a phase.
+ * Needs two buffers of the slab's size next to the slab (reference call site: _simulator_mpi.py:469-475; the reference
+ * class exports no such method and its only specification is the commented-out test _simulator_mpi_test.py:481-537). */
+int hiq_emulate_time_evolution(hiq_engine* e, const int* term_offsets, const int* factor_index, const char* factor_pauli,
+                               const double* coefs_re_im, int n_terms, double time, const int64_t* ids, int n_ids,
+                               const int64_t* ctrls, int n_ctrls);
 /* amps: 2^n_ids complex128 on the host (the whole vector on every rank); index bit i <-> ids[i] */
 int hiq_set_wavefunction(hiq_engine* e, const double* amps_re_im, uint64_t n_amps, const int64_t* ids, int n_ids);
 /* emulate_math with the function tabulated over the concatenated registers (reg_ids in bit order, register 0

@@ -23,7 +23,7 @@ def main():
     from hiqsimulator_b200 import world
     flags = M.FLAG_DRY_RUN if mode == "dry" else 0
     rank, size = world.init_world(flags)
-    if name.startswith("ops:"):
+    if name.startswith("ops:") or name.startswith("tevo:"):
         return operator_case(name, mode, M, world, rank, size)
     if name.startswith("shor:"):
         return shor_case(name, mode, M, world, rank, size)
@@ -85,8 +85,8 @@ def shor_case(name, mode, M, world, rank, R):
 
 
 def operator_case(name, mode, M, world, rank, R):
-    _, nq, seed = name.split(":")
-    script = scripts.operator_script(int(nq), R, int(seed))
+    kind, nq, seed = name.split(":")
+    script = (scripts.time_evolution_script if kind == "tevo" else scripts.operator_script)(int(nq), R, int(seed))
     if mode == "dry":
         stop = next(j for j, op in enumerate(script) if op[0] == "measure_qubits")
         script = script[:stop]
@@ -116,7 +116,7 @@ def operator_case(name, mode, M, world, rank, R):
         if rank == 0:
             exp = scripts.run_on_oracle(script, R)
             merged = scripts.merge_rank_outputs([g[0] for g in gathered])
-            scripts.assert_outputs_match(script, merged, exp)
+            scripts.assert_outputs_match(script, merged, exp, tol=1e-11 if kind == "tevo" else 1e-12)
             for g in gathered:
                 assert np.array_equal(g[1], merged[last][1]) and g[2] == merged[last][0]
     world.barrier()

@@ -294,6 +294,30 @@ def operator_script(nq, R, seed, max_cluster=3, ngates=25):
     return script
 
 
+def time_evolution_script(nq, R, seed):
+    """random gates, then controlled and uncontrolled TimeEvolution calls (Hamiltonians with X/Y/Z strings on local and
+    global qubits, identity terms, negative times), each followed by a look at the state"""
+    rng = np.random.default_rng(2000 + seed)
+    script = random_script(nq, R, seed, ngates=20, max_cluster=4, queries=False)
+    o = statevec.SimulatorMPI(*script[0][1:], R)
+    for op in script[1:]:
+        if op[0] not in ("cheat_local", "get_qubits_ids"):
+            getattr(o, op[0])(*op[1:])
+    allq = [q for q in o.get_qubits_ids() if q >= 0]
+    ids = [int(x) for x in rng.permutation(allq)]
+    reg, rest = ids[:-2], ids[-2:]
+    h1 = random_terms(rng, len(reg), 4, True, max_factors=3) + [([], 0.7)]
+    script.append(("emulate_time_evolution", h1, 0.8, reg, [rest[0]]))
+    script.append(("cheat_local",))
+    h2 = random_terms(rng, len(ids), 3, True, max_factors=4)
+    script.append(("emulate_time_evolution", h2, -0.45, ids, []))
+    script.append(("cheat_local",))
+    script.append(("emulate_time_evolution", [([], 1.3)], 0.5, reg, rest))  # a pure phase on the controlled part
+    script.append(("cheat_local",))
+    script.append(("get_probability", [True], [ids[0]]))
+    return script
+
+
 def _dispatch(sim, op):
     if op[0] == "emulate_math_fn":
         return sim.emulate_math(MATH_FUNCS[op[1]], op[2], op[3])

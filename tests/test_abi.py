@@ -68,3 +68,18 @@ def test_dense_block_shape_is_host_only_and_finds_select_bits():
     assert ks == 2 and order == [0, 1]
     ks, order = K.dense_block_shape(cr)  # diagonal: one nominal mixing bit
     assert ks == 1 and sorted(order) == [0, 1]
+
+
+def test_reference_import_paths_resolve():
+    """the two import statements of the reference's Python layer (reference: _simulator_mpi.py:39, cengines/__init__.py:15)
+    resolve to this repository's modules through the hiq/ shim tree"""
+    from hiq.projectq.backends._sim._cppsim_mpi import SimulatorMPI as SimulatorBackend
+    from hiq.projectq.cengines._sched_cpp import ClusterScheduler, SwapScheduler
+    from hiqsimulator_b200 import _cppsim_mpi, _sched_cpp
+    assert SimulatorBackend is _cppsim_mpi.SimulatorMPI
+    assert SwapScheduler is _sched_cpp.SwapScheduler and ClusterScheduler is _sched_cpp.ClusterScheduler
+    for name in ("get_qubits_ids", "get_local_qubits_ids", "get_global_qubits_ids", "set_qubits_perm", "swap_qubits", "allocate_qureg",
+                 "allocate_qubit", "deallocate_qubit", "measure_qubits", "apply_controlled_gate", "emulate_math", "get_amplitude",
+                 "get_probability", "run", "entropy", "cheat_local", "collapse_wavefunction",   # reference: _cppsim_mpi.cpp:63-82
+                 "get_expectation_value", "apply_qubit_operator", "set_wavefunction", "emulate_time_evolution", "cheat"):
+        assert hasattr(SimulatorBackend, name), name

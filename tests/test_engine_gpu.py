@@ -375,7 +375,19 @@ def test_engine_operator_calls_match_oracle(nq, seed):
     assert dict(d) == exp[last][0] and np.array_equal(np.asarray(full), got[last][1])
 
 
-@pytest.mark.parametrize("name,R", [("ops:9:41", 2), ("ops:10:42", 4), ("ops:11:43", 8), ("ops:10:44", 2)])
+@pytest.mark.parametrize("nq,seed", [(8, 51), (11, 52), (13, 53)])
+def test_engine_time_evolution_matches_oracle(nq, seed):
+    """emulate_time_evolution (ProjectQ's sliced Taylor series on the device: Pauli-apply, masked norm, masked axpy
+    kernels) == the numpy restatement of the same algorithm, itself pinned to scipy's expm (tests/test_operators_cpu.py);
+    the reference class has no implementation: parity unpinned"""
+    M = _M()
+    script = scripts.time_evolution_script(nq, 1, seed)
+    exp = scripts.run_on_oracle(script, 1)
+    got = scripts.run_on_sim(M.SimulatorMPI, script)
+    scripts.assert_outputs_match(script, got, exp, tol=1e-11)
+
+
+@pytest.mark.parametrize("name,R", [("ops:9:41", 2), ("ops:10:42", 4), ("ops:11:43", 8), ("ops:10:44", 2), ("tevo:10:45", 2), ("tevo:11:46", 4)])
 def test_engine_operator_calls_multi_gpu(name, R):
     if _gpu_count() < R:
         pytest.skip("needs %d GPUs" % R)

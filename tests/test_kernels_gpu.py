@@ -268,7 +268,8 @@ TILE_RUNS = [
     (14, [(3, (0, 1, 2), (1, 2), 6), (4, (1, 2, 3, 4), None, 2)], 11),                                                  # slot-0 targets
     (15, [(4, (0, 5, 9, 13), None, 1), (4, (2, 6, 9, 12), None, 2)], 11),                                               # two full products
     (17, [(2, (3, 16), None, 1), (1, (14,), None, 0), (3, (15, 0, 7), (1,), 4), (4, (12, 13, 14, 15), (0,), 7)], 11),
-    (16, [(4, (0, 1, 14, 15), None, 12), (4, (2, 3, 12, 13), None, 9)], 12),
+    (16, [(4, (0, 1, 14, 15), None, 12), (4, (2, 3, 12, 13), None, 9)], 11),
+    (18, [(4, (10, 11, 16, 17), None, 16), (4, (12, 13, 14, 15), (1, 2), 16)], 12),
 ]
 
 

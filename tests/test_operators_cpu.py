@@ -105,6 +105,54 @@ def test_ref_set_wavefunction():  # :546-560
     assert o.get_probability([True], [1]) == pytest.approx(1.0)
 
 
+@pytest.mark.parametrize("R", [1, 2, 4])
+def test_ref_time_evolution(R):  # _simulator_mpi_test.py:481-537 (commented out in the reference: parity unpinned)
+    """the reference's own specification of TimeEvolution: a controlled exp(-i t H) compared with scipy's expm"""
+    import scipy.sparse
+    import scipy.sparse.linalg
+    rng = np.random.default_rng(7)
+    N = 8
+    t = 1.1
+    o = _oracle(N + 1, R, max_cluster=4)
+    loc = o.get_local_qubits_ids()
+    ctrl = loc[-1]
+    qureg = [q for q in range(N + 1) if q != ctrl]  # with R > 1 some of them are global (left in |0>: no swaps here)
+    Rx = lambda a: np.array([[math.cos(a / 2), -1j * math.sin(a / 2)], [-1j * math.sin(a / 2), math.cos(a / 2)]])  # noqa: E731
+    Ry = lambda a: np.array([[math.cos(a / 2), -math.sin(a / 2)], [math.sin(a / 2), math.cos(a / 2)]], dtype=complex)  # noqa: E731
+    for q in qureg:
+        if q in loc:
+            _g(o, Rx(rng.random()), q)
+            _g(o, Ry(rng.random()), q)
+    pos0, init = o.cheat()
+    init = init.copy()
+    op = [([(0, "X"), (1, "Y"), (2, "Z"), (3, "Y"), (4, "X")], 0.3), ([], 1.1),
+          ([(0, "Y"), (1, "Z"), (3, "X"), (5, "Y")], -1.4), ([(1, "Y"), (2, "X"), (3, "X"), (4, "Y")], -1.1)]
+    _g(o, H, ctrl)
+    o.emulate_time_evolution(op, t, qureg, [ctrl])
+    pos, final = o.cheat()
+    nb = N + 1
+    sp = {"X": scipy.sparse.csr_matrix(X), "Y": scipy.sparse.csr_matrix(Y), "Z": scipy.sparse.csr_matrix(Z)}
+    ident = scipy.sparse.identity(2, format="csr", dtype=complex)
+    mat = 0
+    for term, c in op:
+        fac = [ident] * nb
+        for idx, g in term:
+            fac[pos[qureg[idx]]] = sp[g]
+        fac.reverse()
+        m = fac[0]
+        for f in fac[1:]:
+            m = scipy.sparse.kron(m, f)
+        mat = mat + m * c
+    full = scipy.sparse.linalg.expm_multiply(-1j * t * mat, init)
+    idx = np.arange(1 << nb)
+    on = ((idx >> pos[ctrl]) & 1) == 1
+    hf = 1 / math.sqrt(2)
+    # the controlled half evolved, the other half untouched (the H on the control splits the state)
+    partner = idx ^ (1 << pos[ctrl])
+    assert np.allclose(final[on], hf * full[partner[on]], atol=1e-10)
+    assert np.allclose(final[~on], hf * init[~on], atol=1e-12)
+
+
 @pytest.mark.parametrize("R", [1, 2])
 def test_ref_emulation_plus2(R):  # :223-244
     nq = 3 if R == 1 else 4

@@ -47,20 +47,23 @@ def main():
         print(json.dumps(r), flush=True)
         out.write(json.dumps(r) + "\n")
 
-    def qft_ops(tg, n):
-        hi = [s for s in range(12, L) if s not in tg]
-        return [([tg[2], tg[3], 3, 15], diag(4))] + [([int(x) for x in rng.choice(hi, size=4, replace=False)], diag(4)) for _ in range(n - 1)]
+    def qft_ops(tg, n, avoid=()):
+        """one op on two of the gate's targets (class E), the others away from every target of the run (per-tuple scalars)"""
+        free = [s for s in range(L) if s not in tg and s not in avoid]
+        return [([tg[2], tg[3], free[0], free[-1]], diag(4))] + [([int(x) for x in rng.choice(free, size=4, replace=False)], diag(4)) for _ in range(n - 1)]
 
     m2 = blocks(2)
     chain = []
+    run_slots = list(range(L - 10, L))
     for i in range(4):
         tg = [L - 4 - 2 * i, L - 3 - 2 * i, L - 2 - 2 * i, L - 1 - 2 * i]
-        chain.append((tg, m2, qft_ops(tg, 8)))
+        chain.append((tg, m2, qft_ops(tg, 8, run_slots)))
     for n in (1, 2, 3):
         rec("tile_qft_chain_%d" % n, lambda: K.apply_tile_program(state, chain[:n]), n, ops_per_gate=8)
     rec("one_launch_per_gate_qft_chain_3", lambda: [K.apply_dense_prediag(state, tg, m, ops) for tg, m, ops in chain[:3]], 3, ops_per_gate=8)
-    low_chain = [([7, 8, 9, 10], m2, qft_ops([7, 8, 9, 10], 4)), ([5, 6, 7, 8], m2, qft_ops([5, 6, 7, 8], 3)),
-                 ([3, 4, 5, 6], m2, qft_ops([3, 4, 5, 6], 2)), ([1, 2, 3, 4], m2, qft_ops([1, 2, 3, 4], 2))]
+    low = list(range(0, 11))
+    low_chain = [([7, 8, 9, 10], m2, qft_ops([7, 8, 9, 10], 4, low)), ([5, 6, 7, 8], m2, qft_ops([5, 6, 7, 8], 3, low)),
+                 ([3, 4, 5, 6], m2, qft_ops([3, 4, 5, 6], 2, low)), ([1, 2, 3, 4], m2, qft_ops([1, 2, 3, 4], 2, low))]
     rec("tile_qft_low_chain_4", lambda: K.apply_tile_program(state, low_chain), 4)
     noop_chain = [(tg, m, []) for tg, m, _ in chain]
     for n in (1, 2, 3):
