@@ -83,6 +83,13 @@ int Comm::allreduce_sum(double* vals, int n, cudaStream_t stream)
      return HIQ_OK;
 }
 
+int Comm::allreduce_sum_device(double* dev, int n, cudaStream_t stream)
+{
+     if (size_ == 1) return HIQ_OK;
+     HIQ_NCCL(nccl().AllReduce(dev, dev, n, ncclDouble, ncclSum, comm_, stream));
+     return HIQ_OK;
+}
+
 int Comm::broadcast_bytes(void* host, size_t bytes, int root, cudaStream_t stream)
 {
      if (size_ == 1) return HIQ_OK;

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "peer_ipc.hpp"
+#include "slab.hpp"
 
 namespace hiq {
 
@@ -43,18 +44,25 @@ public:
      // Staging of the packed exchange (engine.cpp, Engine::exchange_packed): one buffer per process, opened by the peers
      // through CUDA IPC.  Process-wide like the communicator: an engine per circuit must not pay cudaMalloc + handle
      // exchange + cudaIpcOpenMemHandle again.
+     // A peer process's view of one of my buffers (or mine of its): chunks received and mapped so far, chunks sent so far.
+     struct PeerView {
+          PeerSlab slab;
+          size_t sent = 0;
+     };
      struct PackedStaging {
-          double2* mine = nullptr;
-          size_t bytes = 0;
+          Slab mine;                    // virtual-memory allocation, exported to the peers chunk by chunk (file descriptors)
           size_t wanted = 0;            // the request that produced this buffer (it may have been halved to fit)
-          std::vector<double2*> peers;  // by world rank
+          std::vector<PeerView> peers;  // by world rank: the peers' staging buffers mapped into this process
           bool failed = false;
+          size_t bytes() const { return mine.mapped_amps() * sizeof(double2); }
      };
      PackedStaging& packed() { return packed_; }
 
      // host-value collectives (values staged through a small device buffer on `stream`)
      int allreduce_sum(double* vals, int n, cudaStream_t stream);
      int broadcast_bytes(void* host, size_t bytes, int root, cudaStream_t stream);
+     // in-place sum of n doubles that already live in device memory (no host bounce, no synchronisation)
+     int allreduce_sum_device(double* dev, int n, cudaStream_t stream);
      // device collective: every rank contributes n doubles, recv holds size()*n (rank-major)
      int allgather(const double* dev_send, double* dev_recv, size_t n, cudaStream_t stream);
 

@@ -80,7 +80,6 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
           }
           if (const char* m = std::getenv("HIQ_SWAP_PACKED")) packed_enabled_ = m[0] == '1';
           if (const char* m = std::getenv("HIQ_SWAP_PACKED_BELOW")) packed_below_slot_ = std::atoi(m);
-          if (const char* m = std::getenv("HIQ_SWAP_PACKED_PULL")) packed_push_ = m[0] != '1';
           if (const char* m = std::getenv("HIQ_SWAP_PACKED_PIECE")) packed_piece_cap_ = std::strtoull(m, nullptr, 10);
           if (const char* m = std::getenv("HIQ_SWAP_P2P_MIN_SLOT")) min_p2p_slot_ = std::atoi(m);
      }
@@ -113,6 +112,7 @@ Engine::~Engine()
           if (d_blocks_) cudaFree(d_blocks_);
           if (swap_buf_) cudaFree(swap_buf_);
           slab_.release();
+          scratch_.release();
           for (auto& t: timed_) {
                cudaEventDestroy(t.start);
                cudaEventDestroy(t.stop);
@@ -171,6 +171,10 @@ void Engine::allocate_local(Index id)
      }
      if (dry_run_) return;
      const auto t_grow = Clock::now();
+     if (slab_.ensure(2 * old) != HIQ_OK && scratch_.data()) {
+          scratch_.release();  // the second buffer of the out-of-place passes gives its memory back to the register
+          cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
+     }
      cu(slab_.ensure(2 * old));
      stats_.slab_grow_s += seconds_since(t_grow);
      cu(check_cuda(cudaMemsetAsync(slab_.data() + old, 0, old * sizeof(double2), stream_), "cudaMemsetAsync"));
@@ -695,13 +699,15 @@ void Engine::masks(const std::vector<Index>& ids, const std::vector<bool>& bits,
 double Engine::probability_internal(uint64_t lm, uint64_t lv, uint64_t gm, uint64_t gv)
 {
      // reference: SimulatorMPI.cpp:841-870
+     // the local sum stays on the device: kernel -> ncclAllReduce in place -> ONE copy to the host and one synchronisation
      double p = 0.0;
      flush_pending();
-     if ((static_cast<uint64_t>(rank_) & gm) == gv) {
+     if ((static_cast<uint64_t>(rank_) & gm) == gv)
           cu(hiqk_prob_masked(slab_.data(), static_cast<int>(locals_.size()), lm, lv, d_vals_, workspace_, stream_));
-          d2h(&p, d_vals_, sizeof(double));
-     }
-     cu(comm_p_->allreduce_sum(&p, 1, stream_));
+     else
+          cu(check_cuda(cudaMemsetAsync(d_vals_, 0, sizeof(double), stream_), "cudaMemsetAsync"));
+     cu(comm_p_->allreduce_sum_device(d_vals_, 1, stream_));
+     d2h(&p, d_vals_, sizeof(double));
      return p;
 }
 
@@ -779,6 +785,7 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
      cu(comm_p_->allgather(d_blocks_ + n * rank_, d_blocks_, n, stream_));
      std::vector<double> tot(n * world_);
      d2h(tot.data(), d_blocks_, sizeof(double) * tot.size());
+     const std::vector<double> raw = tot;  // the block sums themselves (the outcome's probability may follow from them)
      // per-rank inclusive prefix, then the running shift over ranks — same order as the reference
      double shift = 0.0;
      for (int r = 0; r < world_; ++r) {
@@ -800,6 +807,7 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
      }
      const uint64_t block_size = size / n;
      uint64_t k = 0;
+     double amp2 = 0.0;  // |amplitude|^2 of the sampled basis state (owner rank)
      if (rank_ == static_cast<int>(src_rank)) {
           double acc = i > 0 ? tot[i - 1] : 0.0;
           std::vector<cplx> blk(block_size);
@@ -809,9 +817,15 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
                acc += std::norm(blk[j]);
                if (acc >= rnd) break;
           }
+          // the scan of the reference may run to the end of the block (k one past it) when rounding leaves acc < rnd
+          amp2 = k < (src_index + 1) * block_size ? std::norm(blk[k - src_index * block_size]) : 0.0;
      }
-     uint64_t res_index = (src_rank << L) + k;
-     cu(comm_p_->broadcast_bytes(&res_index, sizeof(res_index), static_cast<int>(src_rank), stream_));
+     struct {
+          uint64_t index;
+          double amp2;
+     } msg = {(src_rank << L) + k, amp2};
+     cu(comm_p_->broadcast_bytes(&msg, sizeof(msg), static_cast<int>(src_rank), stream_));
+     const uint64_t res_index = msg.index;
 
      std::vector<bool> res(ids.size());
      uint64_t lm = 0, lv = 0, gm = 0, gv = 0;
@@ -833,7 +847,27 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
                }
           }
      }
-     const double norm = probability_internal(lm, lv, gm, gv);
+     // Probability of the outcome (reference: a second sweep, getProbability_internal, SimulatorMPI.cpp:996-997).  Two
+     // cases need no sweep: every measured local slot lies above the block granularity, so the outcome is a union of
+     // whole blocks and its probability the sum of their block sums; or every qubit was measured, and it is the squared
+     // modulus of the sampled amplitude.  Otherwise the masked reduction runs.
+     double norm;
+     const int block_bits = L - static_cast<int>(__builtin_ctzll(n));  // log2(block size)
+     uint64_t all_globals = 0;
+     for (size_t pos = 0; pos < globals_.size(); ++pos)
+          if (globals_[pos] != kNone) all_globals |= 1ull << pos;
+     if ((lm & ((1ull << block_bits) - 1ull)) == 0) {
+          norm = 0.0;
+          const uint64_t bm = lm >> block_bits, bv = lv >> block_bits;
+          for (int r = 0; r < world_; ++r) {
+               if ((static_cast<uint64_t>(r) & gm) != gv) continue;
+               const double* blk = raw.data() + n * r;
+               for (uint64_t b = 0; b < n; ++b)
+                    if ((b & bm) == bv) norm += blk[b];
+          }
+     }
+     else if (lm == size - 1 && gm == all_globals && msg.amp2 > 0.0) norm = msg.amp2;
+     else norm = probability_internal(lm, lv, gm, gv);
      normalize(norm, lm, lv, gm, gv);
      stats_.measures_s += seconds_since(t0);
      return res;
@@ -992,29 +1026,30 @@ void Engine::group_barrier(const std::vector<int>& peer_ranks)
      if (r != ncclSuccess) throw EngineError(HIQ_ERR_CUDA, std::string("ncclGroupEnd: ") + nccl().GetErrorString(r));
 }
 
-bool Engine::map_peers(const std::vector<int>& peer_ranks)
+bool Engine::map_peer_chunks(const Slab& mine, std::vector<PeerView>& views, uint64_t tag, const std::vector<int>& peer_ranks)
 {
-     // Handshake: send every group peer the chunks of my slab it has not seen yet, and map the chunks the
-     // peers send me.  Slabs grow in lock-step on all ranks (allocation is collective), so a peer's view is
-     // complete when it has as many chunks as my own slab.
+     // Handshake: send every listed peer the chunks of `mine` it has not seen yet, and map the chunks the peers send
+     // me.  Buffers grow in lock-step on all ranks (allocation is collective), so a peer's view is complete when it
+     // has as many chunks as my own buffer.  `tag` names the buffer generation (engine epoch for slabs, 0 for the
+     // process-wide staging buffer); messages with another tag belong to a buffer that no longer exists and are dropped.
      FdChannel& ch = comm_p_->fds();
      if (!ch.is_open()) {
           set_error(HIQ_ERR_RUNTIME, "descriptor channel is not open");
           return false;
      }
-     if (peer_views_.empty()) peer_views_.resize(world_);
+     if (views.empty()) views.resize(world_);
      struct Out {
           int rank;
           size_t index;
      };
      std::vector<Out> outbox;
      for (int pr: peer_ranks) {
-          PeerView& v = peer_views_[pr];
-          for (size_t i = v.sent; i < slab_.n_chunks(); ++i) outbox.push_back({pr, i});
+          PeerView& v = views[pr];
+          for (size_t i = v.sent; i < mine.n_chunks(); ++i) outbox.push_back({pr, i});
      }
      auto complete = [&] {
           for (int pr: peer_ranks)
-               if (peer_views_[pr].slab.n_chunks() < slab_.n_chunks()) return false;
+               if (views[pr].slab.n_chunks() < mine.n_chunks()) return false;
           return true;
      };
      auto receive_one = [&](int timeout_ms) -> bool {
@@ -1025,13 +1060,13 @@ bool Engine::map_peers(const std::vector<int>& peer_ranks)
                set_error(HIQ_ERR_RUNTIME, "peer ipc: message from an unknown rank");
                return false;
           }
-          PeerView& v = peer_views_[m.src_rank];
-          if (m.epoch != epoch_) {  // a message of another engine generation: not for this slab
+          PeerView& v = views[m.src_rank];
+          if (m.epoch != tag) {  // a message of another buffer generation: not for this handshake
                ::close(m.fd);
                return true;
           }
           if (!v.slab.data()) {
-               if (v.slab.init(device_, slab_.reserved_bytes()) != HIQ_OK) {
+               if (v.slab.init(device_, mine.reserved_bytes()) != HIQ_OK) {
                     ::close(m.fd);
                     return false;
                }
@@ -1055,14 +1090,14 @@ bool Engine::map_peers(const std::vector<int>& peer_ranks)
                const Out& o = outbox[next];
                FdMessage m;
                m.index = static_cast<uint32_t>(o.index);
-               m.total = static_cast<uint32_t>(slab_.n_chunks());
-               m.size = slab_.chunk_bytes(o.index);
-               m.epoch = epoch_;
-               if (slab_.export_chunk(o.index, &m.fd) != HIQ_OK) return false;
+               m.total = static_cast<uint32_t>(mine.n_chunks());
+               m.size = mine.chunk_bytes(o.index);
+               m.epoch = tag;
+               if (mine.export_chunk(o.index, &m.fd) != HIQ_OK) return false;
                const int rc = ch.send_fd(o.rank, m, 0 /* do not wait: drain my own queue instead */);
                ::close(m.fd);
                if (rc == HIQ_OK) {
-                    peer_views_[o.rank].sent = o.index + 1;
+                    views[o.rank].sent = o.index + 1;
                     ++next;
                     continue;
                }
@@ -1089,7 +1124,7 @@ bool Engine::ensure_peer_views(const std::vector<int>& peer_ranks)
           if (!stale && (peer_views_[pr].sent < slab_.n_chunks() || peer_views_[pr].slab.n_chunks() < slab_.n_chunks())) stale = true;
      if (stale) {
           const auto t_map = Clock::now();
-          double failed = map_peers(peer_ranks) ? 0.0 : 1.0;
+          double failed = map_peer_chunks(slab_, peer_views_, epoch_, peer_ranks) ? 0.0 : 1.0;
           stats_.peer_map_s += seconds_since(t_map);
           const std::string why = failed != 0.0 ? hiq_last_error() : "";
           cu(comm_p_->allreduce_sum(&failed, 1, stream_));
@@ -1153,100 +1188,67 @@ bool Engine::exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& 
 
 bool Engine::ensure_packed_staging(size_t want_bytes, size_t min_bytes)
 {
-     // Collective over the world (every rank takes part in every swap, with the same arguments): allocate my staging
-     // buffer, publish its CUDA IPC handle with one all-gather, open the peers' buffers.  The outcome — including the
-     // size, halved until every rank could allocate it — is agreed on by all ranks.  The buffers belong to the process
-     // (Comm::packed()), so the engines a caller creates one after the other share them.
+     // Collective over the world (every rank takes part in every swap, with the same arguments).  The staging buffer is a
+     // virtual-memory allocation like the slab, shared the same way: its chunks travel to the peers as file descriptors
+     // and are mapped there with access for the peer's GPU only.  (CUDA runtime IPC handles were measured to slow every
+     // later cuMemMap / cuMemSetAccess of the process by 15-30x once peer access had been enabled through them.)
+     // The buffer belongs to the process (Comm::packed()): the engines a caller creates one after the other share it.
      Comm::PackedStaging& S = comm_p_->packed();
      if (S.failed) {
           set_error(HIQ_ERR_RUNTIME, "the packed exchange could not be set up in this process group");
           return false;
      }
-     if (S.mine && want_bytes <= S.wanted && S.bytes >= min_bytes) return true;
-     cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
-     cu(check_cuda(cudaStreamSynchronize(comm_stream_), "cudaStreamSynchronize"));
-     for (double2*& p: S.peers)
-          if (p) {
-               cudaIpcCloseMemHandle(p);
-               p = nullptr;
+     std::vector<int> others;
+     for (int r = 0; r < world_; ++r)
+          if (r != rank_) others.push_back(r);
+     auto views_complete = [&] {
+          if (S.peers.empty()) return false;
+          for (int r: others)
+               if (S.peers[r].sent < S.mine.n_chunks() || S.peers[r].slab.n_chunks() < S.mine.n_chunks()) return false;
+          return true;
+     };
+     if (S.mine.data() && want_bytes <= S.wanted && S.bytes() >= min_bytes && views_complete()) return true;
+     if (!S.mine.data()) {
+          if (S.mine.init(device_, (16ull << 30) / sizeof(double2), true) != HIQ_OK) {
+               S.failed = true;
+               return false;
           }
-     if (S.mine) {
-          cudaFree(S.mine);
-          S.mine = nullptr;
-          S.bytes = 0;
      }
-     S.peers.assign(world_, nullptr);
-     std::string why;
-     size_t bytes = want_bytes;
+     // grow to the wanted size, halving the request until every rank could map it
+     size_t bytes = std::max(want_bytes, S.bytes());
      for (;;) {
-          double failed = 0.0;
-          if (cudaMalloc(&S.mine, bytes) != cudaSuccess) {
-               cudaGetLastError();
-               S.mine = nullptr;
-               failed = 1.0;
-          }
+          double failed = S.mine.ensure(bytes / sizeof(double2)) == HIQ_OK ? 0.0 : 1.0;
           cu(comm_p_->allreduce_sum(&failed, 1, stream_));
           if (failed == 0.0) break;
-          if (S.mine) {
-               cudaFree(S.mine);
-               S.mine = nullptr;
-          }
           bytes /= 2;
-          if (bytes < min_bytes) {
+          if (bytes < min_bytes || bytes <= S.bytes()) {
+               if (S.bytes() >= min_bytes) break;  // what is mapped already will do (more pieces)
                S.failed = true;
                set_error(HIQ_ERR_RUNTIME, "no device memory for the staging buffer of the packed exchange");
                return false;
           }
      }
-     double failed = 0.0;
-     cudaIpcMemHandle_t mine;
-     std::memset(&mine, 0, sizeof(mine));
-     if (cudaIpcGetMemHandle(&mine, S.mine) != cudaSuccess) {
-          failed = 1.0;
-          why = std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(cudaGetLastError());
-     }
-     static_assert(sizeof(cudaIpcMemHandle_t) % sizeof(double) == 0, "handle travels as doubles");
-     constexpr size_t HD = sizeof(cudaIpcMemHandle_t) / sizeof(double);
-     double* d_handles = nullptr;
-     std::vector<cudaIpcMemHandle_t> all(world_);
-     cu(check_cuda(cudaMalloc(&d_handles, world_ * sizeof(cudaIpcMemHandle_t)), "cudaMalloc handles"));
-     cu(check_cuda(cudaMemcpyAsync(d_handles + HD * rank_, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream_), "cudaMemcpyAsync"));
-     cu(comm_p_->allgather(d_handles + HD * rank_, d_handles, HD, stream_));
-     cu(check_cuda(cudaMemcpyAsync(all.data(), d_handles, world_ * sizeof(cudaIpcMemHandle_t), cudaMemcpyDeviceToHost, stream_),
-                   "cudaMemcpyAsync"));
-     cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
-     cudaFree(d_handles);
-     cu(comm_p_->allreduce_sum(&failed, 1, stream_));  // somebody has no handle: nobody opens anything
-     if (failed == 0.0) {
-          for (int r = 0; r < world_ && failed == 0.0; ++r) {
-               if (r == rank_) continue;
-               void* p = nullptr;
-               if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                    failed = 1.0;
-                    why = std::string("cudaIpcOpenMemHandle: ") + cudaGetErrorString(cudaGetLastError());
-               }
-               S.peers[r] = static_cast<double2*>(p);
-          }
-          cu(comm_p_->allreduce_sum(&failed, 1, stream_));
-     }
+     double failed = map_peer_chunks(S.mine, S.peers, 0 /* tag of the staging buffer */, others) ? 0.0 : 1.0;
+     const std::string why = failed != 0.0 ? hiq_last_error() : "";
+     cu(comm_p_->allreduce_sum(&failed, 1, stream_));
      if (failed != 0.0) {
           S.failed = true;
-          set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not set up the packed exchange" : why);
+          set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not map the staging buffers" : why);
           return false;
      }
-     S.bytes = bytes;
-     S.wanted = want_bytes;
+     S.wanted = std::max(S.wanted, want_bytes);
      return true;
 }
 
 bool Engine::exchange_packed(const std::vector<int>& gpos, const std::vector<int>& slots)
 {
      // Same transposition as exchange_staged(), but the wire carries contiguous full-line traffic whatever the swapped
-     // slots are (the in-place kernel makes 16-64 B runs when a slot is below 3, and NVLink moves 32 B sectors).
-     //   push (default)  piece i is gathered from my slab straight into the PEERS' staging buffers (posted NVLink
-     //                   writes), a stream-ordered barrier tells the group the pieces have landed, and every rank
-     //                   scatters its own staging buffer into its slab (local, HBM speed)
-     //   pull            piece i is gathered into MY staging buffer (local), barrier, the peers scatter from it (NVLink reads)
+     // slots are (the in-place kernel makes 16-64 B runs when a slot is below 3, and NVLink moves 32 B sectors): piece i
+     // is gathered from my slab straight into the PEERS' staging buffers (posted NVLink writes), a stream-ordered barrier
+     // tells the group the pieces have landed, and every rank scatters its own staging buffer into its slab (local, HBM
+     // speed).  Measured on 2 B200 at L = 32 (profiles/r02c_swap_n2_*.jsonl): 601 GB/s per direction for a swapped slot 1
+     // or 2 and 500 for slot 0, against 387-504 and 316 for the in-place kernel; pulling the pieces with NVLink reads
+     // instead was slower (495-545) and is not kept.
      // Pipeline over two streams: the gathers and the barriers run on the engine stream, the scatters on the second one,
      // so the scatter of piece i overlaps the gather of piece i + 1.  Two staging buffers; barrier i also certifies
      // that everybody has scattered piece i - 1, which is what frees the buffer piece i + 1 goes into.
@@ -1267,7 +1269,7 @@ bool Engine::exchange_packed(const std::vector<int>& gpos, const std::vector<int
      if (!ensure_packed_staging(std::min(full, kStagingMax), floor_bytes)) return false;
      Comm::PackedStaging& S = comm_p_->packed();
      uint64_t piece = chunk;
-     while (2ull * n_peers * piece * sizeof(double2) > S.bytes) piece >>= 1;
+     while (2ull * n_peers * piece * sizeof(double2) > S.bytes()) piece >>= 1;
      while (packed_piece_cap_ && piece > packed_piece_cap_ && piece > 1) piece >>= 1;
      std::vector<int> peer_ranks;
      std::vector<uint64_t> pats;
@@ -1298,17 +1300,15 @@ bool Engine::exchange_packed(const std::vector<int>& gpos, const std::vector<int
           const int b = static_cast<int>(i % 2);
           for (int k = 0; k < n_peers; ++k) {
                const size_t off = (static_cast<size_t>(b) * n_peers + k) * piece;
-               mine[k] = S.mine + off;
-               theirs[k] = S.peers[peer_ranks[k]] + off;
+               mine[k] = S.mine.data() + off;
+               theirs[k] = S.peers[peer_ranks[k]].slab.data() + off;
           }
-          cu(hiqk_swap_move(slab_.data(), L, q, slots.data(), n_peers, pats.data(), i * piece, piece,
-                            packed_push_ ? theirs.data() : mine.data(), 1, stream_));
+          cu(hiqk_swap_move(slab_.data(), L, q, slots.data(), n_peers, pats.data(), i * piece, piece, theirs.data(), 1, stream_));
           if (i >= 1) cu(check_cuda(cudaStreamWaitEvent(stream_, scattered[(i - 1) % 2], 0), "cudaStreamWaitEvent"));
           group_barrier(peer_ranks);
           cu(check_cuda(cudaEventRecord(gathered[b], stream_), "cudaEventRecord"));
           cu(check_cuda(cudaStreamWaitEvent(comm_stream_, gathered[b], 0), "cudaStreamWaitEvent"));
-          cu(hiqk_swap_move(slab_.data(), L, q, slots.data(), n_peers, pats.data(), i * piece, piece,
-                            packed_push_ ? mine.data() : theirs.data(), 0, comm_stream_));
+          cu(hiqk_swap_move(slab_.data(), L, q, slots.data(), n_peers, pats.data(), i * piece, piece, mine.data(), 0, comm_stream_));
           cu(check_cuda(cudaEventRecord(scattered[b], comm_stream_), "cudaEventRecord"));
      }
      // the slab is complete, and nobody starts the next exchange (or frees anything) while a peer still reads a buffer

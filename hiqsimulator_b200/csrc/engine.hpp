@@ -118,6 +118,7 @@ public:
      void gather_state_to_host(void* dst, uint64_t cap_amps);
 
 private:
+     using PeerView = Comm::PeerView;
      static constexpr Index kNone = -1;  // empty global slot (reference: kNotFound_ stored in an int64)
      using Clock = std::chrono::steady_clock;
 
@@ -136,7 +137,8 @@ private:
      void exchange(const std::vector<int>& gpos, const std::vector<int>& slots);
      void exchange_staged(const std::vector<int>& gpos, const std::vector<int>& slots);  // pack -> NCCL send/recv -> unpack
      bool exchange_p2p(const std::vector<int>& gpos, const std::vector<int>& slots);     // in place over peer-mapped slabs
-     bool map_peers(const std::vector<int>& peer_ranks);
+     // handshake over the descriptor channel: send the peers the chunks of `mine` they have not seen, map theirs
+     bool map_peer_chunks(const Slab& mine, std::vector<PeerView>& views, uint64_t tag, const std::vector<int>& peer_ranks);
      bool ensure_peer_views(const std::vector<int>& peer_ranks);  // world-agreed: all ranks succeed or all fail
      struct PauliGroup {
           uint64_t lx = 0;  // flip mask over local slots
@@ -167,6 +169,10 @@ private:
      std::function<double()> rng_;
 
      Slab slab_;
+     // Second buffer of the out-of-place passes (register permutations, operator accumulation): same reservation as the
+     // slab, mapped on first use and kept for the engine's lifetime — Shor's algorithm calls emulate_math 2n times.
+     Slab scratch_;
+     double2* scratch_buffer(uint64_t amps, const char* who);
      Comm* comm_p_ = nullptr;  // process-wide communicator (Comm::shared), not owned
      cudaStream_t stream_ = nullptr;
      cudaStream_t comm_stream_ = nullptr;
@@ -177,19 +183,15 @@ private:
      size_t swap_buf_bytes_ = 0;
      cudaEvent_t swap_events_[4] = {nullptr, nullptr, nullptr, nullptr};  // packed[2], exchanged[2]
      // peer-mapped slabs (NVLink P2P): views of the other ranks' slabs and how many of my chunks each has been sent
-     struct PeerView {
-          PeerSlab slab;
-          size_t sent = 0;
-     };
+
      std::vector<PeerView> peer_views_;
      uint64_t epoch_ = 0;
      int swap_mode_ = 0;        // 0 auto, 1 staged NCCL only, 2 peer-mapped only, 3 packed peer-read only
      // packed peer-read exchange (low swapped slots): pack into a staging buffer that the group peers have opened
      // through CUDA IPC, barrier, unpack straight from the PEER's staging buffer (contiguous NVLink loads)
-     bool packed_enabled_ = false;      // HIQ_SWAP_PACKED=1
+     bool packed_enabled_ = true;       // HIQ_SWAP_PACKED=0: low swapped slots take the in-place kernel too (A/B measurements)
      int packed_below_slot_ = 3;        // auto mode: used when the lowest swapped slot is below this
      uint64_t packed_piece_cap_ = 0;    // HIQ_SWAP_PACKED_PIECE: largest piece in amplitudes (tests drive the multi-piece pipeline with it)
-     bool packed_push_ = true;          // pieces are written into the peers' staging (HIQ_SWAP_PACKED_PULL=1: peers read mine)
      bool ensure_packed_staging(size_t want_bytes, size_t min_bytes);  // process-wide buffers live in Comm::packed()
      bool exchange_packed(const std::vector<int>& gpos, const std::vector<int>& slots);
      bool p2p_broken_ = false;  // the handshake failed once: stay on the staged path

@@ -38,6 +38,14 @@ struct DeviceBuffer {
 };
 }  // namespace
 
+double2* Engine::scratch_buffer(uint64_t amps, const char* who)
+{
+     if (!scratch_.data()) cu(scratch_.init(device_, 1ull << max_local_, false));
+     if (scratch_.ensure(amps) != HIQ_OK)
+          fail(std::string(who) + ": needs a second buffer of the slab's size, which does not fit in device memory");
+     return scratch_.data();
+}
+
 // ------------------------------------------------------------------------------------ Pauli groups
 std::vector<Engine::PauliGroup> Engine::pauli_groups(const std::vector<PauliTerm>& terms, const std::vector<Index>& ids,
                                                      const char* what) const
@@ -197,14 +205,10 @@ void Engine::apply_qubit_operator(const std::vector<PauliTerm>& terms, const std
           return;
      }
      // general operator: new = sum over groups, accumulated in a second buffer (ProjectQ keeps three copies)
-     DeviceBuffer acc;
-     if (!dry_run_) {
-          if (cudaMalloc(&acc.p, n * sizeof(double2)) != cudaSuccess) {
-               cudaGetLastError();
-               fail("apply_qubit_operator(): an operator whose terms flip different qubit sets needs a second buffer of the "
-                    "slab's size, which does not fit in device memory");
-          }
-     }
+     struct {
+          void* p = nullptr;
+     } acc;
+     if (!dry_run_) acc.p = scratch_buffer(n, "apply_qubit_operator(): an operator whose terms flip different qubit sets");
      bool first = true;
      for (const PauliGroup& g: groups) {
           const int partner = rank_ ^ g.gx;
@@ -434,11 +438,8 @@ void Engine::emulate_math(int kind, uint64_t a, uint64_t N, const std::vector<ui
      if (!peer_ranks.empty() && !ensure_peer_views(peer_ranks))
           fail(std::string("emulate_math(): registers on global qubits need the peers' slabs mapped into this process: ") + hiq_last_error());
      if (!participate) return;  // a global control is 0 here — and on every rank this one could exchange with
-     DeviceBuffer tmp, table;
-     if (cudaMalloc(&tmp.p, n * sizeof(double2)) != cudaSuccess) {
-          cudaGetLastError();
-          fail("emulate_math(): needs a second buffer of the slab's size, which does not fit in device memory");
-     }
+     DeviceBuffer table;
+     double2* tmp = scratch_buffer(n, "emulate_math()");
      if (!inverse.empty()) {
           cu(check_cuda(cudaMalloc(&table.p, inverse.size() * sizeof(uint32_t)), "cudaMalloc table"));
           cu(check_cuda(cudaMemcpyAsync(table.p, inverse.data(), inverse.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream_),
@@ -450,10 +451,17 @@ void Engine::emulate_math(int kind, uint64_t a, uint64_t N, const std::vector<ui
      slabs[rank_] = slab_.data();
      for (int pr: peer_ranks) slabs[pr] = peer_views_[pr].slab.data();
      if (!peer_ranks.empty()) group_barrier(peer_ranks);  // the peers' gates are complete before their slabs are read
-     cu(hiqk_permute_gather(tmp.p, slabs.data(), world_, rank_, L, &perm, stream_));
+     cu(hiqk_permute_gather(tmp, slabs.data(), world_, rank_, L, &perm, stream_));
      if (!peer_ranks.empty()) group_barrier(peer_ranks);  // nobody overwrites a slab a peer still reads
-     cu(check_cuda(cudaMemcpyAsync(slab_.data(), tmp.p, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream_), "cudaMemcpyAsync"));
-     cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
+     if (world_ == 1) {
+          // one process: the permuted copy becomes the slab (the peers of a multi-GPU world have the slab's memory mapped,
+          // there the result is copied back)
+          slab_.swap(scratch_);
+     }
+     else {
+          cu(check_cuda(cudaMemcpyAsync(slab_.data(), tmp, n * sizeof(double2), cudaMemcpyDeviceToDevice, stream_), "cudaMemcpyAsync"));
+     }
+     if (table.p) cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));  // the table is freed on return
 }
 
 // ------------------------------------------------------------------------------------ cheat()

@@ -5,7 +5,6 @@
 #include <algorithm>
 #include <string>
 #include <cstdlib>
-#include <mutex>
 
 #include "hiq_host.hpp"
 
@@ -78,44 +77,6 @@ static int check_cu(CUresult r, const char* what)
           if (_rc != HIQ_OK) return _rc;               \
      } while (0)
 
-// One released slab per process can be kept mapped and handed to the next engine with the same reservation
-// (HIQ_SLAB_POOL=1, opt-in): a caller that builds an engine per circuit — the reference's usage, one SimulatorMPI per
-// run — then pays cuMemCreate / cuMemMap of a 128 GiB slab once instead of per engine.  Contents are not preserved or
-// cleared; the engine fills what it allocates.
-namespace {
-struct PooledSlab {
-     bool valid = false;
-     int device = 0;
-     bool shareable = false;
-     CUdeviceptr base = 0;
-     size_t reserved = 0, mapped = 0, gran = 0;
-     std::vector<std::pair<CUmemGenericAllocationHandle, size_t>> chunks;
-};
-PooledSlab g_pool;
-std::mutex g_pool_mu;
-bool slab_pool_enabled()
-{
-     static const bool on = [] {
-          const char* e = std::getenv("HIQ_SLAB_POOL");
-          return e && e[0] == '1';
-     }();
-     return on;
-}
-void free_pooled_locked()
-{
-     if (!g_pool.valid) return;
-     cudaDeviceSynchronize();
-     size_t off = 0;
-     for (auto& c: g_pool.chunks) {
-          g_drv.MemUnmap(g_pool.base + off, c.second);
-          g_drv.MemRelease(c.first);
-          off += c.second;
-     }
-     g_drv.MemAddressFree(g_pool.base, g_pool.reserved);
-     g_pool = PooledSlab{};
-}
-}  // namespace
-
 int Slab::init(int device, uint64_t max_amps, bool shareable)
 {
      device_ = device;
@@ -138,17 +99,6 @@ int Slab::init(int device, uint64_t max_amps, bool shareable)
      want = std::min(want, total);  // more than the device holds can never be mapped
      want = std::max(want, gran_);
      reserved_ = (want + gran_ - 1) / gran_ * gran_;
-     if (slab_pool_enabled()) {
-          std::lock_guard<std::mutex> lock(g_pool_mu);
-          if (g_pool.valid && g_pool.device == device && g_pool.shareable == shareable && g_pool.reserved == reserved_) {
-               base_ = g_pool.base;
-               mapped_ = g_pool.mapped;
-               chunks_ = std::move(g_pool.chunks);
-               g_pool = PooledSlab{};
-               return HIQ_OK;
-          }
-          free_pooled_locked();  // a different shape is wanted: give the memory back first
-     }
      HIQ_CU(g_drv.MemAddressReserve(&base_, reserved_, 0, 0, 0));
      return HIQ_OK;
 }
@@ -190,23 +140,6 @@ int Slab::ensure(uint64_t amps)
 void Slab::release()
 {
      if (!base_) return;
-     if (slab_pool_enabled() && mapped_ > 0) {
-          std::lock_guard<std::mutex> lock(g_pool_mu);
-          cudaDeviceSynchronize();
-          free_pooled_locked();
-          g_pool.valid = true;
-          g_pool.device = device_;
-          g_pool.shareable = shareable_;
-          g_pool.base = base_;
-          g_pool.reserved = reserved_;
-          g_pool.mapped = mapped_;
-          g_pool.gran = gran_;
-          g_pool.chunks = std::move(chunks_);
-          chunks_.clear();
-          base_ = 0;
-          mapped_ = reserved_ = 0;
-          return;
-     }
      cudaDeviceSynchronize();
      size_t off = 0;
      for (auto& c: chunks_) {

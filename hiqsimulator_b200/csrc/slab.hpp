@@ -36,6 +36,17 @@ public:
      size_t chunk_bytes(size_t i) const { return chunks_[i].second; }
      // a new file descriptor for physical chunk i (the caller closes it after sending it away)
      int export_chunk(size_t i, int* fd) const;
+     // exchange the two buffers (address ranges and physical memory): an out-of-place pass ends with a swap, not a copy
+     void swap(Slab& o)
+     {
+          std::swap(device_, o.device_);
+          std::swap(base_, o.base_);
+          std::swap(reserved_, o.reserved_);
+          std::swap(mapped_, o.mapped_);
+          std::swap(gran_, o.gran_);
+          std::swap(shareable_, o.shareable_);
+          chunks_.swap(o.chunks_);
+     }
 
 private:
      int device_ = 0;

@@ -19,6 +19,7 @@
 //    tile) and kept in shared memory; the part of a selector that depends on the tile is computed once per tile.
 #include <algorithm>
 #include <array>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <mutex>
@@ -213,7 +214,19 @@ int local_pos(const TilePlan& pl, int slot)
      return -1;
 }
 
-// smallest supported tile that holds the `lo` low slots (>= 4: 256 B runs) and every target of the run
+// fewest contiguous low slots a tile may have: 4 = 256-byte runs in HBM (HIQ_TILE_MIN_LO=3 allows 128-byte runs, which lets
+// an 8-slot run take the 2^11 tile with four CTAs per SM instead of the 2^12 one with two)
+int tile_min_lo()
+{
+     static const int v = [] {
+          const char* e = std::getenv("HIQ_TILE_MIN_LO");
+          const int x = e ? std::atoi(e) : 4;
+          return x < 3 ? 3 : (x > 6 ? 6 : x);
+     }();
+     return v;
+}
+
+// smallest supported tile that holds at least tile_min_lo() low slots and every target of the run
 bool choose_tile(int L, int n_steps, const hiqk_tile_step* steps, TilePlan& pl, std::string& why)
 {
      uint64_t u = 0;
@@ -238,7 +251,7 @@ bool choose_tile(int L, int n_steps, const hiqk_tile_step* steps, TilePlan& pl, 
           int lo = T;
           auto n_hi = [&](int l) { return __builtin_popcountll(u >> l); };
           while (lo > 0 && lo + n_hi(lo) > T) --lo;
-          if (lo + n_hi(lo) != T || lo < 4) continue;
+          if (lo + n_hi(lo) != T || lo < tile_min_lo()) continue;
           pl.T = T;
           pl.lo = lo;
           pl.n_hi = 0;

@@ -189,12 +189,12 @@ def test_engine_matches_golden_multi_gpu(name):
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
-@pytest.mark.parametrize("mode", ["p2p", "packed", "packed_pull", "staged"])
+@pytest.mark.parametrize("mode", ["p2p", "packed", "staged"])
 @pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("r1_")])
 def test_engine_matches_golden_multi_gpu_swap_transports(name, mode):
     """the same golden runs with the exchange forced onto each transport — in place over peer-mapped slabs, packed
-    (pieces pushed into the peers' staging buffers / pulled from them) and the staged NCCL pipeline: every transport
-    performs the same transposition"""
+    (pieces pushed into the peers' staging buffers) and the staged NCCL pipeline: every transport performs the same
+    transposition"""
     R = int(name[1])
     if _gpu_count() < R:
         pytest.skip("needs %d GPUs" % R)
@@ -205,11 +205,9 @@ def test_engine_matches_golden_multi_gpu_swap_transports(name, mode):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
            "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
-    env = dict(os.environ, HIQ_SWAP_MODE=mode.split("_")[0])
-    if mode.startswith("packed"):
+    env = dict(os.environ, HIQ_SWAP_MODE=mode)
+    if mode == "packed":
         env["HIQ_SWAP_PACKED_PIECE"] = "16"  # many pieces even on these small slabs: the two-buffer pipeline is exercised
-    if mode == "packed_pull":
-        env["HIQ_SWAP_PACKED_PULL"] = "1"
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 

@@ -1,7 +1,7 @@
 """Swap sweep on N GPUs (mirrors the reference's opyt-mpi.cpp all_to_all loop): global<->local swaps of
 q qubits for several local-slot classes, peer-mapped and staged transports, NVLink GB/s per GPU per
 direction = 16 B * 2^L * (1 - 2^-q) / t.  Launch with torchrun; JSON lines on rank 0.
-    HIQ_SWAP_MODE=p2p|staged torchrun --nproc-per-node N tools/bench_swap.py --L 30
+    HIQ_SWAP_MODE=p2p|packed|staged torchrun --nproc-per-node N tools/bench_swap.py --L 30     (default: automatic choice)
 """
 import argparse
 import json
@@ -27,7 +27,7 @@ def main():
     sim = M.SimulatorMPI(1, L, 4)
     sim.allocate_qureg(list(range(n)), 2.0 ** (-n / 2))
     sim.synchronize()
-    mode = os.environ.get("HIQ_SWAP_MODE", "auto") + ("_pull" if os.environ.get("HIQ_SWAP_PACKED_PULL") == "1" else "")
+    mode = os.environ.get("HIQ_SWAP_MODE", "auto")
     cases = []
     for q in range(1, g + 1):
         cases += [(q, "top", list(range(L - q, L))), (q, "mid", list(range(12, 12 + q))), (q, "slot3+", list(range(3, 3 + q))),
