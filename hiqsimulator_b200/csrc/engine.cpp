@@ -776,6 +776,7 @@ std::vector<bool> Engine::measure_qubits(const std::vector<Index>& ids)
      // two-level inverse-CDF sampling of the reference (SimulatorMPI.cpp:897-1008)
      need_device("MeasureQubits()");
      flush_pending();
+     cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));  // queued gates are not the measurement's time
      const auto t0 = Clock::now();
      const int L = static_cast<int>(locals_.size());
      const uint64_t size = 1ull << L;
