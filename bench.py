@@ -100,13 +100,17 @@ class RecordingBackend:
         self.inner.receive(cmds)
 
 
-def schedule_circuit(n, L, cmds, backend_class, sched_module=None, cluster=4, use_planner=True):
+def schedule_circuit(n, L, cmds, backend_class, sched_module=None, cluster=4):
     """Run the GreedyScheduler once against `backend_class` (a dry-run engine of this repository, or the reference
     engine itself in the reference arm) -> recorded command stream, schedule shape."""
     from hiqsimulator_b200 import backends, cengines, ops
     inner = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=L, max_fused_qubits=cluster, backend_class=backend_class)
     rec = RecordingBackend(inner)
-    gs = cengines.GreedyScheduler(cluster_size=cluster, sched_module=sched_module, use_planner=use_planner)
+    if sched_module is None:
+        gs = cengines.GreedyScheduler(cluster_size=cluster)
+    else:  # the reference arm: the reference's own Python loop around the unmodified reference scheduler
+        from oracle import greedy_loop
+        gs = greedy_loop.ReferenceLoopScheduler(cluster_size=cluster, sched_module=sched_module)
     eng = cengines.HiQMainEngine(rec, [gs])
     t0 = time.perf_counter()
     eng.receive([ops.AllocateQureg(list(range(n)), 0)])
@@ -254,7 +258,7 @@ def run_reference_steps(kind, steps, warmup, budget_s, n_cpu=None, log=None):
     # ---- probe: a few fused passes of the same generator at 26 qubits (1 GiB state, far beyond the last-level cache)
     if n_cpu is None:
         pn = 26
-        pstream, pshape, pbe = schedule_circuit(pn, pn, build_circuit(kind, pn)[:12 * pn], refsim.SimulatorMPI, refsched, use_planner=False)
+        pstream, pshape, pbe = schedule_circuit(pn, pn, build_circuit(kind, pn)[:12 * pn], refsim.SimulatorMPI, refsched)
         fl = flush_positions(pstream)
         t0 = time.perf_counter()
         replay(pbe, pstream)
@@ -275,7 +279,7 @@ def run_reference_steps(kind, steps, warmup, budget_s, n_cpu=None, log=None):
             log["probe"] = "%d passes of %s-%d: %.1f GB/s" % (len(fl), kind, pn, rate / 1e9)
     cmds = build_circuit(kind, n_cpu)
     t_s = time.perf_counter()
-    stream, shape, be = schedule_circuit(n_cpu, n_cpu, cmds, refsim.SimulatorMPI, refsched, use_planner=False)
+    stream, shape, be = schedule_circuit(n_cpu, n_cpu, cmds, refsim.SimulatorMPI, refsched)
     shape["reference_scheduler_s"] = round(time.perf_counter() - t_s, 2)
     fl = flush_positions(stream)
     # bounded sample: the first P fused passes of the plan when the whole circuit x (steps + warmup) exceeds the budget

@@ -1,6 +1,9 @@
-"""GreedyScheduler: the stage/cluster driver loop around `_sched_cpp`, restated without ProjectQ.
+"""GreedyScheduler: the engine that caches gates and hands them to the backend stage by stage, cluster by cluster.
 
-Behavioural spec: reference hiq/projectq/cengines/_greedyscheduler.py:95-265.
+Behavioural spec: reference hiq/projectq/cengines/_greedyscheduler.py:95-265.  The stage / cluster loop
+itself (which cluster next, which qubits swap) runs inside `_sched_cpp.GreedyPlanner` (csrc/sched.cpp), one step per
+`next()`, on a host thread that runs ahead of the device; the reference's Python loop, restated, lives in
+oracle/greedy_loop.py as a cross-check and as the driver of the unmodified reference scheduler.
 Gates are cached; Allocate / AllocateQureg / fast-forwarding commands force scheduling:
   first time only, the SwapScheduler picks the initial local set and the backend is *relabelled*
   (set_qubits_perm, no data motion); then ClusterScheduler is asked repeatedly which cached gates
@@ -16,15 +19,13 @@ from . import ops
 
 
 class GreedyScheduler:
-    def __init__(self, supremacy_circuit=False, num_splits=10 ** 6, cluster_size=4, sched_module=None, use_planner=True,
-                 prefetch=True):
+    def __init__(self, supremacy_circuit=False, num_splits=10 ** 6, cluster_size=4, sched_module=None, prefetch=True):
         if sched_module is None:
             from . import _sched_cpp as sched_module
         self._sched = sched_module
         self._cmd_list = []
         self._was_scheduling = False
         self._supremacy_circuit = supremacy_circuit
-        self._use_planner = use_planner  # False: the Python loop of the reference drives ClusterScheduler / SwapScheduler directly
         self._prefetch = prefetch        # planner steps are computed ahead of the device on a host thread
         self.NUM_SPLITS = num_splits
         self.CLUSTER_SIZE = cluster_size
@@ -42,43 +43,9 @@ class GreedyScheduler:
     def send(self, cmds):
         self.next_engine.receive(cmds)
 
-    # -- reference: _greedyscheduler.py:95-112
-    def _prepare_ctrlz(self):
-        local_qubits = self.backend.get_local_qubits_ids()
-        global_qubits = self.backend.get_global_qubits_ids()
-        for cmd in self._cmd_list:
-            if cmd.is_z:
-                assert len(cmd.qubits) == 1
-                if cmd.qubits[0] in global_qubits:
-                    for i, c in enumerate(cmd.controls):
-                        if c in local_qubits:
-                            cmd.controls[i], cmd.qubits[0] = cmd.qubits[0], cmd.controls[i]
-                            break
-
     def _get_commands(self):
         return ([list(c.qubits) for c in self._cmd_list], [list(c.controls) for c in self._cmd_list],
                 [False] * len(self._cmd_list))
-
-    # -- reference: _greedyscheduler.py:119-137
-    def _call_cluster_scheduler(self):
-        self._prepare_ctrlz()
-        local_qubits = self.backend.get_local_qubits_ids()
-        global_qubits = self.backend.get_global_qubits_ids()
-        while True:
-            gate, gate_ctrl, gate_diag = self._get_commands()
-            t0 = time.perf_counter()
-            cs = self._sched.ClusterScheduler(gate, gate_ctrl, gate_diag, local_qubits, global_qubits, self.CLUSTER_SIZE)
-            avail = cs.ScheduleCluster()
-            self.cluster_seconds += time.perf_counter() - t0
-            if len(avail) == 0:
-                return
-            self.n_clusters += 1
-            self.log.append(("cluster", [self._cmd_list[i].uid for i in avail]))
-            for i in avail:
-                self.send([self._cmd_list[i]])
-            self.send([ops.Flush()])
-            for i in reversed(sorted(avail)):
-                del self._cmd_list[i]
 
     # -- reference: _greedyscheduler.py:151-173
     def _remove_ending_cz(self):
@@ -98,23 +65,6 @@ class GreedyScheduler:
             else:
                 used.update(allq)
             i -= 1
-
-    # -- reference: _greedyscheduler.py:175-193
-    def _call_swap_scheduler(self):
-        local_qubits = self.backend.get_local_qubits_ids()
-        gate, gate_ctrl, gate_diag = self._get_commands()
-        t0 = time.perf_counter()
-        new_locals = self._sched.SwapScheduler(gate, gate_ctrl, gate_diag, self.NUM_SPLITS, len(local_qubits), True).ScheduleSwap()
-        if len(new_locals) == 0:
-            new_locals = self._sched.SwapScheduler(gate, gate_ctrl, gate_diag, self.NUM_SPLITS, len(local_qubits), False).ScheduleSwap()
-        self.swap_seconds += time.perf_counter() - t0
-        g_to_l = sorted(set(new_locals) - set(local_qubits))
-        l_to_g = []
-        if len(g_to_l) > 0:
-            lst = sorted(set(local_qubits) - set(new_locals))
-            assert len(lst) >= len(g_to_l)
-            l_to_g = lst[:len(g_to_l)]
-        return g_to_l, l_to_g
 
     # -- reference: _greedyscheduler.py:195-201
     def _check_commands(self):
@@ -185,38 +135,16 @@ class GreedyScheduler:
         self.swap_seconds += planner.swap_seconds()
         self._cmd_list = []
 
-    # -- reference: _greedyscheduler.py:203-242
+    # -- reference: _greedyscheduler.py:203-242 (the stage / cluster loop itself runs inside the planner)
     def _force_scheduling(self):
         if len(self._cmd_list) == 0:
             return
         self._check_commands()
-        if self._use_planner and not self._supremacy_circuit and hasattr(self._sched, "GreedyPlanner"):
-            self._force_scheduling_planned()
-            return
         if self._supremacy_circuit:
             self._remove_ending_cz()
-        if not self._was_scheduling:
-            self._was_scheduling = True
-            ids_list = list(self.backend.get_qubits_ids())
-            g_to_l, l_to_g = self._call_swap_scheduler()
-            for i in range(len(l_to_g)):
-                p1 = ids_list.index(g_to_l[i])
-                p2 = ids_list.index(l_to_g[i])
-                ids_list[p1], ids_list[p2] = ids_list[p2], ids_list[p1]
-            self.backend.set_qubits_perm(ids_list)
-            self.log.append(("perm", list(ids_list)))
-        self._call_cluster_scheduler()
-        while len(self._cmd_list) > 0:
-            g_to_l, l_to_g = self._call_swap_scheduler()
-            assert len(g_to_l) > 0
-            pairs = []
-            for i in range(len(g_to_l)):
-                pairs += [g_to_l[i], l_to_g[i]]
-            self.n_swaps += 1
-            self.log.append(("swap", list(pairs)))
-            self.send([ops.MetaSwap(pairs)])
-            self._call_cluster_scheduler()
-        assert len(self._cmd_list) == 0
+            if len(self._cmd_list) == 0:
+                return
+        self._force_scheduling_planned()
 
     def _send_deallocations(self):
         for c in sorted(self._deallocations_cache, key=lambda cmd: cmd.qubits[0], reverse=True):

@@ -246,7 +246,11 @@ bool choose_tile(int L, int n_steps, const hiqk_tile_step* steps, TilePlan& pl, 
           }
           u |= seen;
      }
-     for (int T = 11; T <= 12; ++T) {
+     static const int min_t = [] {
+          const char* e = std::getenv("HIQ_TILE_MIN_T");  // measurements: force the 2^12 tile
+          return e ? std::atoi(e) : 11;
+     }();
+     for (int T = std::max(11, std::min(12, min_t)); T <= 12; ++T) {
           if (T > L) break;
           int lo = T;
           auto n_hi = [&](int l) { return __builtin_popcountll(u >> l); };

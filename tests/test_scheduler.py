@@ -169,12 +169,39 @@ def test_planner_equals_python_loop(kind, n, R, ml, cluster):
     assert runs[0][2] == runs[1][2]          # every descriptor the engine emitted (fused matrices bit for bit)
 
 
+def test_planner_with_supremacy_preprocessing_equals_python_loop():
+    """supremacy_circuit=True (trailing controlled-Z gates dropped, reference _greedyscheduler.py:151-173) is a preprocessing
+    of the cached list: the planner path and the reference's loop emit the same schedule"""
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    from hiqsimulator_b200 import backends, cengines, circuits
+    from oracle import greedy_loop
+    nq, cmds = circuits.random_circuit(12, 6, seed=3)
+    logs = []
+    for cls in (cengines.GreedyScheduler, greedy_loop.ReferenceLoopScheduler):
+        be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=10, max_fused_qubits=4,
+                                   backend_class=lambda s, ml, mc: M.SimulatorMPI(s, ml, mc, 0, 4, M.FLAG_DRY_RUN))
+        gs = cls(cluster_size=4, supremacy_circuit=True)
+        eng = cengines.HiQMainEngine(be, [gs])
+        eng.allocate_qureg(nq)
+        c2 = copy.deepcopy(cmds)
+        for i, c in enumerate(c2):
+            c.uid = i
+        eng.receive(c2)
+        eng.flush()
+        logs.append([[k, [int(x) for x in v]] for k, v in gs.log])
+    assert logs[0] == logs[1] and len(logs[0]) > 5
+
+
 def greedy_log_ex(n, cmds, R, max_local, cluster, use_planner):
     from hiqsimulator_b200 import _cppsim_mpi as M
     from hiqsimulator_b200 import backends, cengines
     be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=max_local, max_fused_qubits=cluster,
                                backend_class=lambda s, ml, mc: M.SimulatorMPI(s, ml, mc, R - 1, R, M.FLAG_DRY_RUN))
-    gs = cengines.GreedyScheduler(cluster_size=cluster, use_planner=use_planner)
+    if use_planner:
+        gs = cengines.GreedyScheduler(cluster_size=cluster)
+    else:
+        from oracle import greedy_loop
+        gs = greedy_loop.ReferenceLoopScheduler(cluster_size=cluster)
     eng = cengines.HiQMainEngine(be, [gs])
     eng.allocate_qureg(n)
     cmds = copy.deepcopy(cmds)
@@ -195,7 +222,8 @@ def greedy_log(n, cmds, R, max_local, sched_module, cluster=4, supremacy=False):
     M.init_world(0, R, b"", 0, M.FLAG_DRY_RUN)
     be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=max_local, max_fused_qubits=cluster)
     M.init_world(0, 1, b"", 0, 0)
-    gs = cengines.GreedyScheduler(cluster_size=cluster, sched_module=sched_module, supremacy_circuit=supremacy)
+    from oracle import greedy_loop
+    gs = greedy_loop.ReferenceLoopScheduler(cluster_size=cluster, sched_module=sched_module, supremacy_circuit=supremacy)
     eng = cengines.HiQMainEngine(be, [gs])
     eng.allocate_qureg(n)
     cmds = copy.deepcopy(cmds)

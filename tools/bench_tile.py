@@ -73,6 +73,14 @@ def main():
     rec("direct_full_product", lambda: K.apply_dense(state, full[0][0], u[0], 0, K.DIRECT), 1)
     for n in (1, 2, 3):
         rec("tile_full_product_x%d" % n, lambda: K.apply_tile_program(state, full[:n]), n)
+    # how the number of far-apart regions a tile gathers from (2^high slots) and the run length (2^low slots) act on a
+    # one-gate pass: targets (hi..hi+3) share the tile with `extra` further high slots brought in by a no-op partner gate
+    ident = np.eye(2, dtype=np.complex128)
+    for extra in (0, 2, 4):
+        steps = [([L - 4, L - 3, L - 2, L - 1], m2, [])]
+        if extra:
+            steps.append(([L - 5 - i for i in range(min(extra, 4))], np.kron(np.eye(1 << (min(extra, 4) - 1)), ident) if extra > 1 else ident, []))
+        rec("tile_mix2_high_slots_%d" % (4 + extra), lambda: K.apply_tile_program(state, steps), 1, tile_bits=K.tile_program_fits(L, steps))
     low = ([0, 9, 17, 25], u[0], [])
     rec("dmma_slot0", lambda: K.apply_dense(state, low[0], u[0], 0, K.AUTO), 1)
     rec("tile_slot0_single", lambda: K.apply_tile_program(state, [low]), 1)
