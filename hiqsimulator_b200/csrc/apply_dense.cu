@@ -548,7 +548,7 @@ static int launch_direct(double2* psi, int L, const int* slots, const double* ma
      constexpr int THREADS = (K >= 4) ? 128 : 256;
      constexpr int MINB = (K >= 5) ? 2 : (K == 4 ? 4 : 4);
      const uint64_t need = (p.n_free + THREADS - 1) / THREADS;
-     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(num_sms()) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(need, cap));
      auto go = [&](auto ks_c, auto m3_c) {
           constexpr int KS = decltype(ks_c)::value;
@@ -648,7 +648,7 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
                if (p.prog.usel[j][t]) p.fast = 0;
      const size_t smem = sizeof(double2) * THREADS * ((1u << K) + std::max(p.e_npat, 1));
      const uint64_t n_chunks = (p.d.n_free + THREADS - 1) / THREADS;
-     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 8);
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(num_sms()) * MINB * 8);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap));
      auto go = [&](auto ks_c, auto m3_c) {
           constexpr int KS = decltype(ks_c)::value;
@@ -658,7 +658,7 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
                // B200, profiles/r02a_prediag_{staged,blockloop}_L30.jsonl: 6.46 -> 5.84 ms for the QFT-like launch at L = 30)
                constexpr int MINB2 = (K >= 3) ? (KS >= 3 ? 4 : 6) : 4;
                const size_t smem2 = sizeof(double2) * THREADS * std::max(p.e_npat, 1);
-               const uint64_t cap2 = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB2 * 8);
+               const uint64_t cap2 = grid_cap(static_cast<uint64_t>(num_sms()) * MINB2 * 8);
                const unsigned grid2 = static_cast<unsigned>(std::min<uint64_t>(n_chunks, cap2));
                dense_direct_pre_blocks_kernel<K, KS, THREADS, MINB2><<<grid2, THREADS, smem2, stream>>>(p);
                count_launch();
@@ -748,7 +748,7 @@ static int launch_tiled(double2* psi, int L, const int* slots, const double* mat
           cudaFuncSetAttribute(dense_tiled_kernel<K, THREADS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
           attr_set = true;
      }
-     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 4);
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(num_sms()) * MINB * 4);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, cap));
      dense_tiled_kernel<K, THREADS, MINB><<<grid, THREADS, smem, stream>>>(p);
      count_launch();
@@ -780,7 +780,7 @@ static int launch_dmma(double2* psi, int L, const int* slots, const double* matr
      }
      const uint64_t groups_per_block = static_cast<uint64_t>(THREADS / 32) * G;
      const uint64_t need = (p.n_groups + groups_per_block - 1) / groups_per_block;
-     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * MINB * 2);
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(num_sms()) * MINB * 2);
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(need, cap));
      dense_dmma_kernel<K, THREADS, MINB, G><<<grid, THREADS, smem, stream>>>(p);
      count_launch();

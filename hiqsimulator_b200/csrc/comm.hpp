@@ -57,6 +57,9 @@ public:
           size_t bytes() const { return mine.mapped_amps() * sizeof(double2); }
      };
      PackedStaging& packed() { return packed_; }
+     // the peer-mapping handshake failed once in this process group (peers on another node, no descriptor channel ...):
+     // every later engine goes straight to the staged NCCL exchange instead of waiting for the handshake to time out again
+     bool p2p_broken = false;
 
      // host-value collectives (values staged through a small device buffer on `stream`)
      int allreduce_sum(double* vals, int n, cudaStream_t stream);

@@ -71,8 +71,6 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
      std::uniform_real_distribution<double> dist(0., 1.);
      rng_ = std::bind(dist, std::ref(rnd_eng_));
      if (!dry_run_) {
-          cu(check_cuda(cudaSetDevice(device_), "cudaSetDevice"));
-          cu(slab_.init(device_, 1ull << max_local_, world_size > 1));
           if (const char* m = std::getenv("HIQ_SWAP_MODE")) {
                if (!std::strcmp(m, "staged") || !std::strcmp(m, "nccl")) swap_mode_ = 1;
                else if (!std::strcmp(m, "p2p")) swap_mode_ = 2;
@@ -87,7 +85,9 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
      if (const char* m = std::getenv("HIQ_TILE_MAX_FULL")) tile_max_full_ = std::atoi(m);
      if (const char* m = std::getenv("HIQ_TILE_MAX_STEPS")) tile_max_steps_ = std::max(1, std::min(HIQK_TILE_MAX_STEPS, std::atoi(m)));
      if (const char* m = std::getenv("HIQ_TILE_SINGLE")) tile_single_ = m[0] == '1';
-     if (!dry_run_) {
+     if (!dry_run_) try {
+          cu(check_cuda(cudaSetDevice(device_), "cudaSetDevice"));
+          cu(slab_.init(device_, 1ull << max_local_, world_size > 1));
           cu(check_cuda(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           cu(check_cuda(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking), "cudaStreamCreate"));
           comm_p_ = Comm::shared(rank, world_size, nccl_id, device_);
@@ -98,32 +98,47 @@ Engine::Engine(uint64_t seed, int max_local, int max_cluster, int rank, int worl
           cu(slab_.ensure(1));
           cu(hiqk_fill(slab_.data(), 0, 1, rank_ == 0 ? 1.0 : 0.0, 0.0, stream_));
      }
+     catch (...) {
+          // a constructor that throws runs no destructor: give back what was created so far (hiq_create may be retried)
+          release_device_resources();
+          throw;
+     }
      ++stats_.total_stages;
      stats_.ctor_s = seconds_since(t_ctor);
 }
 
-Engine::~Engine()
+void Engine::release_device_resources()
 {
-     if (!dry_run_) {
-          cudaSetDevice(device_);
-          cudaDeviceSynchronize();
-          if (workspace_) cudaFree(workspace_);
-          if (d_vals_) cudaFree(d_vals_);
-          if (d_blocks_) cudaFree(d_blocks_);
-          if (swap_buf_) cudaFree(swap_buf_);
-          slab_.release();
-          scratch_.release();
-          for (auto& t: timed_) {
-               cudaEventDestroy(t.start);
-               cudaEventDestroy(t.stop);
-          }
-          for (auto ev: event_pool_) cudaEventDestroy(ev);
-          for (auto ev: swap_events_)
-               if (ev) cudaEventDestroy(ev);
-          if (stream_) cudaStreamDestroy(stream_);
-          if (comm_stream_) cudaStreamDestroy(comm_stream_);
+     if (dry_run_) return;
+     cudaSetDevice(device_);
+     cudaDeviceSynchronize();
+     if (workspace_) cudaFree(workspace_);
+     if (d_vals_) cudaFree(d_vals_);
+     if (d_blocks_) cudaFree(d_blocks_);
+     if (swap_buf_) cudaFree(swap_buf_);
+     workspace_ = nullptr;
+     d_vals_ = d_blocks_ = nullptr;
+     swap_buf_ = nullptr;
+     slab_.release();
+     scratch_.release();
+     for (auto& t: timed_) {
+          cudaEventDestroy(t.start);
+          cudaEventDestroy(t.stop);
      }
+     timed_.clear();
+     for (auto ev: event_pool_) cudaEventDestroy(ev);
+     event_pool_.clear();
+     for (auto& ev: swap_events_)
+          if (ev) {
+               cudaEventDestroy(ev);
+               ev = nullptr;
+          }
+     if (stream_) cudaStreamDestroy(stream_);
+     if (comm_stream_) cudaStreamDestroy(comm_stream_);
+     stream_ = comm_stream_ = nullptr;
 }
+
+Engine::~Engine() { release_device_resources(); }
 
 void Engine::synchronize()
 {
@@ -1008,7 +1023,7 @@ void Engine::exchange(const std::vector<int>& gpos, const std::vector<int>& slot
      if (want_packed && !comm_p_->packed().failed && exchange_packed(gpos, slots)) return;
      if (swap_mode_ == 3) fail(std::string("SwapQubits(): packed exchange unavailable: ") + hiq_last_error());
      const bool want_p2p = swap_mode_ == 2 || (swap_mode_ == 0 && lowest >= min_p2p_slot_);
-     if (want_p2p && !p2p_broken_ && exchange_p2p(gpos, slots)) return;
+     if (want_p2p && !comm_p_->p2p_broken && exchange_p2p(gpos, slots)) return;
      if (swap_mode_ == 2) fail(std::string("SwapQubits(): peer-mapped exchange unavailable: ") + hiq_last_error());
      exchange_staged(gpos, slots);
 }
@@ -1083,7 +1098,7 @@ bool Engine::map_peer_chunks(const Slab& mine, std::vector<PeerView>& views, uin
      size_t next = 0;
      const auto t0 = Clock::now();
      while (next < outbox.size() || !complete()) {
-          if (seconds_since(t0) > 60.0) {
+          if (seconds_since(t0) > 20.0) {
                set_error(HIQ_ERR_RUNTIME, "peer ipc: handshake timed out");
                return false;
           }
@@ -1116,7 +1131,7 @@ bool Engine::ensure_peer_views(const std::vector<int>& peer_ranks)
      // The handshake runs only when some view is incomplete — a condition that is the same on every rank,
      // because slabs grow in lock-step — and its outcome is agreed on by the whole world, so that either
      // all ranks take the peer-mapped path or all fall back (swap: staged exchange; emulate_math: error).
-     if (p2p_broken_) {
+     if (comm_p_->p2p_broken) {
           set_error(HIQ_ERR_RUNTIME, "peer-mapped slabs are unavailable in this process group");
           return false;
      }
@@ -1130,7 +1145,7 @@ bool Engine::ensure_peer_views(const std::vector<int>& peer_ranks)
           const std::string why = failed != 0.0 ? hiq_last_error() : "";
           cu(comm_p_->allreduce_sum(&failed, 1, stream_));
           if (failed != 0.0) {
-               p2p_broken_ = true;
+               comm_p_->p2p_broken = true;
                set_error(HIQ_ERR_RUNTIME, why.empty() ? "a peer rank could not map the slabs" : why);
                return false;
           }

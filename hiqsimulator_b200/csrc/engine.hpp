@@ -158,6 +158,7 @@ private:
      void queue_diagonal(const Descriptor& d);
      void flush_pending(size_t keep = 0);
      void ensure_scratch();
+     void release_device_resources();
 
      const double max_float_error_ = 1e-12;
      size_t min_local_, max_local_, max_global_, max_cluster_;
@@ -194,7 +195,6 @@ private:
      uint64_t packed_piece_cap_ = 0;    // HIQ_SWAP_PACKED_PIECE: largest piece in amplitudes (tests drive the multi-piece pipeline with it)
      bool ensure_packed_staging(size_t want_bytes, size_t min_bytes);  // process-wide buffers live in Comm::packed()
      bool exchange_packed(const std::vector<int>& gpos, const std::vector<int>& slots);
-     bool p2p_broken_ = false;  // the handshake failed once: stay on the staged path
      int min_p2p_slot_ = 0;     // lowest swapped slot for which the in-place kernel is used in auto mode
      int dense_variant_ = 0;
 

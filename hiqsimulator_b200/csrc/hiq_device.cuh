@@ -7,7 +7,7 @@ namespace hiq {
 
 constexpr int kMaxTargets = 5;   // the reference's Run() accepts up to 5 fused qubits
                                  // (reference: src/simulator-mpi/SimulatorMPI.cpp:470-524)
-constexpr int kNumSMs = 148;     // B200
+constexpr int kNumSMsB200 = 148;  // B200; the launchers size their grids from the device's own count (num_sms())
 
 // Positions (ascending) at which zero bits are inserted into a counter to
 // enumerate indices whose target/control bits are clear ("bit deposit").

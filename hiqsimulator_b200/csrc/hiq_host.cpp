@@ -23,6 +23,25 @@ int check_launch(const char* what) { return check_cuda(cudaGetLastError(), what)
 
 void count_launch(unsigned n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
+int num_sms()
+{
+     static std::atomic<int> cache[64];
+     int dev = 0;
+     if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+          cudaGetLastError();
+          return 148;
+     }
+     int n = cache[dev].load(std::memory_order_relaxed);
+     if (n == 0) {
+          if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) {
+               cudaGetLastError();
+               n = 148;
+          }
+          cache[dev].store(n, std::memory_order_relaxed);
+     }
+     return n;
+}
+
 static std::atomic<uint64_t> g_max_grid{0};
 uint64_t grid_cap(uint64_t natural)
 {

@@ -18,6 +18,8 @@ void count_launch(unsigned n = 1);
 // grid-size cap of the persistent kernels: `natural` unless hiqk_debug_set_max_grid() lowered it (tests use
 // that to drive the multi-iteration / prefetch paths on small slabs)
 uint64_t grid_cap(uint64_t natural);
+// multiprocessors of the current device (cached per device; 148 on B200): persistent grids are multiples of it
+int num_sms();
 
 struct DiagProg;
 // host builders of the batched-diagonal program (defined in stream_kernels.cu)

@@ -76,7 +76,7 @@ extern "C" int hiqk_microbench(int what, int iters, double* out_value)
           HIQ_CUDA(cudaMemset(src, 0, n * sizeof(double2)));
           for (int r = 0; r < iters + 2; ++r) {
                cudaEventRecord(e0);
-               mb_copy_kernel<<<kNumSMs * 32, 256>>>(src, dst, n);
+               mb_copy_kernel<<<num_sms() * 32, 256>>>(src, dst, n);
                cudaEventRecord(e1);
                HIQ_CUDA(cudaEventSynchronize(e1));
                float ms;
@@ -93,7 +93,7 @@ extern "C" int hiqk_microbench(int what, int iters, double* out_value)
           double* out = nullptr;
           HIQ_CUDA(cudaMalloc(&out, sizeof(double)));
           const int inner = 4096;
-          const unsigned grid = kNumSMs * 8;
+          const unsigned grid = num_sms() * 8;
           for (int r = 0; r < iters + 2; ++r) {
                cudaEventRecord(e0);
                if (what == HIQK_MB_DFMA_TFLOPS) mb_dfma_kernel<<<grid, 256>>>(out, inner, 0.999999, 1e-7);

@@ -28,7 +28,7 @@ constexpr int kOpMaxPartials = 4096;  // per component; the workspace holds 2 x 
 static unsigned op_grid(uint64_t items, int per_thread)
 {
      const uint64_t need = (items + static_cast<uint64_t>(kOpThreads) * per_thread - 1) / (static_cast<uint64_t>(kOpThreads) * per_thread);
-     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * 8 * 2);
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(num_sms()) * 8 * 2);
      return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(need, cap)));
 }
 

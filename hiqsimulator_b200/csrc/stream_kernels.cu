@@ -22,7 +22,7 @@ static unsigned stream_grid(uint64_t items, int per_thread = 4)
 {
      const uint64_t need = (items + static_cast<uint64_t>(kStreamThreads) * per_thread - 1) /
                            (static_cast<uint64_t>(kStreamThreads) * per_thread);
-     const uint64_t cap = grid_cap(static_cast<uint64_t>(kNumSMs) * 8 * 4);  // 8 CTAs/SM resident, 4 waves
+     const uint64_t cap = grid_cap(static_cast<uint64_t>(num_sms()) * 8 * 4);  // 8 CTAs/SM resident, 4 waves
      return static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(need, cap)));
 }
 
@@ -424,7 +424,7 @@ extern "C" int hiqk_apply_diag_batch(void* slab, int L, const hiqk_diag_op* ops,
                if ((u >> b) & 1) o |= 1ull << upos[b];
           p.uoff[u] = o;
      }
-     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_chunks, grid_cap(static_cast<uint64_t>(kNumSMs) * 4 * 8)));
+     const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_chunks, grid_cap(static_cast<uint64_t>(num_sms()) * 4 * 8)));
      diag_batch_kernel<<<grid, kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
      count_launch();
      return check_launch("diag_batch_kernel");

@@ -140,7 +140,7 @@ extern "C" int hiqk_swap_move(void* slab, int L, int q, const int* slots, int n_
                if ((peer_pats[k] >> i) & 1ull) p.pat_bits[k] |= 1ull << sorted[i];
      }
      const uint64_t need = (count + static_cast<uint64_t>(kSwapThreads) * 4 - 1) / (static_cast<uint64_t>(kSwapThreads) * 4);
-     const uint64_t per_peer = std::max<uint64_t>(1, grid_cap(static_cast<uint64_t>(kNumSMs) * 8) / n_peers);
+     const uint64_t per_peer = std::max<uint64_t>(1, grid_cap(static_cast<uint64_t>(num_sms()) * 8) / n_peers);
      dim3 grid(static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(need, per_peer))), static_cast<unsigned>(n_peers));
      if (pack) swap_move_kernel<true><<<grid, kSwapThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
      else swap_move_kernel<false><<<grid, kSwapThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
@@ -186,7 +186,7 @@ extern "C" int hiqk_swap_p2p(void* local, void* const* peer_slabs, int n_peers, 
      }
      if (total == 0) return HIQ_OK;
      const uint64_t need = (total + static_cast<uint64_t>(kSwapThreads) * 4 - 1) / (static_cast<uint64_t>(kSwapThreads) * 4);
-     const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(need, grid_cap(static_cast<uint64_t>(kNumSMs) * 8))));
+     const unsigned grid = static_cast<unsigned>(std::max<uint64_t>(1, std::min<uint64_t>(need, grid_cap(static_cast<uint64_t>(num_sms()) * 8))));
      swap_p2p_kernel<<<grid, kSwapThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
      count_launch();
      return check_launch("swap_p2p_kernel");

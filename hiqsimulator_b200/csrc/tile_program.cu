@@ -593,7 +593,7 @@ extern "C" int hiqk_apply_tile_program(void* slab, int L, int n_steps, const hiq
                cudaFuncSetAttribute(tile_program_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
                attr = true;
           }
-          const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, grid_cap(static_cast<uint64_t>(kNumSMs) * 4)));
+          const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, grid_cap(static_cast<uint64_t>(num_sms()) * 4)));
           tile_program_kernel<11><<<grid, 1 << 7, smem, st>>>(p);
      }
      else {
@@ -602,7 +602,7 @@ extern "C" int hiqk_apply_tile_program(void* slab, int L, int n_steps, const hiq
                cudaFuncSetAttribute(tile_program_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
                attr = true;
           }
-          const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, grid_cap(static_cast<uint64_t>(kNumSMs) * 2)));
+          const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, grid_cap(static_cast<uint64_t>(num_sms()) * 2)));
           tile_program_kernel<12><<<grid, 1 << 8, smem, st>>>(p);
      }
      count_launch();
