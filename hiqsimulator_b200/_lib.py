@@ -71,6 +71,7 @@ _SIGNATURES = {
     "hiqk_swap_unpack": (C.c_int, [_vp, C.c_int, C.c_int, _ip, _u64, _u64, _u64, _vp, _vp]),
     "hiqk_swap_p2p": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, C.c_int, _ip, C.POINTER(_u64), _u64, C.POINTER(_u64),
                                C.POINTER(_u64), _vp]),
+    "hiqk_dense_is_monomial": (C.c_int, [C.c_int, _dp]),
     "hiqk_tile_program_fits": (C.c_int, [C.c_int, C.c_int, C.POINTER(TileStep)]),
     "hiqk_apply_tile_program": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(TileStep), _vp]),
     "hiqk_axpy_masked": (C.c_int, [_vp, _vp, C.c_int, _u64, _u64, C.c_double, C.c_double, _vp]),

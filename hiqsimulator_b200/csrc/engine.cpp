@@ -449,7 +449,8 @@ void Engine::execute(const Descriptor& d)
                cand.d = d;
                cand.variant = variant;
                cand.direct = direct;
-               cand.full = hiqk_dense_direct_mixing_bits(d.k, reinterpret_cast<const double*>(d.payload.data())) >= 4;
+               cand.full = hiqk_dense_direct_mixing_bits(d.k, reinterpret_cast<const double*>(d.payload.data())) >= 4 &&
+                           !hiqk_dense_is_monomial(d.k, reinterpret_cast<const double*>(d.payload.data()));
                // the diagonals queued so far precede this gate; more than one launch carries go out as batched passes first
                const size_t cap = tile_enabled_ ? HIQK_TILE_MAX_OPS : HIQK_MAX_DIAG_OPS;
                if (pending_.size() > cap) flush_pending(cap);

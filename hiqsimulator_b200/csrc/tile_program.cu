@@ -19,6 +19,7 @@
 //    tile) and kept in shared memory; the part of a selector that depends on the tile is computed once per tile.
 #include <algorithm>
 #include <array>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -34,7 +35,7 @@ namespace hiq {
 
 constexpr int kTileMaxSteps = HIQK_TILE_MAX_STEPS;
 constexpr int kTileMaxOps = HIQK_TILE_MAX_OPS;  // diagonal ops per gate
-constexpr int kTileLutEntries = 512;            // table pool shared by all ops of a launch (8 KB of shared memory)
+constexpr int kTileLutEntries = 1024;           // table pool shared by all ops of a launch (shared memory holds what is used)
 // per-thread context in shared memory, computed once per launch: the physical tile position of the thread's tuple of
 // every gate (u32) and, per diagonal op, the selector bits its tuple base contributes (u8)
 constexpr int kTileCtxBytes = kTileMaxSteps * (4 + kTileMaxOps);
@@ -42,6 +43,14 @@ constexpr int kTileCtxBytes = kTileMaxSteps * (4 + kTileMaxOps);
 struct TileStepDesc {
      int ks;                          // mixing bits, 1..4 (4 = full product, three-multiplication form)
      int n_ops, n_e;                  // diagonal ops applied to a tuple before the gate; the last n_e touch its targets
+     int sel_off;                     // first selector-byte row of this gate's ops in shared memory
+     int n_t;                         // the first n_t ops have every slot outside the tile: one factor per TILE
+     int n_em;                        // ... and the last n_em of those touch MIXING bits (a factor per element; the other
+                                      // class-E ops only see select bits: one factor per block of the reduced product)
+     int in_mask;                     // tuple-block bits that are REAL select bits of the gate (the others pad the tuple to 16)
+     int n_in, n_out;                 // select bits inside the tile / outside it (the latter choose the block per TILE)
+     uint8_t out_slot[4];             // slab slots of the outside select bits, in matrix-bit order
+     uint8_t mono_row[16];            // monomial form (ks == 0): the one row that column c feeds; its coefficient is m[c]
      uint8_t tpos[4];                 // tile-local target positions, ascending (bit deposit of the thread index)
      uint16_t ploff[16];              // physical (swizzled) tile offset of tuple element c
      uint16_t lut_off[kTileMaxOps];   // first table entry of op j in the pool
@@ -63,6 +72,7 @@ struct TileParams {
      TileStepDesc step[kTileMaxSteps];
      const double2* lut;    // table pool in device memory (staged by the launcher), copied to shared memory at kernel start
      int n_lut;
+     int lut_pad;           // table pool entries reserved in shared memory (n_lut rounded up)
      double2 m[kTileMaxSteps][256];
      double msum[kTileMaxSteps][256];
 };
@@ -73,58 +83,152 @@ __device__ __forceinline__ uint32_t tile_phys(uint32_t j, const uint32_t (&mask)
      return j ^ ((__popc(j & mask[0]) & 1u) | ((__popc(j & mask[1]) & 1u) << 1) | ((__popc(j & mask[2]) & 1u) << 2));
 }
 
-template <int S, int THREADS>
-__device__ __forceinline__ void tile_step(const TileParams& p, double2* __restrict__ tile, const double2* __restrict__ lut,
-                                          const uint32_t* __restrict__ ctx_pb, const uint8_t* __restrict__ ctx_sel,
-                                          const uint32_t (&selh)[kTileMaxSteps][kTileMaxOps])
+// One gate applied to this thread's tuple, reduced product (KS < 4 mixing bits: 2^(4-KS) independent blocks).  The 16
+// elements are gathered first (sixteen independent shared-memory loads in flight), then the diagonal factors: ops that
+// avoid the targets give one scalar per tuple; class-E ops that only see select bits give one factor per BLOCK, folded
+// into that scalar (2^(4-KS) products instead of 16); class-E ops on mixing bits are applied element by element.
+template <int S, int THREADS, int KS>
+__device__ __forceinline__ void tile_step_blocks(const TileParams& p, double2* __restrict__ tile, const double2* __restrict__ lut,
+                                                 const uint32_t* __restrict__ ctx_pb, const uint8_t* __restrict__ ctx_sel,
+                                                 const uint32_t (&selh)[kTileMaxSteps][kTileMaxOps], const double2 (&stile)[kTileMaxSteps], uint64_t tbase)
 {
+     constexpr int DS = 1 << KS;
+     constexpr int NB = 16 / DS;
      const TileStepDesc& d = p.step[S];
      const int tid = threadIdx.x;
      const uint32_t pb = ctx_pb[S * THREADS + tid];
-     const uint8_t* my_sel = ctx_sel + (S * kTileMaxOps) * THREADS + tid;  // op j: my_sel[j * THREADS]
+     const uint8_t* my_sel = ctx_sel + d.sel_off * THREADS + tid;  // op j: my_sel[j * THREADS]
      double2 in[16];
 #pragma unroll
      for (int c = 0; c < 16; ++c) in[c] = tile[pb ^ d.ploff[c]];
      if (d.n_ops) {
           const int n_s = d.n_ops - d.n_e;
-          double2 sc = make_double2(1.0, 0.0);
-          for (int j = 0; j < n_s; ++j) sc = cmul(sc, lut[d.lut_off[j] + (selh[S][j] | my_sel[j * THREADS])]);
-          if (d.n_e == 0) {
+          const int n_es = d.n_e - d.n_em;  // class-E ops that only see select bits
+          double2 sc = stile[S];  // product of the ops that only see slots outside the tile
+          for (int j = d.n_t; j < n_s; ++j) sc = cmul(sc, lut[d.lut_off[j] + (selh[S][j] | my_sel[j * THREADS])]);
+          double2 f[NB];
 #pragma unroll
-               for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], sc);
+          for (int blk = 0; blk < NB; ++blk) f[blk] = sc;
+          for (int j = n_s; j < n_s + n_es; ++j) {
+               const uint32_t sel0 = d.lut_off[j] + (selh[S][j] | my_sel[j * THREADS]);
+#pragma unroll
+               for (int blk = 0; blk < NB; ++blk) f[blk] = cmul(f[blk], lut[sel0 + d.esel[j][blk * DS]]);
           }
-          else {
-               for (int j = n_s; j < d.n_ops; ++j) {
-                    const uint32_t sel0 = selh[S][j] | my_sel[j * THREADS];
+          for (int j = n_s + n_es; j < d.n_ops; ++j) {
+               const uint32_t sel0 = d.lut_off[j] + (selh[S][j] | my_sel[j * THREADS]);
 #pragma unroll
-                    for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], lut[d.lut_off[j] + (sel0 | d.esel[j][c])]);
-               }
-               if (n_s) {
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], sc);
-               }
+               for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], lut[sel0 + d.esel[j][c]]);
           }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], f[c >> KS]);
      }
-     auto store = [&](int b, double2 v) { tile[pb ^ d.ploff[b]] = v; };
-     switch (d.ks) {
-          case 1: apply_rows<4, 1>(in, p.m[S], store); break;
-          case 2: apply_rows<4, 2>(in, p.m[S], store); break;
-          case 3: apply_rows<4, 3>(in, p.m[S], store); break;
-          default: apply_rows_3m(in, p.m[S], p.msum[S], store); break;
+     // The select bits of the gate pick the 2^KS x 2^KS block that acts on a tuple block: those inside the tile are part
+     // of the tuple (block blk of the tuple <-> block blk & in_mask of the matrix), those outside it are the same for the
+     // whole tile (tbase) — so only MIXING bits have to be tile bits, and a run of gates needs a much smaller tile.
+     uint32_t osel = 0;
+#pragma unroll
+     for (int i = 0; i < 3; ++i)
+          if (i < d.n_out) osel |= static_cast<uint32_t>((tbase >> d.out_slot[i]) & 1ull) << i;
+     const uint32_t obase = osel << d.n_in;
+#pragma unroll
+     for (int blk = 0; blk < NB; ++blk) {
+          const double2* __restrict__ mb = p.m[S] + ((blk & d.in_mask) | obase) * (DS * 17);
+#pragma unroll
+          for (int r = 0; r < DS; ++r) {
+               double2 acc = make_double2(0.0, 0.0);
+#pragma unroll
+               for (int j = 0; j < DS; ++j) cmac(acc, mb[r * 16 + j], in[blk * DS + j]);
+               tile[pb ^ d.ploff[blk * DS + r]] = acc;
+          }
      }
 }
 
-template <int T>
-__global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : 4) tile_program_kernel(const __grid_constant__ TileParams p)
+// Full 16 x 16 product (three-multiplication form): the whole tuple is live.
+template <int S, int THREADS>
+__device__ __forceinline__ void tile_step_full(const TileParams& p, double2* __restrict__ tile, const double2* __restrict__ lut,
+                                               const uint32_t* __restrict__ ctx_pb, const uint8_t* __restrict__ ctx_sel,
+                                               const uint32_t (&selh)[kTileMaxSteps][kTileMaxOps], const double2 (&stile)[kTileMaxSteps])
+{
+     const TileStepDesc& d = p.step[S];
+     const int tid = threadIdx.x;
+     const uint32_t pb = ctx_pb[S * THREADS + tid];
+     const uint8_t* my_sel = ctx_sel + d.sel_off * THREADS + tid;
+     double2 in[16];
+#pragma unroll
+     for (int c = 0; c < 16; ++c) in[c] = tile[pb ^ d.ploff[c]];
+     if (d.n_ops) {
+          const int n_s = d.n_ops - d.n_e;
+          double2 sc = stile[S];
+          for (int j = d.n_t; j < n_s; ++j) sc = cmul(sc, lut[d.lut_off[j] + (selh[S][j] | my_sel[j * THREADS])]);
+          for (int j = n_s; j < d.n_ops; ++j) {
+               const uint32_t sel0 = selh[S][j] | my_sel[j * THREADS];
+#pragma unroll
+               for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], lut[d.lut_off[j] + (sel0 | d.esel[j][c])]);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], sc);
+     }
+     apply_rows_3m(in, p.m[S], p.msum[S], [&](int b, double2 v) { tile[pb ^ d.ploff[b]] = v; });
+}
+
+// Monomial matrix (one nonzero per row and column: products of X / Y / Z / phase gates, fused permutations): no products to
+// sum — element c goes to row mono_row[c] times its coefficient.
+template <int S, int THREADS>
+__device__ __forceinline__ void tile_step_mono(const TileParams& p, double2* __restrict__ tile, const double2* __restrict__ lut,
+                                               const uint32_t* __restrict__ ctx_pb, const uint8_t* __restrict__ ctx_sel,
+                                               const uint32_t (&selh)[kTileMaxSteps][kTileMaxOps], const double2 (&stile)[kTileMaxSteps])
+{
+     const TileStepDesc& d = p.step[S];
+     const int tid = threadIdx.x;
+     const uint32_t pb = ctx_pb[S * THREADS + tid];
+     const uint8_t* my_sel = ctx_sel + d.sel_off * THREADS + tid;
+     double2 in[16];
+#pragma unroll
+     for (int c = 0; c < 16; ++c) in[c] = tile[pb ^ d.ploff[c]];
+     if (d.n_ops) {
+          const int n_s = d.n_ops - d.n_e;
+          double2 sc = stile[S];
+          for (int j = d.n_t; j < n_s; ++j) sc = cmul(sc, lut[d.lut_off[j] + (selh[S][j] | my_sel[j * THREADS])]);
+          for (int j = n_s; j < d.n_ops; ++j) {
+               const uint32_t sel0 = selh[S][j] | my_sel[j * THREADS];
+#pragma unroll
+               for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], lut[d.lut_off[j] + (sel0 | d.esel[j][c])]);
+          }
+#pragma unroll
+          for (int c = 0; c < 16; ++c) in[c] = cmul(in[c], sc);
+     }
+#pragma unroll
+     for (int c = 0; c < 16; ++c) tile[pb ^ d.ploff[d.mono_row[c]]] = cmul(p.m[S][c], in[c]);
+}
+
+template <int S, int THREADS, bool FULL>
+__device__ __forceinline__ void tile_step(const TileParams& p, double2* __restrict__ tile, const double2* __restrict__ lut,
+                                          const uint32_t* __restrict__ ctx_pb, const uint8_t* __restrict__ ctx_sel,
+                                          const uint32_t (&selh)[kTileMaxSteps][kTileMaxOps], const double2 (&stile)[kTileMaxSteps], uint64_t tbase)
+{
+     // two forms: 4 x 4 blocks (gates with at most two mixing bits; a lone mixing bit takes a select or padding bit as
+     // its partner) and the full 16 x 16 product (everything else)
+     if (p.step[S].ks == 0) tile_step_mono<S, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh, stile);
+     else if (p.step[S].ks <= 2) tile_step_blocks<S, THREADS, 2>(p, tile, lut, ctx_pb, ctx_sel, selh, stile, tbase);
+     else if constexpr (FULL) tile_step_full<S, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh, stile);
+}
+
+// FULL = false: no gate of the run is a full 16 x 16 product (the code of that form is left out).
+// NBUF = 2: the tile of the NEXT iteration is copied into a second buffer (cp.async, its own commit group) while the gates
+// run on the current one, so the HBM latency and most of the transfer hide behind the arithmetic; with one buffer the CTAs
+// of an SM fall into lock-step (all loading, then all computing) and the pass costs memory time PLUS compute time.
+// Shared memory (dynamic): tiles | table pool (lut_pad entries) | tuple positions [gate][thread] | selector bytes [op][thread].
+template <int T, bool FULL, int NBUF>
+__global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : (NBUF == 2 ? 3 : 4)) tile_program_kernel(const __grid_constant__ TileParams p)
 {
      constexpr int THREADS = 1 << (T - 4);
      static_assert(THREADS >= kTileMaxSteps * kTileMaxOps, "one thread per (gate, op) computes the per-tile selectors");
      extern __shared__ double2 dyn_smem[];
-     double2* tile = dyn_smem;                                         // 2^T amplitudes
-     double2* lut = dyn_smem + (1 << T);                               // table pool
-     uint32_t* ctx_pb = reinterpret_cast<uint32_t*>(lut + kTileLutEntries);   // [gate][thread]
-     uint8_t* ctx_sel = reinterpret_cast<uint8_t*>(ctx_pb + kTileMaxSteps * THREADS);  // [gate][op][thread]
+     double2* lut = dyn_smem + NBUF * (1 << T);                                // table pool
+     uint32_t* ctx_pb = reinterpret_cast<uint32_t*>(lut + p.lut_pad);          // [gate][thread]
+     uint8_t* ctx_sel = reinterpret_cast<uint8_t*>(ctx_pb + p.n_steps * THREADS);  // [op of the run][thread]
      __shared__ uint32_t selh[kTileMaxSteps][kTileMaxOps];
+     __shared__ double2 stile[kTileMaxSteps];
      const int tid = threadIdx.x;
      for (int i = tid; i < p.n_lut; i += THREADS) lut[i] = p.lut[i];
      // this thread's slice of the tile in the load / store phases: positions tid + i * THREADS
@@ -148,15 +252,33 @@ __global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : 4) tile_program_ke
 #pragma unroll
                for (int l = 0; l < 5; ++l)
                     if (d.lpos[j][l] != 0xFF) sel |= ((base >> d.lpos[j][l]) & 1u) << l;
-               ctx_sel[(s * kTileMaxOps + j) * THREADS + tid] = static_cast<uint8_t>(sel);
+               ctx_sel[(d.sel_off + j) * THREADS + tid] = static_cast<uint8_t>(sel);
           }
      }
-     __syncthreads();
-     for (uint64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
-          const uint64_t tbase = insert_zero_bits(t, p.outer) << p.lo;
-          double2* g = p.psi + tbase + goff_t;
+     auto tile_base = [&](uint64_t t) { return insert_zero_bits(t, p.outer) << p.lo; };
+     auto issue_load = [&](uint64_t t, double2* buf) {
+          const double2* g = p.psi + tile_base(t) + goff_t;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) cp_async16(&tile[pt ^ p.pi[i]], g + p.ioff[i]);
+          for (int i = 0; i < 16; ++i) cp_async16(&buf[pt ^ p.pi[i]], g + p.ioff[i]);
+     };
+     uint64_t t = blockIdx.x;
+     int cur = 0;
+     if (NBUF == 2 && t < p.n_tiles) {
+          issue_load(t, dyn_smem);
+          cp_async_commit();
+     }
+     __syncthreads();  // table pool and per-thread context are in place
+     for (; t < p.n_tiles; t += gridDim.x) {
+          double2* tile = dyn_smem + cur * (1 << T);
+          const uint64_t tbase = tile_base(t);
+          if (NBUF == 2) {
+               // the other buffer was stored (and its reads fenced by the barrier that ended the previous iteration)
+               if (t + gridDim.x < p.n_tiles) issue_load(t + gridDim.x, dyn_smem + (cur ^ 1) * (1 << T));
+               cp_async_commit();
+          }
+          else {
+               issue_load(t, tile);
+          }
           if (tid < kTileMaxSteps * kTileMaxOps) {
                const int s = tid / kTileMaxOps, j = tid % kTileMaxOps;
                if (s < p.n_steps && j < p.step[s].n_ops) {
@@ -166,25 +288,42 @@ __global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : 4) tile_program_ke
                     selh[s][j] = sel;
                }
           }
-          cp_async_wait_all();
+          if (tid >= THREADS - kTileMaxSteps) {
+               // one thread per gate: the factors of the ops that only see slots outside the tile, once per tile
+               const int s = tid - (THREADS - kTileMaxSteps);
+               if (s < p.n_steps) {
+                    double2 f = make_double2(1.0, 0.0);
+                    for (int j = 0; j < p.step[s].n_t; ++j) {
+                         uint32_t sel = 0;
+#pragma unroll
+                         for (int l = 0; l < 5; ++l) sel |= static_cast<uint32_t>((tbase >> p.step[s].outer[j][l]) & 1ull) << l;
+                         f = cmul(f, lut[p.step[s].lut_off[j] + sel]);
+                    }
+                    stile[s] = f;
+               }
+          }
+          if (NBUF == 2) cp_async_wait_group<1>();  // everything but the copies of the next tile has landed
+          else cp_async_wait_all();
           __syncthreads();
-          tile_step<0, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
+          tile_step<0, THREADS, FULL>(p, tile, lut, ctx_pb, ctx_sel, selh, stile, tbase);
           __syncthreads();
           if (p.n_steps > 1) {
-               tile_step<1, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
+               tile_step<1, THREADS, FULL>(p, tile, lut, ctx_pb, ctx_sel, selh, stile, tbase);
                __syncthreads();
           }
           if (p.n_steps > 2) {
-               tile_step<2, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
+               tile_step<2, THREADS, FULL>(p, tile, lut, ctx_pb, ctx_sel, selh, stile, tbase);
                __syncthreads();
           }
           if (p.n_steps > 3) {
-               tile_step<3, THREADS>(p, tile, lut, ctx_pb, ctx_sel, selh);
+               tile_step<3, THREADS, FULL>(p, tile, lut, ctx_pb, ctx_sel, selh, stile, tbase);
                __syncthreads();
           }
+          double2* g = p.psi + tbase + goff_t;
 #pragma unroll
           for (int i = 0; i < 16; ++i) g[p.ioff[i]] = tile[pt ^ p.pi[i]];
-          __syncthreads();  // the next tile's copies overwrite the tile
+          __syncthreads();  // this buffer is refilled next (one buffer: by the next tile; two: by the tile after the next)
+          if (NBUF == 2) cur ^= 1;
      }
 }
 
@@ -194,9 +333,14 @@ __global__ void __launch_bounds__(1 << (T - 4), T >= 12 ? 2 : 4) tile_program_ke
 namespace {
 
 struct PlannedStep {
-     int lp[4];            // tile-local positions of the matrix bits (mixing bits first)
-     int ks;
-     double m[2 * 256];    // 16 x 16 complex, index bits in the order of lp
+     int ks = 0;           // 2 = block form (4 x 4 blocks), 4 = full product
+     int n_in = 0;         // select bits inside the tile
+     int n_out = 0;        // select bits outside the tile
+     int lp[4];            // tile positions of the thread's tuple bits: mixing bits, inside select bits, padding
+     int out_slot[4];      // slab slots of the outside select bits
+     int k = 0;
+     int order[5];         // matrix bits of the gate in the planned order: mixing, inside selects, outside selects
+     double m[2 * 256];    // the gate's matrix in that bit order, leading dimension 16
 };
 
 struct TilePlan {
@@ -226,10 +370,27 @@ int tile_min_lo()
      return v;
 }
 
-// smallest supported tile that holds at least tile_min_lo() low slots and every target of the run
+bool is_monomial(int k, const double* m)
+{
+     const int d = 1 << k;
+     for (int b = 0; b < d; ++b) {
+          int in_row = 0, in_col = 0;
+          for (int c = 0; c < d; ++c) {
+               in_row += (m[2 * (b * d + c)] != 0.0 || m[2 * (b * d + c) + 1] != 0.0) ? 1 : 0;
+               in_col += (m[2 * (c * d + b)] != 0.0 || m[2 * (c * d + b) + 1] != 0.0) ? 1 : 0;
+          }
+          if (in_row != 1 || in_col != 1) return false;
+     }
+     return true;
+}
+
+// smallest supported tile that holds at least tile_min_lo() low slots and every MIXING bit of the run: a select bit (an
+// index bit of the matrix that no nonzero entry mixes) only chooses which block acts on the mixing bits, so it may stay
+// outside the tile — there it is the same for the whole tile
 bool choose_tile(int L, int n_steps, const hiqk_tile_step* steps, TilePlan& pl, std::string& why)
 {
      uint64_t u = 0;
+     pl.steps.assign(n_steps, PlannedStep());
      for (int s = 0; s < n_steps; ++s) {
           const hiqk_tile_step& st = steps[s];
           if (st.k < 1 || st.k > 4 || !st.matrix) {
@@ -244,7 +405,15 @@ bool choose_tile(int L, int n_steps, const hiqk_tile_step* steps, TilePlan& pl, 
                }
                seen |= 1ull << st.slots[l];
           }
-          u |= seen;
+          PlannedStep& ps = pl.steps[s];
+          ps.k = st.k;
+          const int raw = hiqk_dense_block_shape(st.k, st.matrix, ps.order);  // mixing bits first in ps.order
+          // block form when at most two bits mix (the first two bits of the order span the blocks: a lone mixing bit is
+          // joined by a select bit, or by a padding bit of the tile when the gate has one target); full product otherwise
+          ps.ks = raw <= 2 ? 2 : 4;
+          if (raw > 2 && is_monomial(st.k, st.matrix)) ps.ks = 0;  // monomial form: as wide as the full one, no arithmetic to speak of
+          const int n_block = ps.ks == 2 ? std::min(2, st.k) : st.k;
+          for (int i = 0; i < n_block; ++i) u |= 1ull << st.slots[ps.order[i]];
      }
      static const int min_t = [] {
           const char* e = std::getenv("HIQ_TILE_MIN_T");  // measurements: force the 2^12 tile
@@ -263,59 +432,89 @@ bool choose_tile(int L, int n_steps, const hiqk_tile_step* steps, TilePlan& pl, 
                if ((u >> s) & 1) pl.hi[pl.n_hi++] = s;
           return true;
      }
-     why = "the targets of the run do not fit a 2^12 tile with 4 low slots";
+     why = "the mixing bits of the run do not fit a 2^12 tile with 4 low slots";
      return false;
 }
 
 void plan_steps(int n_steps, const hiqk_tile_step* steps, TilePlan& pl)
 {
-     pl.steps.resize(n_steps);
      for (int s = 0; s < n_steps; ++s) {
           const hiqk_tile_step& st = steps[s];
-          int lp[4];
-          uint32_t used = 0;
-          for (int l = 0; l < st.k; ++l) {
-               lp[l] = local_pos(pl, st.slots[l]);
-               used |= 1u << lp[l];
-          }
-          // k < 4: add select bits the matrix does not mix — tile positions >= 3 first, so the gathers keep the three low
-          // address bits for the lanes of a quarter warp
-          int k = st.k;
-          for (int pos = 3; pos < pl.T && k < 4; ++pos)
-               if (!((used >> pos) & 1)) {
-                    lp[k++] = pos;
-                    used |= 1u << pos;
-               }
-          for (int pos = 0; pos < 3 && k < 4; ++pos)
-               if (!((used >> pos) & 1)) {
-                    lp[k++] = pos;
-                    used |= 1u << pos;
-               }
-          // I (x) M on the added high index bits
-          const int d0 = 1 << st.k;
-          std::vector<double> full(2 * 256, 0.0);
-          for (int b = 0; b < 16; ++b)
-               for (int c = 0; c < 16; ++c)
-                    if ((b >> st.k) == (c >> st.k)) {
-                         full[2 * (b * 16 + c)] = st.matrix[2 * ((b & (d0 - 1)) * d0 + (c & (d0 - 1)))];
-                         full[2 * (b * 16 + c) + 1] = st.matrix[2 * ((b & (d0 - 1)) * d0 + (c & (d0 - 1))) + 1];
-                    }
-          int order[5];
           PlannedStep& ps = pl.steps[s];
-          ps.ks = hiqk_dense_block_shape(4, full.data(), order);
-          int map[16];
-          for (int x = 0; x < 16; ++x) {
-               int o = 0;
-               for (int i = 0; i < 4; ++i)
-                    if ((x >> i) & 1) o |= 1 << order[i];
-               map[x] = o;
-          }
-          for (int i = 0; i < 4; ++i) ps.lp[i] = lp[order[i]];
-          for (int b = 0; b < 16; ++b)
-               for (int c = 0; c < 16; ++c) {
-                    ps.m[2 * (b * 16 + c)] = full[2 * (map[b] * 16 + map[c])];
-                    ps.m[2 * (b * 16 + c) + 1] = full[2 * (map[b] * 16 + map[c]) + 1];
+          const int n_block = ps.ks == 2 ? std::min(2, st.k) : st.k;  // gate bits that span a block
+          // gate bits in the planned order: block bits, select bits inside the tile (low slots, block bits of other gates
+          // of the run), select bits outside it
+          int order[5], n = 0;
+          for (int i = 0; i < n_block; ++i) order[n++] = ps.order[i];
+          ps.n_in = ps.n_out = 0;
+          for (int i = n_block; i < st.k; ++i)
+               if (local_pos(pl, st.slots[ps.order[i]]) >= 0) {
+                    order[n++] = ps.order[i];
+                    ++ps.n_in;
                }
+          for (int i = n_block; i < st.k; ++i)
+               if (local_pos(pl, st.slots[ps.order[i]]) < 0) {
+                    ps.out_slot[ps.n_out++] = st.slots[ps.order[i]];
+                    order[n++] = ps.order[i];
+               }
+          for (int i = 0; i < st.k; ++i) ps.order[i] = order[i];
+          // the thread's tuple = four tile bits: block bits (padded to the block width with tile bits the gate does not
+          // touch: identity factors), inside select bits, padding.  Padding prefers tile positions >= 3, so that the
+          // gathers keep the three low address bits for the lanes of a quarter warp.
+          uint32_t used = 0;
+          for (int i = 0; i < st.k; ++i) {
+               const int lp = local_pos(pl, st.slots[i]);
+               if (lp >= 0) used |= 1u << lp;
+          }
+          auto pad = [&] {
+               for (int pos = 3; pos < pl.T; ++pos)
+                    if (!((used >> pos) & 1)) {
+                         used |= 1u << pos;
+                         return pos;
+                    }
+               for (int pos = 0; pos < 3; ++pos)
+                    if (!((used >> pos) & 1)) {
+                         used |= 1u << pos;
+                         return pos;
+                    }
+               return -1;
+          };
+          const int block_width = ps.ks == 2 ? 2 : 4;
+          int nt = 0;
+          for (int i = 0; i < n_block; ++i) ps.lp[nt++] = local_pos(pl, st.slots[order[i]]);
+          const int n_block_pad = block_width - n_block;  // identity factors inside the block
+          for (int i = 0; i < n_block_pad; ++i) ps.lp[nt++] = pad();
+          for (int i = 0; i < ps.n_in; ++i) ps.lp[nt++] = local_pos(pl, st.slots[order[n_block + i]]);
+          while (nt < 4) ps.lp[nt++] = pad();
+          // the matrix over [block bits, block padding, inside selects, outside selects], leading dimension 16:
+          // entry (b, c) = M(gate bits of b, gate bits of c) when the padding bits of b and c agree, else 0
+          const int d0 = 1 << st.k;
+          const int kk = st.k + n_block_pad;  // <= 4
+          std::memset(ps.m, 0, sizeof(ps.m));
+          auto gate_index = [&](int x) {  // planned index -> (index into the caller's matrix, padding bits)
+               int o = 0;
+               for (int i = 0; i < n_block; ++i)
+                    if ((x >> i) & 1) o |= 1 << order[i];
+               for (int i = n_block; i < st.k; ++i)
+                    if ((x >> (i + n_block_pad)) & 1) o |= 1 << order[i];
+               return o;
+          };
+          const int pad_mask = ((1 << n_block_pad) - 1) << n_block;
+          for (int b = 0; b < (1 << kk); ++b)
+               for (int c = 0; c < (1 << kk); ++c) {
+                    if ((b & pad_mask) != (c & pad_mask)) continue;
+                    const int gb = gate_index(b), gc = gate_index(c);
+                    ps.m[2 * (b * 16 + c)] = st.matrix[2 * (gb * d0 + gc)];
+                    ps.m[2 * (b * 16 + c) + 1] = st.matrix[2 * (gb * d0 + gc) + 1];
+               }
+          if (ps.ks != 2 && kk < 4) {
+               // full form of a 3-target gate: the fourth tuple bit is padding — replicate the 8 x 8 matrix on its two values
+               for (int b = 0; b < 8; ++b)
+                    for (int c = 0; c < 8; ++c) {
+                         ps.m[2 * ((b + 8) * 16 + c + 8)] = ps.m[2 * (b * 16 + c)];
+                         ps.m[2 * ((b + 8) * 16 + c + 8) + 1] = ps.m[2 * (b * 16 + c) + 1];
+                    }
+          }
      }
 }
 
@@ -420,11 +619,15 @@ int fill_params(TileParams& p, double2* lut_host, void* slab, int L, int n_steps
           p.ioff[i] = o;
           p.pi[i] = static_cast<uint16_t>(host_phys(static_cast<uint32_t>(i) << (T - 4), pl.swz_mask));
      }
-     int lut_used = 0;
+     int lut_used = 0, ops_total = 0;
      for (int s = 0; s < n_steps; ++s) {
           const PlannedStep& ps = pl.steps[s];
           TileStepDesc& d = p.step[s];
           d.ks = ps.ks;
+          d.n_in = ps.n_in;
+          d.n_out = ps.n_out;
+          d.in_mask = (1 << ps.n_in) - 1;
+          for (int i = 0; i < 4; ++i) d.out_slot[i] = static_cast<uint8_t>(i < ps.n_out ? ps.out_slot[i] : 63);
           int sorted[4] = {ps.lp[0], ps.lp[1], ps.lp[2], ps.lp[3]};
           std::sort(sorted, sorted + 4);
           uint32_t tm = 0;
@@ -440,6 +643,14 @@ int fill_params(TileParams& p, double2* lut_host, void* slab, int L, int n_steps
           }
           std::memcpy(p.m[s], ps.m, sizeof(double) * 2 * 256);
           for (int i = 0; i < 256; ++i) p.msum[s][i] = ps.m[2 * i] + ps.m[2 * i + 1];
+          if (ps.ks == 0) {
+               for (int c = 0; c < 16; ++c)
+                    for (int b = 0; b < 16; ++b)
+                         if (ps.m[2 * (b * 16 + c)] != 0.0 || ps.m[2 * (b * 16 + c) + 1] != 0.0) {
+                              d.mono_row[c] = static_cast<uint8_t>(b);
+                              p.m[s][c] = make_double2(ps.m[2 * (b * 16 + c)], ps.m[2 * (b * 16 + c) + 1]);
+                         }
+          }
           // diagonal ops: the ones that avoid the gate's (padded) targets first, class E last
           const hiqk_tile_step& st = steps[s];
           if (st.n_pre < 0 || st.n_pre > kTileMaxOps || (st.n_pre && !st.pre)) {
@@ -447,7 +658,9 @@ int fill_params(TileParams& p, double2* lut_host, void* slab, int L, int n_steps
                return HIQ_ERR_ARG;
           }
           std::vector<int> order;
-          std::vector<bool> is_e(st.n_pre, false);
+          std::vector<bool> is_e(st.n_pre, false), is_em(st.n_pre, false);
+          uint32_t mix_mask = 0;  // tile positions of the block bits (tuple bits 0 .. ks-1; every tuple bit in the monomial form)
+          for (int i = 0; i < (ps.ks == 0 ? 4 : ps.ks) && i < 4; ++i) mix_mask |= 1u << ps.lp[i];
           for (int j = 0; j < st.n_pre; ++j) {
                const hiqk_diag_op& o = st.pre[j];
                if (o.k < 0 || o.k > kMaxTargets) {
@@ -463,14 +676,27 @@ int fill_params(TileParams& p, double2* lut_host, void* slab, int L, int n_steps
                     seen |= 1ull << o.slots[l];
                     const int lp = local_pos(pl, o.slots[l]);
                     if (lp >= 0 && ((tm >> lp) & 1)) is_e[j] = true;
+                    if (lp >= 0 && ((mix_mask >> lp) & 1)) is_em[j] = true;
                }
           }
+          std::vector<bool> is_t(st.n_pre, true);  // every slot outside the tile
           for (int j = 0; j < st.n_pre; ++j)
-               if (!is_e[j]) order.push_back(j);
+               for (int l = 0; l < st.pre[j].k; ++l)
+                    if (local_pos(pl, st.pre[j].slots[l]) >= 0) is_t[j] = false;
           for (int j = 0; j < st.n_pre; ++j)
-               if (is_e[j]) order.push_back(j);
+               if (is_t[j]) order.push_back(j);
+          for (int j = 0; j < st.n_pre; ++j)
+               if (!is_e[j] && !is_t[j]) order.push_back(j);
+          for (int j = 0; j < st.n_pre; ++j)
+               if (is_e[j] && !is_em[j]) order.push_back(j);
+          for (int j = 0; j < st.n_pre; ++j)
+               if (is_em[j]) order.push_back(j);
+          d.n_em = static_cast<int>(std::count(is_em.begin(), is_em.end(), true));
           d.n_ops = st.n_pre;
           d.n_e = static_cast<int>(std::count(is_e.begin(), is_e.end(), true));
+          d.n_t = static_cast<int>(std::count(is_t.begin(), is_t.end(), true));
+          d.sel_off = ops_total;
+          ops_total += st.n_pre;
           for (int jj = 0; jj < st.n_pre; ++jj) {
                const hiqk_diag_op& o = st.pre[order[jj]];
                if (lut_used + (1 << o.k) > kTileLutEntries) {
@@ -497,6 +723,7 @@ int fill_params(TileParams& p, double2* lut_host, void* slab, int L, int n_steps
           }
      }
      p.n_lut = lut_used;
+     p.lut_pad = (lut_used + 15) & ~15;
      return HIQ_OK;
 }
 
@@ -535,15 +762,24 @@ int ring_acquire(LutRing*& ring, int& slot)
      return HIQ_OK;
 }
 
-size_t tile_smem_bytes(int T)
+size_t tile_smem_bytes(int T, int nbuf, const TileParams& p)
 {
-     return sizeof(double2) * ((1u << T) + kTileLutEntries) + static_cast<size_t>(kTileCtxBytes) * (1u << (T - 4));
+     int ops_total = 0;
+     for (int s = 0; s < p.n_steps; ++s) ops_total += p.step[s].n_ops;
+     const size_t threads = 1u << (T - 4);
+     return sizeof(double2) * (static_cast<size_t>(nbuf) * (1u << T) + p.lut_pad) + threads * (4 * p.n_steps + ops_total) + 16;
 }
 
 }  // namespace
 }  // namespace hiq
 
 using namespace hiq;
+
+extern "C" int hiqk_dense_is_monomial(int k, const double* matrix)
+{
+     if (!matrix || k < 1 || k > kMaxTargets) return 0;
+     return is_monomial(k, matrix) ? 1 : 0;
+}
 
 extern "C" int hiqk_tile_program_fits(int L, int n_steps, const hiqk_tile_step* steps)
 {
@@ -560,6 +796,30 @@ extern "C" int hiqk_tile_program_fits(int L, int n_steps, const hiqk_tile_step* 
           }
      }
      if (lut > kTileLutEntries) return 0;
+     if (const char* e = std::getenv("HIQ_TILE_DEBUG"); e && e[0] == '2') {
+          // where the diagonal ops of the run would sit (host-only analysis)
+          plan_steps(n_steps, steps, pl);
+          std::fprintf(stderr, "  plan T=%d lo=%d high slots:", pl.T, pl.lo);
+          for (int i = 0; i < pl.n_hi; ++i) std::fprintf(stderr, " %d", pl.hi[i]);
+          std::fprintf(stderr, "\n");
+          for (int s = 0; s < n_steps; ++s) {
+               uint32_t tm = 0;
+               for (int i = 0; i < 4; ++i) tm |= 1u << pl.steps[s].lp[i];
+               int outer_only = 0, on_tuple = 0;
+               for (int j = 0; j < steps[s].n_pre; ++j) {
+                    bool any_in = false, tup = false;
+                    for (int l = 0; l < steps[s].pre[j].k; ++l) {
+                         const int lp = local_pos(pl, steps[s].pre[j].slots[l]);
+                         any_in = any_in || lp >= 0;
+                         tup = tup || (lp >= 0 && ((tm >> lp) & 1));
+                    }
+                    outer_only += any_in ? 0 : 1;
+                    on_tuple += tup ? 1 : 0;
+               }
+               std::fprintf(stderr, "    gate %d (form %d, selects in/out %d/%d): %d ops, %d with every slot outside the tile, %d on tuple bits\n", s,
+                            pl.steps[s].ks, pl.steps[s].n_in, pl.steps[s].n_out, steps[s].n_pre, outer_only, on_tuple);
+          }
+     }
      return pl.T;
 }
 
@@ -582,29 +842,41 @@ extern "C" int hiqk_apply_tile_program(void* slab, int L, int n_steps, const hiq
      if (rc != HIQ_OK) return rc;
      rc = fill_params(p, ring->host[slot], slab, L, n_steps, steps, pl, why);
      if (rc != HIQ_OK) return set_error(rc, "hiqk_apply_tile_program: " + why);
-     const size_t smem = tile_smem_bytes(pl.T);
      cudaStream_t st = static_cast<cudaStream_t>(stream);
      p.lut = ring->dev[slot];
      if (p.n_lut)
           HIQ_CUDA(cudaMemcpyAsync(ring->dev[slot], ring->host[slot], sizeof(double2) * p.n_lut, cudaMemcpyHostToDevice, st));
-     if (pl.T == 11) {
-          static bool attr = false;
-          if (!attr) {
-               cudaFuncSetAttribute(tile_program_kernel<11>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-               attr = true;
+     bool full = false;
+     for (const PlannedStep& ps: pl.steps) full = full || ps.ks >= 4;
+     static const bool double_buffer = [] {
+          const char* e = std::getenv("HIQ_TILE_DOUBLE_BUFFER");  // A/B measurements: 1 = two buffers
+          return e && e[0] == '1';
+     }();
+     auto go = [&](void (*kernel)(TileParams), int threads, int nbuf) {
+          const size_t smem = tile_smem_bytes(pl.T, nbuf, p);
+          static std::vector<void (*)(TileParams)> configured;  // under `mu`: the kernels whose shared-memory limit is raised
+          if (std::find(configured.begin(), configured.end(), kernel) == configured.end()) {
+               cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+               configured.push_back(kernel);
           }
-          const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, grid_cap(static_cast<uint64_t>(num_sms()) * 4)));
-          tile_program_kernel<11><<<grid, 1 << 7, smem, st>>>(p);
-     }
-     else {
-          static bool attr = false;
-          if (!attr) {
-               cudaFuncSetAttribute(tile_program_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-               attr = true;
+          int per_sm = 0;
+          if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem) != cudaSuccess || per_sm < 1) {
+               cudaGetLastError();
+               per_sm = 1;
           }
-          const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, grid_cap(static_cast<uint64_t>(num_sms()) * 2)));
-          tile_program_kernel<12><<<grid, 1 << 8, smem, st>>>(p);
+          const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_tiles, grid_cap(static_cast<uint64_t>(num_sms()) * per_sm)));
+          kernel<<<grid, threads, smem, st>>>(p);
+     };
+     if (pl.T == 11 && double_buffer) {
+          if (full) go(tile_program_kernel<11, true, 2>, 1 << 7, 2);
+          else go(tile_program_kernel<11, false, 2>, 1 << 7, 2);
      }
+     else if (pl.T == 11) {
+          if (full) go(tile_program_kernel<11, true, 1>, 1 << 7, 1);
+          else go(tile_program_kernel<11, false, 1>, 1 << 7, 1);
+     }
+     else if (full) go(tile_program_kernel<12, true, 1>, 1 << 8, 1);
+     else go(tile_program_kernel<12, false, 1>, 1 << 8, 1);
      count_launch();
      ring->used[slot] = true;
      cudaEventRecord(ring->ev[slot], st);

@@ -154,6 +154,9 @@ typedef struct hiqk_tile_step {
      int n_pre;
 } hiqk_tile_step;
 int hiqk_tile_program_fits(int L, int n_steps, const hiqk_tile_step* steps);
+/* 1 when the 2^k x 2^k matrix has exactly one nonzero entry per row and column (a permutation with phases: fused X / Y / Z /
+ * phase gates) — a tile program applies it without summing products.  Host only. */
+int hiqk_dense_is_monomial(int k, const double* matrix);
 int hiqk_apply_tile_program(void* slab, int L, int n_steps, const hiqk_tile_step* steps, void* stream);
 
 /* Remove bit `slot` from the index space keeping the half where that bit == keep:

@@ -263,13 +263,30 @@ TILE_RUNS = [
     # (L, [(k, slots, select bits of the matrix or None = dense, number of diagonal ops)], expected tile bits)
     (15, [(4, (11, 12, 13, 14), None, 0)], 11),
     (15, [(4, (11, 12, 13, 14), (2, 3), 3), (4, (9, 10, 13, 14), (0, 1), 5), (4, (9, 10, 11, 12), (2, 3), 12)], 11),   # 6 high slots
-    (16, [(4, (12, 13, 14, 15), (0, 1), 2), (4, (10, 11, 12, 13), (2, 3), 4), (4, (8, 9, 10, 11), (2, 3), 6)], 12),     # QFT-like chain
+    (16, [(4, (12, 13, 14, 15), (0, 1), 2), (4, (10, 11, 12, 13), (2, 3), 4), (4, (8, 9, 10, 11), (2, 3), 6)], 11),     # QFT-like chain
+    (20, [(4, (16, 17, 18, 19), (2, 3), 5), (4, (14, 15, 16, 17), (2, 3), 7), (4, (12, 13, 14, 15), (2, 3), 6), (4, (10, 11, 12, 13), (2, 3), 4)], 12),
+    (19, [(4, (3, 9, 14, 18), (0, 2, 3), 3), (3, (17, 5, 11), (0, 1), 2), (2, (18, 16), (0,), 2), (4, (2, 8, 13, 17), (1, 2, 3), 9)], 11),  # select bits outside the tile
     (16, [(4, (7, 8, 9, 10), (2, 3), 2), (4, (5, 6, 7, 8), (2, 3), 3), (4, (3, 4, 5, 6), (2, 3), 4), (4, (1, 2, 3, 4), (2, 3), 5)], 11),
     (14, [(3, (0, 1, 2), (1, 2), 6), (4, (1, 2, 3, 4), None, 2)], 11),                                                  # slot-0 targets
     (15, [(4, (0, 5, 9, 13), None, 1), (4, (2, 6, 9, 12), None, 2)], 11),                                               # two full products
     (17, [(2, (3, 16), None, 1), (1, (14,), None, 0), (3, (15, 0, 7), (1,), 4), (4, (12, 13, 14, 15), (0,), 7)], 11),
     (16, [(4, (0, 1, 14, 15), None, 12), (4, (2, 3, 12, 13), None, 9)], 11),
-    (18, [(4, (10, 11, 16, 17), None, 16), (4, (12, 13, 14, 15), (1, 2), 16)], 12),
+    (18, [(4, (10, 11, 16, 17), None, 16), (4, (12, 13, 14, 15), (1, 2), 16)], 11),
+]
+
+
+def monomial_matrix(k, seed):
+    """a permutation of the basis states with random phases (what fused X / Y / Z / phase gates make)"""
+    rng = np.random.default_rng(seed)
+    d = 1 << k
+    m = np.zeros((d, d), dtype=np.complex128)
+    m[rng.permutation(d), np.arange(d)] = np.exp(1j * rng.uniform(0, 2 * np.pi, size=d))
+    return m
+
+
+TILE_RUNS += [
+    (16, [(4, (9, 11, 12, 14), "mono", 3), (4, (12, 13, 14, 15), (2, 3), 4), (3, (10, 4, 13), "mono", 6), (4, (1, 3, 4, 6), "mono", 0)], 12),
+    (17, [(4, (13, 14, 15, 16), "mono", 0), (4, (5, 9, 12, 16), None, 5), (2, (0, 16), "mono", 2)], 11),
 ]
 
 
@@ -283,7 +300,12 @@ def test_tile_program_matches_oracle(case):
     rng = np.random.default_rng(900 + case)
     steps = []
     for i, (k, slots, select, n_pre) in enumerate(run):
-        m = rand_matrix(k, 17 * case + i) if select is None else multiplexed_matrix(k, list(select), 13 * case + i)
+        if select is None:
+            m = rand_matrix(k, 17 * case + i)
+        elif select == "mono":
+            m = monomial_matrix(k, 19 * case + i)
+        else:
+            m = multiplexed_matrix(k, list(select), 13 * case + i)
         ops = _rand_diag_ops(L, n_pre, 1000 * case + i)
         ops = [(sl[:4], d[:1 << len(sl[:4])]) for sl, d in ops]  # tables of at most 16 entries (cluster size 4)
         if n_pre:  # one op entirely inside the targets, one overlapping them partly
@@ -323,7 +345,7 @@ def test_tile_program_multi_iteration(tiny_grid):
 def test_tile_program_rejects_what_does_not_fit():
     from hiqsimulator_b200 import kernels as K
     m = rand_matrix(4, 1)
-    wide = [((20, 21, 22, 23), m, []), ((10, 11, 12, 13), m, []), ((15, 16, 17, 18), m, [])]  # 12 high slots
+    wide = [((20, 21, 22, 23), m, []), ((10, 11, 12, 13), m, []), ((15, 16, 17, 18), m, [])]  # 12 high mixing slots
     assert K.tile_program_fits(26, wide) == 0
     assert K.tile_program_fits(26, wide[:2]) == 12
     assert K.tile_program_fits(10, [((0, 1, 2, 3), m, [])]) == 0  # slab smaller than a tile
