@@ -134,8 +134,9 @@ def run_shor(eng, N: int, a: int, n: int | None = None, verbose: bool = False):
             print(measurements[k], end="", flush=True)
     eng.receive([ops.Measure(list(x))])
     eng.flush()
-    y = sum(measurements[2 * n - 1 - i] * 1.0 / (1 << (i + 1)) for i in range(2 * n))
-    r = Fraction(y).limit_denominator(N - 1).denominator
+    # the measured phase as an exact rational (the reference example sums floats, which drops bits beyond 2n = 53)
+    y = Fraction(sum(measurements[2 * n - 1 - i] << (2 * n - 1 - i) for i in range(2 * n)), 1 << (2 * n))
+    r = y.limit_denominator(N - 1).denominator
     return r, measurements
 
 

@@ -1305,8 +1305,12 @@ bool Engine::exchange_packed(const std::vector<int>& gpos, const std::vector<int
      }
      cudaEvent_t* gathered = &swap_events_[0];   // [2] piece gathered and certified by the barrier (engine stream)
      cudaEvent_t* scattered = &swap_events_[2];  // [2] piece scattered into my slab (second stream)
+     // Entry barrier with the peers of THIS exchange.  The staging buffers belong to the process, and consecutive swaps may
+     // pair a rank with different peers (another subset of the global bits): a peer that has not reached this exchange may
+     // still be scattering the previous one out of the very buffer the first gather writes into.  Its stream reaches this
+     // barrier only after that scatter (and the closing barrier of its previous exchange) has completed.
+     group_barrier(peer_ranks);
      if (swap_mark_[0]) {
-          // nothing here waits for a peer before moving data: the first gather goes into a staging buffer, not into a slab
           cudaEventRecord(swap_mark_[0], stream_);
           cudaEventRecord(swap_mark_[1], stream_);
           swap_marked_ = true;

@@ -178,14 +178,8 @@ def test_engine_matches_golden_multi_gpu(name):
     R = int(name[1])
     if _gpu_count() < R:
         pytest.skip("needs %d GPUs" % R)
-    import socket
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    from torchrun_util import run_torchrun
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "gpu"], timeout=600)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
@@ -198,17 +192,11 @@ def test_engine_matches_golden_multi_gpu_swap_transports(name, mode):
     R = int(name[1])
     if _gpu_count() < R:
         pytest.skip("needs %d GPUs" % R)
-    import socket
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
+    from torchrun_util import run_torchrun
     env = dict(os.environ, HIQ_SWAP_MODE=mode)
     if mode == "packed":
         env["HIQ_SWAP_PACKED_PIECE"] = "16"  # many pieces even on these small slabs: the two-buffer pipeline is exercised
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "gpu"], env=env, timeout=300)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
@@ -389,14 +377,8 @@ def test_engine_time_evolution_matches_oracle(nq, seed):
 def test_engine_operator_calls_multi_gpu(name, R):
     if _gpu_count() < R:
         pytest.skip("needs %d GPUs" % R)
-    import socket
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    from torchrun_util import run_torchrun
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "gpu"], timeout=600)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
@@ -578,12 +560,6 @@ def test_pipeline_grover_matches_oracle(n_search, iters, cluster):
 def test_pipeline_shor_multi_gpu(name, R):
     if _gpu_count() < R:
         pytest.skip("needs %d GPUs" % R)
-    import socket
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
-           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(HERE, "mp_worker.py"), name, "gpu"]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    from torchrun_util import run_torchrun
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "gpu"], timeout=600)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]

@@ -41,19 +41,8 @@ def _ram_gib():
 
 
 def _torchrun(R, *worker_args, timeout=1500):
-    s = socket.socket()
-    s.bind(("127.0.0.1", 0))
-    port = s.getsockname()[1]
-    s.close()
-    if R == 1:
-        cmd = [sys.executable, os.path.join(HERE, "mp_fullsize_worker.py"), *worker_args]
-    else:
-        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R), "--master-addr", "127.0.0.1",
-               "--master-port", str(port), os.path.join(HERE, "mp_fullsize_worker.py"), *worker_args]
-    env = dict(os.environ)
-    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
-        env.pop(k, None)
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, env=env)
+    from torchrun_util import run_torchrun
+    res = run_torchrun(R, os.path.join(HERE, "mp_fullsize_worker.py"), list(worker_args), timeout=timeout)
     assert res.returncode == 0 and "FULLSIZE_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
     line = [ln for ln in res.stdout.splitlines() if ln.startswith("FULLSIZE_OK")][-1]
     return json.loads(line[len("FULLSIZE_OK "):])

@@ -21,11 +21,8 @@ def _free_port():
 
 @pytest.mark.parametrize("name,R", [("r2_q10_gates", 2), ("r2_q9", 2), ("r4_q12_gates", 4)])
 def test_dry_run_world(name, R):
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(HERE, "mp_worker.py"), name, "dry"]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    from torchrun_util import run_torchrun
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "dry"], env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=300)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
 
 
@@ -33,9 +30,6 @@ def test_dry_run_world(name, R):
 def test_dry_run_world_operator_calls(name, R):
     """get_expectation_value / apply_qubit_operator / emulate_math / set_wavefunction host logic, one dry-run engine
     per gloo rank, traces replayed on rank 0 against the numpy oracle"""
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(R),
-           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
-           os.path.join(HERE, "mp_worker.py"), name, "dry"]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    from torchrun_util import run_torchrun
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "dry"], env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=300)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
