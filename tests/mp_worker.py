@@ -3,6 +3,7 @@
 usage: mp_worker.py <golden name> <mode>      mode = dry (CPU, gloo) | gpu (NCCL)
        mp_worker.py ops:<qubits>:<seed> <mode>   operator-level script (scripts.operator_script) checked against the
                                                  numpy oracle instead of a golden fixture
+       mp_worker.py swapskew:<qubits>:<seed> <mode>   exchanges with changing peer sets while half of the ranks are held back
 Rank 0 compares the merged outputs with the expectation and exits non-zero on mismatch."""
 import os
 import sys
@@ -18,15 +19,40 @@ from golden_util import load_golden  # noqa: E402
 
 
 def main():
-    name, mode = sys.argv[1], sys.argv[2]
+    names, mode = sys.argv[1], sys.argv[2]
     from hiqsimulator_b200 import _cppsim_mpi as M
     from hiqsimulator_b200 import world
     flags = M.FLAG_DRY_RUN if mode == "dry" else 0
     rank, size = world.init_world(flags)
+    # several cases on one process group: name+name+...; name@transport forces the exchange transport for that case
+    for name in names.split("+"):
+        forced = None
+        if "@" in name:
+            name, forced = name.split("@")
+        saved = {k: os.environ.get(k) for k in ("HIQ_SWAP_MODE", "HIQ_SWAP_PACKED_PIECE")}
+        if forced:
+            os.environ["HIQ_SWAP_MODE"] = forced
+            if forced == "packed":
+                os.environ["HIQ_SWAP_PACKED_PIECE"] = "16"
+        try:
+            one_case(name, mode, M, world, rank, size)
+        finally:
+            for k, v in saved.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+        if rank == 0:
+            print("MP_WORKER_OK", name + ("@" + forced if forced else ""), mode, flush=True)
+
+
+def one_case(name, mode, M, world, rank, size):
     if name.startswith("ops:") or name.startswith("tevo:"):
         return operator_case(name, mode, M, world, rank, size)
     if name.startswith("shor:"):
         return shor_case(name, mode, M, world, rank, size)
+    if name.startswith("swapskew:"):
+        return swap_skew_case(name, mode, M, world, rank, size)
     R, script, exp = load_golden(name)
     assert size == R, (size, R)
     if mode == "dry":
@@ -51,8 +77,56 @@ def main():
             merged = scripts.merge_rank_outputs(gathered)
             scripts.assert_outputs_match(script, merged, exp)
     world.barrier()
-    if rank == 0:
-        print("MP_WORKER_OK", name, mode)
+
+
+def swap_skew_case(name, mode, M, world, rank, R):
+    """Consecutive exchanges whose peer sets differ (scripts.swap_skew_script), with the ranks that meet a NEW partner in
+    the next exchange held back on the host: the partner reaches that exchange while they are still inside the current
+    one.  Whatever the transport shares between exchanges (the packed transport's process-wide staging buffers) has to
+    survive this; the final slabs must equal the numpy oracle's.  name = swapskew:<qubits>:<seed>[:<transport>,...] —
+    the transports (auto, packed, packed-pieces, p2p, staged) are run one after the other on the same process group
+    (the engine reads HIQ_SWAP_MODE / HIQ_SWAP_PACKED_PIECE when it is constructed)."""
+    import time
+    parts = name.split(":")
+    nq, seed = int(parts[1]), int(parts[2])
+    transports = parts[3].split(",") if len(parts) > 3 else ["auto"]
+    script, holds = scripts.swap_skew_script(nq, R, seed)
+    hold_s = float(os.environ.get("HIQ_TEST_SKEW_SECONDS", "0.05"))
+
+    def before_op(j, op):
+        if rank in holds.get(j, ()):
+            time.sleep(hold_s)
+    exp = scripts.run_on_oracle(script, R) if rank == 0 else None
+    if mode == "dry":
+        e = M.SimulatorMPI(*script[0][1:])
+        for j, op in enumerate(script[1:], 1):
+            if op[0] == "cheat_local":
+                break
+            before_op(j, op)
+            scripts._dispatch(e, op)
+        gathered = world.gather_objects(e.trace())
+        if rank == 0:
+            state = scripts.replay_traces(gathered, R)
+            assert np.abs(state - exp[-1][1]).max() <= 1e-12
+    else:
+        for transport in transports:
+            for k in ("HIQ_SWAP_MODE", "HIQ_SWAP_PACKED_PIECE"):
+                os.environ.pop(k, None)
+            if transport != "auto":
+                os.environ["HIQ_SWAP_MODE"] = transport.split("-")[0]
+            if "pieces" in transport:
+                os.environ["HIQ_SWAP_PACKED_PIECE"] = "16"  # many pieces: the two-buffer pipeline is exercised too
+            keep = []
+            out = scripts.run_on_sim(M.SimulatorMPI, script, keep, before_op)
+            st = keep[0].stats()
+            gathered = world.gather_objects((out, {k: int(st[k]) for k in ("swaps_p2p", "swaps_staged", "swaps_packed")}))
+            if rank == 0:
+                merged = scripts.merge_rank_outputs([g[0] for g in gathered])
+                scripts.assert_outputs_match(script, merged, exp)
+                print("SWAP_SKEW_OK", transport, gathered[0][1], flush=True)
+            del keep, out
+            world.barrier()
+    world.barrier()
 
 
 def shor_case(name, mode, M, world, rank, R):
@@ -80,8 +154,6 @@ def shor_case(name, mode, M, world, rank, R):
             assert (g[0], g[1], g[2]) == (r0, bits0, final0), (g[:3], (r0, bits0, final0))
             assert g[4] == id2pos0 and np.abs(g[3] - full0).max() <= 1e-12
     world.barrier()
-    if rank == 0:
-        print("MP_WORKER_OK", name, mode)
 
 
 def operator_case(name, mode, M, world, rank, R):
@@ -120,8 +192,6 @@ def operator_case(name, mode, M, world, rank, R):
             for g in gathered:
                 assert np.array_equal(g[1], merged[last][1]) and g[2] == merged[last][0]
     world.barrier()
-    if rank == 0:
-        print("MP_WORKER_OK", name, mode)
 
 
 if __name__ == "__main__":

@@ -153,12 +153,15 @@ def merge_rank_outputs(per_rank):
     return out
 
 
-def run_on_sim(make_sim, script, keep=None):
+def run_on_sim(make_sim, script, keep=None, before_op=None):
     """Execute on one rank of an object with the pybind surface (reference module or ours).
-    keep: optional list that receives the simulator object (so the caller can go on using it)."""
+    keep: optional list that receives the simulator object (so the caller can go on using it);
+    before_op(j, op): optional hook called ahead of every op (the skew tests hold ranks back with it)."""
     sim = None
     out = []
-    for op in script:
+    for j, op in enumerate(script):
+        if before_op is not None:
+            before_op(j, op)
         try:
             if op[0] == "ctor":
                 sim = make_sim(*op[1:])
@@ -451,6 +454,70 @@ def replay_traces(traces, R, info=None):
 
 
 # ------------------------------------------------------------------ scheduled circuits as scripts
+def swap_skew_script(nq, R, seed, exchanges=12):
+    """Consecutive single-pair exchanges on ALTERNATING global bits (the peer sets of two consecutive exchanges differ),
+    low local slots (the packed transport in automatic mode), an all-pairs exchange now and then, a dense gate between
+    some of them.  Returns (script, holds): holds[j] = the ranks to delay on the host before op j — the ranks whose
+    partner in the NEXT exchange is a rank that was not delayed, so that the partner reaches the next exchange while
+    the delayed rank is still inside this one (the case a process-wide staging buffer has to survive)."""
+    rng = np.random.default_rng(seed)
+    G = R.bit_length() - 1
+    assert G >= 2, "needs at least 4 ranks"
+    L = nq - G
+    ctor = ("ctor", 11 + seed, L, 3)
+    script = [ctor, ("allocate_qureg", list(range(nq)), 0)]
+    o = statevec.SimulatorMPI(*ctor[1:], R)
+    o.allocate_qureg(list(range(nq)), 0)
+    holds = {}
+
+    def emit(op):
+        script.append(op)
+        getattr(o, op[0])(*op[1:])
+
+    def mix():
+        loc = o.get_local_qubits_ids()
+        for _ in range(3):
+            ids = [int(x) for x in rng.choice(loc, size=2, replace=False)]
+            emit(("apply_controlled_gate", haar_unitary(4, rng).tolist(), ids, []))
+            emit(("run",))
+
+    def rotate(ids):
+        for q in ids:
+            emit(("apply_controlled_gate", haar_unitary(2, rng).tolist(), [int(q)], []))
+            emit(("run",))
+
+    # every amplitude non-zero and different on every rank: rotate the local qubits, trade G of them for the global ones
+    # (this first exchange also sets up the staging buffers, a collective step), rotate what came in
+    rotate(o.get_local_qubits_ids())
+    glo, loc = o.get_global_qubits_ids(), o.get_local_qubits_ids()
+    pairs = []
+    for gp in range(G):
+        pairs += [int(glo[gp]), int(loc[gp])]
+    emit(("swap_qubits", pairs))
+    rotate(glo)
+    mix()
+    gpos_seq = [e % G for e in range(exchanges)]
+    for e, g in enumerate(gpos_seq):
+        glo = o.get_global_qubits_ids()
+        loc = o.get_local_qubits_ids()
+        if e % 5 == 4:  # all global bits at once: the peer set is the whole world
+            slots = [int(x) for x in rng.choice(min(L, 4), size=G, replace=False)]
+            pairs = []
+            for gp, s in zip(range(G), slots):
+                pairs += [int(glo[gp]), int(loc[s])]
+        else:
+            pairs = [int(glo[g]), int(loc[int(rng.integers(0, 3))])]
+        if e % 2 == 0 and e + 1 < exchanges:
+            nxt = gpos_seq[e + 1]
+            holds[len(script)] = [r for r in range(R) if not (r >> nxt) & 1]
+        emit(("swap_qubits", pairs))
+        if e % 3 == 2:
+            mix()
+    emit(("get_qubits_ids",))
+    script.append(("cheat_local",))
+    return script, holds
+
+
 def scheduled_script(kind, n, R, cluster=4, seed=1, depth=20):
     """The bench's pipeline (circuit generator -> GreedyScheduler -> backend) recorded as a script: the post-scheduler
     command stream (initial relabelling, gates, flushes, swaps) for `R` ranks, planned against a dry-run engine, ending

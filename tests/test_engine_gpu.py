@@ -183,6 +183,24 @@ def test_engine_matches_golden_multi_gpu(name):
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
 
 
+@pytest.mark.parametrize("R", [4, 8])
+def test_swaps_with_changing_peers_and_rank_skew_multi_gpu(R):
+    """consecutive exchanges on alternating global bits (the partner changes every time) while the ranks that meet a new
+    partner next are held back on the host, so that the partner arrives at the next exchange before they have left the
+    current one: what a transport keeps between exchanges (the packed transport's process-wide staging buffers) must
+    survive it.  Without the entry barrier of Engine::exchange_packed this case reads a staging buffer the previous
+    partner has not finished with (seen as wrong amplitudes in the R = 8 golden runs, profiles/r02e_pytest_gpu_r8.log).
+    Every transport is run on the same process group, one after the other."""
+    if _gpu_count() < R:
+        pytest.skip("needs %d GPUs" % R)
+    from torchrun_util import run_torchrun
+    transports = "auto,packed,packed-pieces,p2p,staged"
+    env = {k: v for k, v in os.environ.items() if k not in ("HIQ_SWAP_MODE", "HIQ_SWAP_PACKED_PIECE")}
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), ["swapskew:%d:5:%s" % (10 + R.bit_length(), transports), "gpu"], env=env, timeout=300)
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-3000:] + res.stderr[-3000:]
+    assert res.stdout.count("SWAP_SKEW_OK") == 5, res.stdout[-3000:]
+
+
 @pytest.mark.parametrize("mode", ["p2p", "packed", "staged"])
 @pytest.mark.parametrize("name", [n for n in golden_names() if not n.startswith("r1_")])
 def test_engine_matches_golden_multi_gpu_swap_transports(name, mode):

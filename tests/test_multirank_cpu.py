@@ -33,3 +33,12 @@ def test_dry_run_world_operator_calls(name, R):
     from torchrun_util import run_torchrun
     res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "dry"], env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=300)
     assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+@pytest.mark.parametrize("name,R", [("swapskew:10:5", 4)])
+def test_dry_run_world_swaps_with_changing_peers(name, R):
+    """the script of the multi-GPU skew test (exchanges on alternating global bits, half of the ranks held back): its
+    descriptor traces, replayed on rank 0, give the oracle's state — the script and its expectation are pinned on the CPU"""
+    from torchrun_util import run_torchrun
+    res = run_torchrun(R, os.path.join(HERE, "mp_worker.py"), [name, "dry"], env=dict(os.environ, OMP_NUM_THREADS="1"), timeout=300)
+    assert res.returncode == 0 and "MP_WORKER_OK" in res.stdout, res.stdout[-2000:] + res.stderr[-2000:]
