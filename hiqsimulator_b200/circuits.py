@@ -108,8 +108,6 @@ def run_shor(eng, N: int, a: int, n: int | None = None, verbose: bool = False):
     The reference decomposes the multiplication through projectq.libs.math (2n+3 qubits with ancillas); here it is
     emulated by the engine (ops.MultiplyByConstantModN -> emulate_math), so the circuit needs n + 1 qubits.
     `eng` is a HiQMainEngine.  Returns (candidate period r, the 2n measured bits)."""
-    from fractions import Fraction
-
     from . import ops
     if n is None:
         n = int(math.ceil(math.log(N, 2)))
@@ -134,10 +132,19 @@ def run_shor(eng, N: int, a: int, n: int | None = None, verbose: bool = False):
             print(measurements[k], end="", flush=True)
     eng.receive([ops.Measure(list(x))])
     eng.flush()
-    # the measured phase as an exact rational (the reference example sums floats, which drops bits beyond 2n = 53)
-    y = Fraction(sum(measurements[2 * n - 1 - i] << (2 * n - 1 - i) for i in range(2 * n)), 1 << (2 * n))
-    r = y.limit_denominator(N - 1).denominator
-    return r, measurements
+    return period_from_bits(measurements, N), measurements
+
+
+def period_from_bits(measurements, N: int) -> int:
+    """Period candidate from the measured bits of the semi-classical phase estimation (reference:
+    examples/shor_mpi.py:95-105): round k measured bit 2n-1-k of the phase, so measurements[2n-1-i] is the bit of weight
+    2^-(i+1); the candidate is the denominator of the closest fraction with denominator < N.  The reference example sums
+    the bits as floats; beyond 2n = 53 bits that drops the low bits the continued fraction needs (a 32-qubit run measures
+    62), so the phase is kept as an exact rational here."""
+    from fractions import Fraction
+    m = len(measurements)
+    y = Fraction(sum(int(measurements[m - 1 - i]) << (m - 1 - i) for i in range(m)), 1 << m)
+    return y.limit_denominator(N - 1).denominator
 
 
 def inverse_circuit(cmds):

@@ -227,3 +227,36 @@ def test_bench_parity_checks_pinned_on_the_oracle(R):
                               samples=256)
     assert res["ok"], res
     assert res["qft_closed_form"]["max_abs_err"] <= 1e-12 and res["random_then_inverse"]["abs_amp0_minus_1"] <= 1e-12
+
+
+def test_shor_period_read_out_is_exact_beyond_53_bits():
+    """circuits.period_from_bits on ideal phase-estimation outcomes of the bench's 32-qubit Shor instance
+    (N = 32771 * 32779, a = 7, 62 measured bits): the exact rational recovers the order for every k coprime to it;
+    the float sum of the reference example (examples/shor_mpi.py:95-105) cannot hold 62 bits and misses some."""
+    import math
+    import random
+    from fractions import Fraction
+
+    from hiqsimulator_b200 import circuits
+    p, q, a = 32771, 32779, 7
+    N = p * q
+    n = int(math.ceil(math.log(N, 2)))
+    assert n == 31
+    lam = (p - 1) * (q - 1) // math.gcd(p - 1, q - 1)
+    r = lam
+    for f in range(2, 40000):  # order of a = lambda(N) stripped of every prime factor that is not needed
+        while r % f == 0 and pow(a, r // f, N) == 1:
+            r //= f
+    assert pow(a, r, N) == 1 and r > 1 << 20
+    rnd = random.Random(5)
+    float_misses = 0
+    for _ in range(200):
+        k = rnd.randrange(1, r)
+        if math.gcd(k, r) != 1:
+            continue
+        Y = (k * (1 << (2 * n)) + r // 2) // r  # the most likely outcome: the 2n-bit fraction closest to k / r
+        bits = [(Y >> j) & 1 for j in range(2 * n)]
+        assert circuits.period_from_bits(bits, N) == r
+        y = sum(bits[2 * n - 1 - i] * 1.0 / (1 << (i + 1)) for i in range(2 * n))
+        float_misses += Fraction(y).limit_denominator(N - 1).denominator != r
+    assert float_misses > 0
