@@ -185,14 +185,19 @@ void Engine::allocate_local(Index id)
           trace_.push_back(d);
      }
      if (dry_run_) return;
+     grow_slab(2 * old);
+     cu(check_cuda(cudaMemsetAsync(slab_.data() + old, 0, old * sizeof(double2), stream_), "cudaMemsetAsync"));
+}
+
+void Engine::grow_slab(uint64_t amps)
+{
      const auto t_grow = Clock::now();
-     if (slab_.ensure(2 * old) != HIQ_OK && scratch_.data()) {
+     if (slab_.ensure(amps) != HIQ_OK && scratch_.data()) {
           scratch_.release();  // the second buffer of the out-of-place passes gives its memory back to the register
           cu(check_cuda(cudaStreamSynchronize(stream_), "cudaStreamSynchronize"));
      }
-     cu(slab_.ensure(2 * old));
+     cu(slab_.ensure(amps));
      stats_.slab_grow_s += seconds_since(t_grow);
-     cu(check_cuda(cudaMemsetAsync(slab_.data() + old, 0, old * sizeof(double2), stream_), "cudaMemsetAsync"));
 }
 
 void Engine::allocate_global(Index id) { globals_[find_sure(globals_, kNone)] = id; }
@@ -213,6 +218,22 @@ void Engine::allocate_qureg(const std::vector<Index>& ids, cplx init)
 {
      if (init != cplx(0.0) && !locals_.empty())
           fail("AllocateQureg(): initialization of only first qureg is supported");
+     if (!dry_run_) {
+          // map the register's final extent in ONE piece instead of one piece per doubling: a slab made of few
+          // virtual-memory chunks is cheaper to hand to the peers (one descriptor + one mapping per chunk and peer)
+          size_t nloc = locals_.size();
+          size_t free_globals = static_cast<size_t>(std::count(globals_.begin(), globals_.end(), kNone));
+          for (size_t i = 0; i < ids.size(); ++i) {  // the allocation policy of allocate_qubit()
+               if (nloc < min_local_) ++nloc;
+               else if (free_globals > 0) --free_globals;
+               else if (nloc < max_local_) ++nloc;
+               else break;  // allocate_qubit() raises when it gets there
+          }
+          if (nloc > locals_.size()) {
+               flush_pending();
+               grow_slab(1ull << nloc);
+          }
+     }
      for (Index q: ids) allocate_qubit(q);
      if (init != cplx(0.0)) {
           uint64_t gmsk = 0;

@@ -130,6 +130,7 @@ private:
      void need_device(const char* what) const;
 
      void allocate_local(Index id);
+     void grow_slab(uint64_t amps);  // map the slab up to `amps` amplitudes (the scratch slab gives way when memory is short)
      void allocate_global(Index id);
      void deallocate_local(Index id);
      void deallocate_global(Index id);
