@@ -357,17 +357,11 @@ int hiq_stream(hiq_engine* e, void** stream)
      return HIQ_OK;
 }
 
-int hiq_trace_count(hiq_engine* e, int* n)
-{
-     NEED(e);
-     *n = static_cast<int>(e->impl.trace().size());
-     return HIQ_OK;
-}
+}  // extern "C"
 
-int hiq_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux)
+namespace {
+int trace_get(const std::vector<Descriptor>& t, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux)
 {
-     NEED(e);
-     const auto& t = e->impl.trace();
      if (i < 0 || i >= static_cast<int>(t.size())) return set_error(HIQ_ERR_ARG, "hiq_trace_get: index out of range");
      const Descriptor& s = t[i];
      d->kind = s.kind;
@@ -385,6 +379,35 @@ int hiq_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int 
           std::copy(s.aux.begin(), s.aux.end(), aux);
      }
      return HIQ_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int hiq_trace_count(hiq_engine* e, int* n)
+{
+     NEED(e);
+     *n = static_cast<int>(e->impl.trace().size());
+     return HIQ_OK;
+}
+
+int hiq_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux)
+{
+     NEED(e);
+     return trace_get(e->impl.trace(), i, d, payload, cap_payload, aux, cap_aux);
+}
+
+int hiq_launch_trace_count(hiq_engine* e, int* n)
+{
+     NEED(e);
+     *n = static_cast<int>(e->impl.launch_trace().size());
+     return HIQ_OK;
+}
+
+int hiq_launch_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux)
+{
+     NEED(e);
+     return trace_get(e->impl.launch_trace(), i, d, payload, cap_payload, aux, cap_aux);
 }
 
 int hiq_trace_clear(hiq_engine* e)

@@ -182,7 +182,7 @@ void Engine::allocate_local(Index id)
           Descriptor d;
           d.kind = HIQ_DESC_GROW;
           d.k = static_cast<int>(locals_.size());
-          trace_.push_back(d);
+          trace_op(d);
      }
      if (dry_run_) return;
      grow_slab(2 * old);
@@ -244,7 +244,7 @@ void Engine::allocate_qureg(const std::vector<Index>& ids, cplx init)
                     Descriptor d;
                     d.kind = HIQ_DESC_FILL;
                     d.payload = {init};
-                    trace_.push_back(d);
+                    trace_op(d);
                }
                if (!dry_run_) cu(hiqk_fill(slab_.data(), 0, 1ull << locals_.size(), init.real(), init.imag(), stream_));
           }
@@ -413,6 +413,39 @@ void Engine::d2h(void* dst, const void* src, size_t bytes)
      cu(check_cuda(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream_), "cudaMemcpyAsync"));
      synchronize();
      stats_.d2h_bytes += static_cast<double>(bytes);
+}
+
+void Engine::trace_op(const Descriptor& d)
+{
+     if (!tracing_) return;
+     // a dry-run engine closes its launch accounting where the device path flushes its queues: before anything that is
+     // not a gate pass (the launch trace then lists the launches in device order)
+     if (dry_run_) flush_pending();
+     trace_.push_back(d);
+     if (dry_run_) launches_.push_back(d);
+}
+
+void Engine::record_launch(int form, const std::vector<LaunchStepRef>& steps)
+{
+     Descriptor r;
+     r.kind = HIQ_DESC_LAUNCH;
+     r.k = static_cast<int>(steps.size());
+     r.slots[0] = form;
+     for (const LaunchStepRef& st: steps) {
+          const int k = st.gate ? st.gate->k : -1;
+          r.aux.push_back(k);
+          for (int l = 0; l < k; ++l) r.aux.push_back(st.gate->slots[l]);
+          r.aux.push_back(st.ops ? static_cast<int64_t>(st.ops->size()) : 0);
+          if (st.gate) r.payload.insert(r.payload.end(), st.gate->payload.begin(), st.gate->payload.end());
+          if (!st.ops) continue;
+          for (const hiqk_diag_op& o: *st.ops) {
+               r.aux.push_back(o.k);
+               for (int l = 0; l < o.k; ++l) r.aux.push_back(o.slots[l]);
+               const cplx* t = reinterpret_cast<const cplx*>(o.lut);
+               r.payload.insert(r.payload.end(), t, t + (1 << o.k));
+          }
+     }
+     launches_.push_back(std::move(r));
 }
 
 namespace {
@@ -595,7 +628,13 @@ void Engine::launch_group()
           tp.stop = take_event();
           cudaEventRecord(tp.start, stream_);
      }
-     if (!dry_run_) cu(hiqk_apply_tile_program(slab_.data(), L, static_cast<int>(steps.size()), steps.data(), stream_));
+     if (dry_run_) {
+          std::vector<LaunchStepRef> rec;
+          for (const HeldGate& h: g) rec.push_back({&h.d, &h.ops});
+          record_launch(HIQ_LAUNCH_TILE, rec);
+     }
+     else
+          cu(hiqk_apply_tile_program(slab_.data(), L, static_cast<int>(steps.size()), steps.data(), stream_));
      ++stats_.gate_launches;
      ++stats_.tile_launches;
      stats_.tile_steps += g.size();
@@ -620,7 +659,11 @@ void Engine::flush_pending(size_t keep)
                tp.stop = take_event();
                cudaEventRecord(tp.start, stream_);
           }
-          if (!dry_run_)
+          if (dry_run_) {
+               const std::vector<hiqk_diag_op> batch(pending_.begin(), pending_.begin() + take);
+               record_launch(HIQ_LAUNCH_DIAG_BATCH, {{nullptr, &batch}});
+          }
+          else
                cu(hiqk_apply_diag_batch(slab_.data(), static_cast<int>(locals_.size()), pending_.data(), static_cast<int>(take), stream_));
           ++stats_.gate_launches;
           if (timing_) {
@@ -649,7 +692,11 @@ void Engine::launch(const Descriptor& d, int variant, const std::vector<hiqk_dia
           cudaEventRecord(tp.start, stream_);
      }
      ++stats_.gate_launches;
-     if (dry_run_) return;
+     if (dry_run_) {
+          if (ops.empty()) launches_.push_back(d);
+          else record_launch(HIQ_LAUNCH_DENSE_PREDIAG, {{&d, &ops}});
+          return;
+     }
      switch (d.kind) {
           case HIQ_DESC_DENSE:
                if (!ops.empty())
@@ -1001,7 +1048,7 @@ void Engine::swap_qubits(const std::vector<Index>& pairs)
                d.aux.push_back(gpos[i]);
                d.aux.push_back(slots[i]);
           }
-          trace_.push_back(d);
+          trace_op(d);
      }
      if (!dry_run_ && !gpos.empty()) {
           flush_pending();

@@ -97,7 +97,14 @@ public:
      };
      std::vector<PassTime> collect_timings();
      const std::vector<Descriptor>& trace() const { return trace_; }
-     void clear_trace() { trace_.clear(); }
+     // dry-run engines only: what would really be LAUNCHED, in device order — the plan's non-gate descriptors as they are,
+     // single gates as they are, and HIQ_DESC_LAUNCH records for launches that carry several passes of the plan
+     const std::vector<Descriptor>& launch_trace() const { return launches_; }
+     void clear_trace()
+     {
+          trace_.clear();
+          launches_.clear();
+     }
      void set_dense_variant(int v) { dense_variant_ = v; }
 
      // ---- operator-level calls of the reference wrapper that the reference class lacks (engine_ops.cpp;
@@ -201,6 +208,13 @@ private:
 
      EngineStats stats_;
      std::vector<Descriptor> trace_;
+     std::vector<Descriptor> launches_;
+     void trace_op(const Descriptor& d);  // a non-gate operation of the plan (swap, grow, fill, operator passes ...)
+     struct LaunchStepRef {
+          const Descriptor* gate;  // nullptr: diagonal factors only
+          const std::vector<hiqk_diag_op>* ops;
+     };
+     void record_launch(int form, const std::vector<LaunchStepRef>& steps);
      struct TimedPass {
           int kind, k, variant, n_ref;
           cudaEvent_t start, stop;

@@ -164,7 +164,7 @@ double Engine::get_expectation_value(const std::vector<PauliTerm>& terms, const 
                }
                for (size_t t0 = 0; t0 < g.terms.size(); t0 += HIQK_MAX_PAULI_TERMS) {
                     const int nt = static_cast<int>(std::min<size_t>(HIQK_MAX_PAULI_TERMS, g.terms.size() - t0));
-                    if (tracing_ && begin == 0) trace_.push_back(pauli_descriptor(HIQ_DESC_PAULI_EXPECT, 0, g.lx, partner, &g.terms[t0], nt));
+                    if (tracing_ && begin == 0) trace_op(pauli_descriptor(HIQ_DESC_PAULI_EXPECT, 0, g.lx, partner, &g.terms[t0], nt));
                     if (dry_run_) continue;
                     double v[2];
                     cu(hiqk_pauli_expect(slab_.data(), L, g.lx, &g.terms[t0], nt, staging, begin, piece, d_vals_, workspace_, stream_));
@@ -191,7 +191,7 @@ void Engine::apply_qubit_operator(const std::vector<PauliTerm>& terms, const std
                Descriptor d;
                d.kind = HIQ_DESC_SCALE;
                d.payload = {cplx(0.0)};
-               trace_.push_back(d);
+               trace_op(d);
           }
           if (!dry_run_) cu(check_cuda(cudaMemsetAsync(slab_.data(), 0, n * sizeof(double2), stream_), "cudaMemsetAsync"));
           return;
@@ -200,7 +200,7 @@ void Engine::apply_qubit_operator(const std::vector<PauliTerm>& terms, const std
           // every term moves amplitude i to the same place: in place, one pass
           const PauliGroup& g = groups[0];
           const int nt = static_cast<int>(g.terms.size());
-          if (tracing_) trace_.push_back(pauli_descriptor(HIQ_DESC_PAULI_APPLY, 0, g.lx, rank_, g.terms.data(), nt));
+          if (tracing_) trace_op(pauli_descriptor(HIQ_DESC_PAULI_APPLY, 0, g.lx, rank_, g.terms.data(), nt));
           if (!dry_run_) cu(hiqk_pauli_apply(slab_.data(), L, g.lx, g.terms.data(), nt, nullptr, 0, nullptr, 0, n, stream_));
           return;
      }
@@ -215,7 +215,7 @@ void Engine::apply_qubit_operator(const std::vector<PauliTerm>& terms, const std
           const uint64_t piece = g.gx ? std::min(n, kPieceAmps) : n;
           for (size_t t0 = 0; t0 < g.terms.size(); t0 += HIQK_MAX_PAULI_TERMS) {
                const int nt = static_cast<int>(std::min<size_t>(HIQK_MAX_PAULI_TERMS, g.terms.size() - t0));
-               if (tracing_) trace_.push_back(pauli_descriptor(HIQ_DESC_PAULI_APPLY, first ? 1 : 2, g.lx, partner, &g.terms[t0], nt));
+               if (tracing_) trace_op(pauli_descriptor(HIQ_DESC_PAULI_APPLY, first ? 1 : 2, g.lx, partner, &g.terms[t0], nt));
                if (!dry_run_) {
                     for (uint64_t begin = 0; begin < n; begin += piece) {
                          double2* staging = nullptr;
@@ -232,7 +232,7 @@ void Engine::apply_qubit_operator(const std::vector<PauliTerm>& terms, const std
      if (tracing_) {
           Descriptor d;
           d.kind = HIQ_DESC_PAULI_COMMIT;
-          trace_.push_back(d);
+          trace_op(d);
      }
      if (!dry_run_) {
           // every send of this rank's slab was issued on stream_ before this copy, so the partners have their data
@@ -343,7 +343,7 @@ void Engine::set_wavefunction(const cplx* amps, uint64_t n_amps, const std::vect
           Descriptor d;
           d.kind = HIQ_DESC_LOAD;
           d.aux = {slice};
-          trace_.push_back(d);
+          trace_op(d);
      }
      if (dry_run_) return;
      flush_pending();
@@ -430,7 +430,7 @@ void Engine::emulate_math(int kind, uint64_t a, uint64_t N, const std::vector<ui
           for (int b = 0; b < perm.n_bits; ++b) d.aux.push_back(perm.pos[b]);
           if (inverse.size() <= (1u << 20))  // larger tables are not worth carrying in a trace
                for (uint32_t v: inverse) d.aux.push_back(v);
-          trace_.push_back(d);
+          trace_op(d);
      }
      if (dry_run_) return;
      flush_pending();

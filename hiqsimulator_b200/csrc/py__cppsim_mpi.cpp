@@ -316,21 +316,25 @@ public:
           d["tile_steps"] = s.tile_steps;
           return d;
      }
-     py::list trace()
+     py::list trace() { return trace_list(hiq_trace_count, hiq_trace_get); }
+     // dry-run engines: the launches behind the plan (diagonal folding and tile runs applied), see include/hiq_b200.h
+     py::list launch_trace() { return trace_list(hiq_launch_trace_count, hiq_launch_trace_get); }
+     py::list trace_list(int (*count)(hiq_engine*, int*), int (*get)(hiq_engine*, int, hiq_descriptor*, double*, int, int64_t*, int))
      {
           int n = 0;
-          check(hiq_trace_count(e_, &n));
+          check(count(e_, &n));
           py::list out;
           for (int i = 0; i < n; ++i) {
                hiq_descriptor d;
-               check(hiq_trace_get(e_, i, &d, nullptr, 0, nullptr, 0));
+               check(get(e_, i, &d, nullptr, 0, nullptr, 0));
                py::array_t<cplx> payload(d.n_payload);
                std::vector<int64_t> aux(d.n_aux);
-               check(hiq_trace_get(e_, i, &d, reinterpret_cast<double*>(payload.mutable_data()), d.n_payload, aux.data(), d.n_aux));
+               check(get(e_, i, &d, reinterpret_cast<double*>(payload.mutable_data()), d.n_payload, aux.data(), d.n_aux));
                py::dict r;
                r["kind"] = d.kind;
                r["k"] = d.k;
                r["slots"] = std::vector<int>(d.slots, d.slots + (d.kind == HIQ_DESC_DENSE || d.kind == HIQ_DESC_DIAG ? d.k : 0));
+               if (d.kind == HIQ_DESC_LAUNCH) r["form"] = d.slots[0];
                r["ctrl_mask"] = d.ctrl_mask;
                r["payload"] = payload;
                r["aux"] = aux;
@@ -425,6 +429,7 @@ PYBIND11_MODULE(_cppsim_mpi, m)
          .def("local_slab_ptr", &SimulatorB200::local_slab_ptr)
          .def("stats", &SimulatorB200::stats)
          .def("trace", &SimulatorB200::trace)
+         .def("launch_trace", &SimulatorB200::launch_trace)
          .def("clear_trace", &SimulatorB200::clear_trace)
          .def("collect_timings", &SimulatorB200::collect_timings)
          .def("stream_ptr", &SimulatorB200::stream_ptr);

@@ -823,6 +823,84 @@ extern "C" int hiqk_tile_program_fits(int L, int n_steps, const hiqk_tile_step* 
      return pl.T;
 }
 
+// Host-only: the parameter image of a launch (see include/hiq_b200.h).  Header words, in order: magic, tile bits,
+// sizeof(TileParams), sizeof(TileStepDesc), max steps, max ops, table-pool entries, sizeof(InsertBits), then the offsets
+// of the TileParams fields {n_tiles, n_steps, lo, outer, swz_mask, ioff, pi, tslot, step, n_lut, lut_pad, m, msum} and of
+// the TileStepDesc fields {ks, n_ops, n_e, sel_off, n_t, n_em, in_mask, n_in, n_out, out_slot, mono_row, tpos, ploff,
+// lut_off, lpos, outer, esel}.
+namespace {
+constexpr int kImageHeaderWords = 64;
+}
+
+extern "C" size_t hiqk_tile_program_image_bytes(void)
+{
+     return kImageHeaderWords * sizeof(uint32_t) + sizeof(TileParams) + sizeof(double2) * kTileLutEntries;
+}
+
+extern "C" int hiqk_tile_program_image(int L, int n_steps, const hiqk_tile_step* steps, void* image, size_t image_bytes)
+{
+     if (!steps || !image) return set_error(HIQ_ERR_ARG, "hiqk_tile_program_image: null argument");
+     if (image_bytes < hiqk_tile_program_image_bytes()) return set_error(HIQ_ERR_ARG, "hiqk_tile_program_image: buffer too small");
+     if (n_steps < 1 || n_steps > kTileMaxSteps || L > 40)
+          return set_error(HIQ_ERR_ARG, "hiqk_tile_program_image: a tile program holds 1.." + std::to_string(kTileMaxSteps) + " gates");
+     TilePlan pl;
+     std::string why;
+     if (!choose_tile(L, n_steps, steps, pl, why)) return set_error(HIQ_ERR_ARG, "hiqk_tile_program_image: " + why);
+     plan_steps(n_steps, steps, pl);
+     solve_swizzle(pl);
+     uint32_t* head = static_cast<uint32_t*>(image);
+     TileParams* p = reinterpret_cast<TileParams*>(head + kImageHeaderWords);
+     double2* lut = reinterpret_cast<double2*>(reinterpret_cast<char*>(p) + sizeof(TileParams));
+     std::memset(image, 0, hiqk_tile_program_image_bytes());
+     const int rc = fill_params(*p, lut, nullptr, L, n_steps, steps, pl, why);
+     if (rc != HIQ_OK) return set_error(rc, "hiqk_tile_program_image: " + why);
+     int w = 0;
+     head[w++] = 0x50545148u;  // 'HQTP'
+     head[w++] = static_cast<uint32_t>(pl.T);
+     head[w++] = sizeof(TileParams);
+     head[w++] = sizeof(TileStepDesc);
+     head[w++] = kTileMaxSteps;
+     head[w++] = kTileMaxOps;
+     head[w++] = kTileLutEntries;
+     head[w++] = sizeof(InsertBits);
+#define HIQ_P_OFF(field) head[w++] = static_cast<uint32_t>(offsetof(TileParams, field))
+     HIQ_P_OFF(n_tiles);
+     HIQ_P_OFF(n_steps);
+     HIQ_P_OFF(lo);
+     HIQ_P_OFF(outer);
+     HIQ_P_OFF(swz_mask);
+     HIQ_P_OFF(ioff);
+     HIQ_P_OFF(pi);
+     HIQ_P_OFF(tslot);
+     HIQ_P_OFF(step);
+     HIQ_P_OFF(n_lut);
+     HIQ_P_OFF(lut_pad);
+     HIQ_P_OFF(m);
+     HIQ_P_OFF(msum);
+#undef HIQ_P_OFF
+#define HIQ_S_OFF(field) head[w++] = static_cast<uint32_t>(offsetof(TileStepDesc, field))
+     HIQ_S_OFF(ks);
+     HIQ_S_OFF(n_ops);
+     HIQ_S_OFF(n_e);
+     HIQ_S_OFF(sel_off);
+     HIQ_S_OFF(n_t);
+     HIQ_S_OFF(n_em);
+     HIQ_S_OFF(in_mask);
+     HIQ_S_OFF(n_in);
+     HIQ_S_OFF(n_out);
+     HIQ_S_OFF(out_slot);
+     HIQ_S_OFF(mono_row);
+     HIQ_S_OFF(tpos);
+     HIQ_S_OFF(ploff);
+     HIQ_S_OFF(lut_off);
+     HIQ_S_OFF(lpos);
+     HIQ_S_OFF(outer);
+     HIQ_S_OFF(esel);
+#undef HIQ_S_OFF
+     static_assert(8 + 13 + 17 <= kImageHeaderWords, "header words");
+     return HIQ_OK;
+}
+
 extern "C" int hiqk_apply_tile_program(void* slab, int L, int n_steps, const hiqk_tile_step* steps, void* stream)
 {
      if (!slab || !steps) return set_error(HIQ_ERR_ARG, "hiqk_apply_tile_program: null argument");

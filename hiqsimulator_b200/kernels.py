@@ -120,6 +120,16 @@ def apply_tile_program(state, steps):
     check(lib().hiqk_apply_tile_program(p, L, len(steps), arr, _stream()))
 
 
+def tile_program_image(L, steps) -> bytes:
+    """the kernel-parameter image apply_tile_program would launch with (header | parameters | table pool) — host only,
+    nothing is computed; tests/tile_emulator.py interprets it"""
+    arr, keep = _tile_steps(steps)
+    n = lib().hiqk_tile_program_image_bytes()
+    buf = C.create_string_buffer(n)
+    check(lib().hiqk_tile_program_image(L, len(steps), arr, buf, n))
+    return buf.raw
+
+
 def dense_prediag_supported(L, slots) -> bool:
     return bool(lib().hiqk_dense_prediag_supported(L, len(slots), _ints(slots)))
 

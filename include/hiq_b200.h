@@ -158,6 +158,15 @@ int hiqk_tile_program_fits(int L, int n_steps, const hiqk_tile_step* steps);
  * phase gates) — a tile program applies it without summing products.  Host only. */
 int hiqk_dense_is_monomial(int k, const double* matrix);
 int hiqk_apply_tile_program(void* slab, int L, int n_steps, const hiqk_tile_step* steps, void* stream);
+/* The kernel-parameter image hiqk_apply_tile_program would launch with, written to host memory — no device call, no
+ * computation: tile choice, tuple layout, bank swizzle, matrices in planned bit order, diagonal-op classes and table
+ * pool exactly as the launcher encodes them.  Layout: 64 x uint32 header (magic 'HQTP', tile bits, structure sizes and
+ * the byte offset of every field: see hiqk_tile_program_image in csrc/tile_program.cu), the parameter structure (slab and
+ * table pointers null), the table pool (complex128).  Lets the launcher's host logic be checked where no GPU is
+ * (tests/tile_emulator.py interprets the image with numpy).  Returns HIQ_OK or HIQ_ERR_* like every other call;
+ * hiqk_tile_program_image_bytes() = the buffer size to pass. */
+size_t hiqk_tile_program_image_bytes(void);
+int hiqk_tile_program_image(int L, int n_steps, const hiqk_tile_step* steps, void* image, size_t image_bytes);
 
 /* Remove bit `slot` from the index space keeping the half where that bit == keep:
  * dst[j] = src[insert_bit(j, slot, keep)], j < 2^(L-1).  dst may alias the start of src
@@ -284,6 +293,14 @@ typedef struct hiq_engine hiq_engine;
 #define HIQ_DESC_PERMUTE 10
 #define HIQ_DESC_LOAD 11 /* set_wavefunction: aux = [slice of the host vector this rank copies, -1 = zeros] */
 #define HIQ_DESC_TILE 12 /* timing records only: one tile-resident launch that carried k dense gates of the plan */
+/* launch trace only (hiq_launch_trace_*): ONE device launch that carries several passes of the plan.  k = steps,
+ * slots[0] = form (HIQ_LAUNCH_*); aux = per step [targets k_s (-1: no dense gate), slot_0 .. slot_{k_s-1}, n_ops, then per
+ * diagonal factor: k_o, slot_0 .. slot_{k_o-1}]; payload = per step the 4^k_s matrix entries, then per factor its 2^k_o
+ * table.  Every step = its factors first, then its dense gate. */
+#define HIQ_DESC_LAUNCH 13
+#define HIQ_LAUNCH_DIAG_BATCH 0    /* hiqk_apply_diag_batch */
+#define HIQ_LAUNCH_DENSE_PREDIAG 1 /* hiqk_apply_dense_prediag */
+#define HIQ_LAUNCH_TILE 2          /* hiqk_apply_tile_program */
 
 typedef struct hiq_descriptor {
      int kind;           /* HIQ_DESC_* */
@@ -389,6 +406,11 @@ int hiq_stream(hiq_engine* e, void** stream);
 int hiq_trace_count(hiq_engine* e, int* n);
 int hiq_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux);
 int hiq_trace_clear(hiq_engine* e);
+/* launch trace of a HIQ_FLAG_DRY_RUN engine: what would really be launched, in device order — the plan's descriptors
+ * after diagonal folding and tile-run grouping (non-gate descriptors and single gates unchanged, HIQ_DESC_LAUNCH records
+ * for the launches that carry several passes).  Same accessors as the descriptor trace; cleared by hiq_trace_clear. */
+int hiq_launch_trace_count(hiq_engine* e, int* n);
+int hiq_launch_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux);
 
 #ifdef __cplusplus
 }

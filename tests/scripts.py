@@ -354,7 +354,66 @@ def script_from_json(s):
 
 # ------------------------------------------------------------------ dry-run trace replay
 KIND = {"none": 0, "dense": 1, "diag": 2, "scale": 3, "swap": 4, "grow": 5, "fill": 6,
-        "pauli_expect": 7, "pauli_apply": 8, "pauli_commit": 9, "permute": 10, "load": 11}
+        "pauli_expect": 7, "pauli_apply": 8, "pauli_commit": 9, "permute": 10, "load": 11, "launch": 13}
+LAUNCH_DIAG_BATCH, LAUNCH_DENSE_PREDIAG, LAUNCH_TILE = 0, 1, 2
+
+
+def decode_launch(d):
+    """HIQ_DESC_LAUNCH record (include/hiq_b200.h) -> [(slots or None, matrix or None, [(slots, table), ...]), ...]"""
+    aux = [int(x) for x in d["aux"]]
+    pay = np.asarray(d["payload"])
+    a = p = 0
+    steps = []
+    for _ in range(int(d["k"])):
+        k = aux[a]
+        a += 1
+        slots = m = None
+        if k >= 0:
+            slots = tuple(aux[a:a + k])
+            a += k
+        n_ops = aux[a]
+        a += 1
+        if k >= 0:
+            m = pay[p:p + (1 << (2 * k))].reshape(1 << k, 1 << k)
+            p += 1 << (2 * k)
+        ops = []
+        for _ in range(n_ops):
+            ko = aux[a]
+            a += 1
+            ops.append((list(aux[a:a + ko]), pay[p:p + (1 << ko)]))
+            a += ko
+            p += 1 << ko
+        steps.append((slots, m, ops))
+    assert a == len(aux) and p == len(pay)
+    return steps
+
+
+def _apply_launch(vec, d, info):
+    """one multi-pass launch of a launch trace with the oracle kernels; tile programs additionally go through the
+    launcher's parameter image + tests/tile_emulator.py when info["tile_emulator"] is set (slab of >= 2^11 amplitudes)"""
+    steps = decode_launch(d)
+    emu = None
+    if d["form"] == LAUNCH_TILE and info.get("tile_emulator"):
+        import tile_emulator
+        from hiqsimulator_b200 import kernels as K
+        L = int(np.log2(vec.shape[0]))
+        emu = vec.copy()
+        tile_emulator.run_image(K.tile_program_image(L, steps), emu)
+    for slots, m, ops in steps:
+        for sl, table in ops:
+            if sl:
+                statevec.apply_diag(vec, sl, table, 0)
+            else:
+                vec *= table[0]
+        if m is not None:
+            statevec.apply_dense(vec, list(slots), m, 0)
+    key = {LAUNCH_DIAG_BATCH: "diag_batch", LAUNCH_DENSE_PREDIAG: "dense_prediag", LAUNCH_TILE: "tile"}[d["form"]]
+    info.setdefault("launch_forms", {}).setdefault(key, 0)
+    info["launch_forms"][key] += 1
+    if emu is not None:
+        err = float(np.abs(emu - vec).max())
+        assert err <= 1e-12, "tile image of a scheduled run differs from the oracle by %g" % err
+        info["tile_images_emulated"] = info.get("tile_images_emulated", 0) + 1
 _COLLECTIVE = {KIND["swap"], KIND["pauli_expect"], KIND["pauli_apply"], KIND["pauli_commit"], KIND["permute"], KIND["load"]}
 
 
@@ -387,6 +446,8 @@ def replay_traces(traces, R, info=None):
                     statevec.apply_diag(vec[r], list(d["slots"]), np.asarray(d["payload"]), int(d["ctrl_mask"]))
                 elif d["kind"] == KIND["scale"]:
                     vec[r] *= d["payload"][0]
+                elif d["kind"] == KIND["launch"]:
+                    _apply_launch(vec[r], d, info)
             if cursors[r] < len(t):
                 stops.append(t[cursors[r]])
                 cursors[r] += 1

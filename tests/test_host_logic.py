@@ -56,6 +56,29 @@ def test_dry_run_traces_reproduce_reference_state(name):
         assert got == id2pos and nl == len(e.get_local_qubits_ids())
 
 
+@pytest.mark.parametrize("name", golden_names())
+def test_launch_traces_reproduce_reference_state(name):
+    """the LAUNCH trace of the same runs (what the device would be handed after diagonal folding and tile-run grouping:
+    batched diagonal passes, dense launches that carry factors, tile programs) replays to the same state"""
+    R, script, exp = load_golden(name)
+    prefix = _gate_prefix(script)
+    engines = _dry_engines(script, R)
+    for op in prefix[1:]:
+        if op[0] == "cheat_local":
+            break
+        for e in engines:
+            getattr(e, op[0])(*op[1:])
+    for e in engines:
+        e.synchronize()  # closes the launch accounting: queued gates go out
+    info = {"tile_emulator": True}
+    state = scripts.replay_traces([e.launch_trace() for e in engines], R, info)
+    id2pos, vec = exp[len(prefix) - 1]
+    assert np.abs(state - vec).max() <= 1e-12
+    for e in engines:  # every pass of the plan is carried by some launch, and folding only ever reduces their number
+        st = e.stats()
+        assert st["gate_launches"] <= st["dense_passes"] + st["diag_passes"] + st["scale_passes"]
+
+
 def test_allocation_policy_matches_reference_example():
     """R=8, max_cluster=4, allocate_qureg(range(35))."""
     from hiqsimulator_b200 import _cppsim_mpi as M
@@ -211,6 +234,55 @@ def test_scheduled_script_dry_run_equals_compiled_reference(kind, n, R):
     state = scripts.replay_traces([e.trace() for e in engines], R)
     assert ids == list(res[-2])
     assert np.abs(state - res[-1][1]).max() <= 1e-12
+
+
+@pytest.mark.parametrize("kind,n,R", [("random", 16, 1), ("qft", 17, 1), ("random", 15, 2), ("qft", 16, 4), ("random", 16, 8)])
+def test_scheduled_launch_traces_equal_compiled_reference(kind, n, R):
+    """the bench pipeline on dry-run engines with enough local qubits for tile runs to form (L >= 11): the launch trace —
+    tile programs executed through the launcher's parameter image and tests/tile_emulator.py — equals the compiled
+    reference run as R processes.  Covers on the CPU what test_engine_tile_runs_match_oracle covers on the GPU:
+    the engine's grouping (which diagonals may ride along which gate, which gates share a tile) and the launcher's
+    encoding of the runs the scheduler really produces."""
+    from oracle import ref
+    if not ref.have_ref():
+        pytest.skip("oracle/_ref is not built")
+    script, shape = scripts.scheduled_script(kind, n, R)
+    res = scripts.merge_rank_outputs(ref.run_script(script, R, 1))
+    engines = _dry_engines(script, R)
+    for op in script[1:-1]:
+        for e in engines:
+            getattr(e, op[0])(*op[1:])
+    for e in engines:
+        e.synchronize()
+    info = {"tile_emulator": True}
+    state = scripts.replay_traces([e.launch_trace() for e in engines], R, info)
+    assert np.abs(state - res[-1][1]).max() <= 1e-12
+    st = engines[0].stats()
+    assert st["tile_launches"] >= 1 and info["tile_images_emulated"] >= R  # tile runs did form, on every rank
+    assert info["launch_forms"]["tile"] == sum(e.stats()["tile_launches"] for e in engines)
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_launch_trace_equals_plan_trace_on_random_scripts(seed):
+    """random gate streams with diagonal gates, controls, swaps (tests/scripts.random_script): the launches the engine forms
+    (batched diagonals, dense gates carrying factors, tile runs — all three forms occur) compute what the plan's
+    one-pass-per-fused-gate sequence computes; the plan traces themselves are pinned to the reference elsewhere in this file"""
+    R = [1, 2, 4, 1][seed % 4]
+    nq = 13 + seed % 4 + (R.bit_length() - 1)
+    script = scripts.random_script(nq, R, 300 + seed, ngates=150, queries=False)
+    engines = _dry_engines(script, R)
+    for op in script[1:]:
+        if op[0] == "cheat_local":
+            continue
+        for e in engines:
+            getattr(e, op[0])(*op[1:])
+    for e in engines:
+        e.synchronize()
+    info = {"tile_emulator": True}
+    launched = scripts.replay_traces([e.launch_trace() for e in engines], R, info)
+    planned = scripts.replay_traces([e.trace() for e in engines], R)
+    assert np.abs(launched - planned).max() <= 1e-12
+    assert info.get("tile_images_emulated", 0) >= 1
 
 
 @pytest.mark.parametrize("R", [1, 4])

@@ -290,14 +290,9 @@ TILE_RUNS += [
 ]
 
 
-@pytest.mark.parametrize("case", range(len(TILE_RUNS)))
-def test_tile_program_matches_oracle(case):
-    """a run of dense gates, each preceded by diagonal factors, in ONE tile-resident pass == the reference's
-    one-sweep-per-fused-gate sequence (numpy oracle), every target / select / class-E configuration"""
-    torch = _torch()
-    from hiqsimulator_b200 import kernels as K
+def tile_case(case):
+    """(L, steps, expected tile bits) of TILE_RUNS[case]; tests/test_tile_program_cpu.py runs the same cases on the CPU"""
     L, run, tile_bits = TILE_RUNS[case]
-    rng = np.random.default_rng(900 + case)
     steps = []
     for i, (k, slots, select, n_pre) in enumerate(run):
         if select is None:
@@ -314,6 +309,16 @@ def test_tile_program_matches_oracle(case):
             other = [s for s in range(L) if s not in slots]
             ops[1] = ([slots[0], other[0], other[-1]], np.exp(1j * np.linspace(0.3, 3.0, 8)))
         steps.append((slots, m, ops))
+    return L, steps, tile_bits
+
+
+@pytest.mark.parametrize("case", range(len(TILE_RUNS)))
+def test_tile_program_matches_oracle(case):
+    """a run of dense gates, each preceded by diagonal factors, in ONE tile-resident pass == the reference's
+    one-sweep-per-fused-gate sequence (numpy oracle), every target / select / class-E configuration"""
+    torch = _torch()
+    from hiqsimulator_b200 import kernels as K
+    L, steps, tile_bits = tile_case(case)
     assert K.tile_program_fits(L, steps) == tile_bits
     ref = rand_state(L, 800 + case)
     dev = torch.from_numpy(ref.copy()).cuda()
