@@ -578,16 +578,18 @@ static int launch_direct(double2* psi, int L, const int* slots, const double* ma
      return with_ks<K>(ks, [&](auto ks_c) { return go(ks_c, std::false_type{}); });
 }
 
+// Host part of the folded-diagonal launch: index split (tid | t | chunk), diagonal program, class-E pattern tables.
 template <int K>
-static int launch_direct_pre(double2* psi, int L, const int* slots, const double* matrix, const hiqk_diag_op* pre, int n_pre,
-                             cudaStream_t stream, int ks = K)
+struct DirectPreShape {
+     static constexpr int THREADS = (K >= 3) ? 128 : 256;
+     static constexpr int TID_BITS = (K >= 3) ? 7 : 8;
+};
+
+template <int K>
+static int fill_direct_pre(DirectPreParams<K>& p, double2* psi, int L, const int* slots, const double* matrix, const hiqk_diag_op* pre,
+                           int n_pre)
 {
-     static DirectPreParams<K> p;  // 10+ KB: keep it off the stack; launches are issued from one host thread per engine
-     static std::mutex mu;
-     std::lock_guard<std::mutex> lock(mu);
-     constexpr int THREADS = (K >= 3) ? 128 : 256;
-     constexpr int TID_BITS = (K >= 3) ? 7 : 8;
-     constexpr int MINB = 4;
+     constexpr int TID_BITS = DirectPreShape<K>::TID_BITS;
      uint64_t tmask = 0;
      for (int t = 0; t < K; ++t) tmask |= 1ull << slots[t];
      // tid occupies the TID_BITS lowest free index positions; t positions are picked among the rest
@@ -646,6 +648,20 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
      for (int j = je; j < p.prog.n; ++j)
           for (int t = 0; t < (1 << n_t); ++t)
                if (p.prog.usel[j][t]) p.fast = 0;
+     return HIQ_OK;
+}
+
+template <int K>
+static int launch_direct_pre(double2* psi, int L, const int* slots, const double* matrix, const hiqk_diag_op* pre, int n_pre,
+                             cudaStream_t stream, int ks = K)
+{
+     static DirectPreParams<K> p;  // 10+ KB: keep it off the stack; launches are issued from one host thread per engine
+     static std::mutex mu;
+     std::lock_guard<std::mutex> lock(mu);
+     constexpr int THREADS = DirectPreShape<K>::THREADS;
+     constexpr int MINB = 4;
+     const int rc = fill_direct_pre<K>(p, psi, L, slots, matrix, pre, n_pre);
+     if (rc != HIQ_OK) return rc;
      const size_t smem = sizeof(double2) * THREADS * ((1u << K) + std::max(p.e_npat, 1));
      const uint64_t n_chunks = (p.d.n_free + THREADS - 1) / THREADS;
      const uint64_t cap = grid_cap(static_cast<uint64_t>(num_sms()) * MINB * 8);
@@ -876,25 +892,20 @@ extern "C" int hiqk_dense_prediag_supported(int L, int k, const int* slots)
      return hiq::pick_variant(L, k, slots) == HIQK_DENSE_DIRECT ? 1 : 0;
 }
 
-extern "C" int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slots, const double* matrix,
-                                        const hiqk_diag_op* pre, int n_pre, void* stream)
+namespace hiq {
+// argument checks and block-shape permutation shared by the launch and by its parameter image
+static int prediag_prepare(const char* who, int L, int k, const int*& slots, const double*& matrix, int (&pslots)[kMaxTargets],
+                           double (&pm)[2 << (2 * 4)], int& ks)
 {
-     using namespace hiq;
-     if (!slab || !slots || !matrix) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: null argument");
-     if (n_pre == 0) return hiqk_apply_dense(slab, L, k, slots, matrix, 0, HIQK_DENSE_DIRECT, stream);
      if (!hiqk_dense_prediag_supported(L, k, slots))
-          return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: needs k <= 4 and targets the DIRECT kernel takes");
+          return set_error(HIQ_ERR_ARG, std::string(who) + ": needs k <= 4 and targets the DIRECT kernel takes");
      uint64_t tmask = 0;
      for (int l = 0; l < k; ++l) {
           if (slots[l] < 0 || slots[l] >= L || ((tmask >> slots[l]) & 1))
-               return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: target slots must be distinct and < L");
+               return set_error(HIQ_ERR_ARG, std::string(who) + ": target slots must be distinct and < L");
           tmask |= 1ull << slots[l];
      }
-     double2* psi = static_cast<double2*>(slab);
-     cudaStream_t st = static_cast<cudaStream_t>(stream);
-     int pslots[kMaxTargets];
-     double pm[2 << (2 * 4)];
-     int ks = k;
+     ks = k;
      if (k >= 2 && dense_blocks_enabled()) {
           const DenseShape sh = dense_shape(k, matrix);
           if (sh.ks < k) {
@@ -904,6 +915,94 @@ extern "C" int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slo
                ks = sh.ks;
           }
      }
+     return HIQ_OK;
+}
+
+constexpr int kPreImageHeaderWords = 64;
+
+template <int K>
+static int direct_pre_image(int L, const int* slots, const double* matrix, const hiqk_diag_op* pre, int n_pre, int ks, void* image)
+{
+     uint32_t* head = static_cast<uint32_t*>(image);
+     DirectPreParams<K>* p = reinterpret_cast<DirectPreParams<K>*>(head + kPreImageHeaderWords);
+     const int rc = fill_direct_pre<K>(*p, nullptr, L, slots, matrix, pre, n_pre);
+     if (rc != HIQ_OK) return rc;
+     using P = DirectPreParams<K>;
+     int w = 0;
+     head[w++] = 0x50445148u;  // 'HQDP'
+     head[w++] = K;
+     head[w++] = DirectPreShape<K>::THREADS;
+     head[w++] = static_cast<uint32_t>(ks);  // mixing bits the kernel uses (block form when < K)
+     head[w++] = (K == 4 && ks == K && dense_3m_enabled()) ? 1 : 0;  // three-multiplication product
+     head[w++] = sizeof(P);
+     head[w++] = kMaxDiagOps;
+     head[w++] = 1 << kMaxUBits;
+     head[w++] = 1 << kMaxTargets;
+     head[w++] = 1 << kMaxTBits;
+     head[w++] = sizeof(InsertBits);
+     head[w++] = static_cast<uint32_t>(offsetof(P, d) + offsetof(DirectParams<K>, n_free));
+     head[w++] = static_cast<uint32_t>(offsetof(P, d) + offsetof(DirectParams<K>, ins));
+     head[w++] = static_cast<uint32_t>(offsetof(P, d) + offsetof(DirectParams<K>, off));
+     head[w++] = static_cast<uint32_t>(offsetof(P, d) + offsetof(DirectParams<K>, m));
+     head[w++] = static_cast<uint32_t>(offsetof(P, d) + offsetof(DirectParams<K>, msum));
+     head[w++] = static_cast<uint32_t>(offsetof(P, n_t));
+     head[w++] = static_cast<uint32_t>(offsetof(P, fast));
+     head[w++] = static_cast<uint32_t>(offsetof(P, toff));
+     head[w++] = static_cast<uint32_t>(offsetof(P, e_npat));
+     head[w++] = static_cast<uint32_t>(offsetof(P, e_pat));
+     head[w++] = static_cast<uint32_t>(offsetof(P, e_cmap));
+     head[w++] = static_cast<uint32_t>(offsetof(P, prog));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_s0));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_s1));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_e));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_s0a));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, slots));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, usel));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, lut));
+     return HIQ_OK;
+}
+}  // namespace hiq
+
+extern "C" size_t hiqk_dense_prediag_image_bytes(void)
+{
+     return hiq::kPreImageHeaderWords * sizeof(uint32_t) + sizeof(hiq::DirectPreParams<4>);
+}
+
+// Host-only: the kernel parameters hiqk_apply_dense_prediag would launch with (see include/hiq_b200.h).
+extern "C" int hiqk_dense_prediag_image(int L, int k, const int* slots, const double* matrix, const hiqk_diag_op* pre, int n_pre,
+                                        void* image, size_t image_bytes)
+{
+     using namespace hiq;
+     if (!slots || !matrix || !pre || !image) return set_error(HIQ_ERR_ARG, "hiqk_dense_prediag_image: null argument");
+     if (image_bytes < hiqk_dense_prediag_image_bytes()) return set_error(HIQ_ERR_ARG, "hiqk_dense_prediag_image: buffer too small");
+     int pslots[kMaxTargets];
+     double pm[2 << (2 * 4)];
+     int ks = k;
+     const int rc = prediag_prepare("hiqk_dense_prediag_image", L, k, slots, matrix, pslots, pm, ks);
+     if (rc != HIQ_OK) return rc;
+     std::memset(image, 0, hiqk_dense_prediag_image_bytes());
+     switch (k) {
+          case 1: return direct_pre_image<1>(L, slots, matrix, pre, n_pre, ks, image);
+          case 2: return direct_pre_image<2>(L, slots, matrix, pre, n_pre, ks, image);
+          case 3: return direct_pre_image<3>(L, slots, matrix, pre, n_pre, ks, image);
+          default: return direct_pre_image<4>(L, slots, matrix, pre, n_pre, ks, image);
+     }
+}
+
+extern "C" int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slots, const double* matrix,
+                                        const hiqk_diag_op* pre, int n_pre, void* stream)
+{
+     using namespace hiq;
+     if (!slab || !slots || !matrix) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: null argument");
+     if (n_pre == 0) return hiqk_apply_dense(slab, L, k, slots, matrix, 0, HIQK_DENSE_DIRECT, stream);
+     double2* psi = static_cast<double2*>(slab);
+     cudaStream_t st = static_cast<cudaStream_t>(stream);
+     int pslots[kMaxTargets];
+     double pm[2 << (2 * 4)];
+     int ks = k;
+     const int rc = prediag_prepare("hiqk_apply_dense_prediag", L, k, slots, matrix, pslots, pm, ks);
+     if (rc != HIQ_OK) return rc;
      switch (k) {
           case 1: return launch_direct_pre<1>(psi, L, slots, matrix, pre, n_pre, st);
           case 2: return launch_direct_pre<2>(psi, L, slots, matrix, pre, n_pre, st, ks);

@@ -400,18 +400,15 @@ int hiq::build_diag_prog(DiagProg& p, int L, const hiqk_diag_op* ops, int n_ops,
      return HIQ_OK;
 }
 
-extern "C" int hiqk_apply_diag_batch(void* slab, int L, const hiqk_diag_op* ops, int n_ops, void* stream)
+namespace hiq {
+// host part of the batched diagonal launch: index split (tid = bits 0..7 | u | chunk) and the diagonal program
+static int fill_diag_batch(DiagBatchParams& p, double2* psi, int L, const hiqk_diag_op* ops, int n_ops, const char* who)
 {
-     if (!slab || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag_batch: bad argument");
-     if (!ops || n_ops < 1 || n_ops > kMaxDiagOps) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag_batch: need 1..16 diagonal ops");
-     static DiagBatchParams p;  // ~9 KB, launches are issued from one host thread per engine
-     static std::mutex mu;
-     std::lock_guard<std::mutex> lock(mu);
      int upos[kMaxUBits];
      const int n_u = choose_u_positions(L, ops, n_ops, 0xffull, kMaxUBits, upos);
-     const int rc = build_diag_prog(p.prog, L, ops, n_ops, upos, n_u, 0, 0xffull, nullptr, "hiqk_apply_diag_batch");
+     const int rc = build_diag_prog(p.prog, L, ops, n_ops, upos, n_u, 0, 0xffull, nullptr, who);
      if (rc != HIQ_OK) return rc;
-     p.psi = static_cast<double2*>(slab);
+     p.psi = psi;
      p.n = 1ull << L;
      p.n_u = n_u;
      p.n_chunks = L > 8 + n_u ? 1ull << (L - 8 - n_u) : 1;
@@ -424,6 +421,58 @@ extern "C" int hiqk_apply_diag_batch(void* slab, int L, const hiqk_diag_op* ops,
                if ((u >> b) & 1) o |= 1ull << upos[b];
           p.uoff[u] = o;
      }
+     return HIQ_OK;
+}
+constexpr int kBatchImageHeaderWords = 32;
+}  // namespace hiq
+
+extern "C" size_t hiqk_diag_batch_image_bytes(void) { return kBatchImageHeaderWords * sizeof(uint32_t) + sizeof(DiagBatchParams); }
+
+// Host-only: the kernel parameters hiqk_apply_diag_batch would launch with (see include/hiq_b200.h).
+extern "C" int hiqk_diag_batch_image(int L, const hiqk_diag_op* ops, int n_ops, void* image, size_t image_bytes)
+{
+     if (!image || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_diag_batch_image: bad argument");
+     if (!ops || n_ops < 1 || n_ops > kMaxDiagOps) return set_error(HIQ_ERR_ARG, "hiqk_diag_batch_image: need 1..16 diagonal ops");
+     if (image_bytes < hiqk_diag_batch_image_bytes()) return set_error(HIQ_ERR_ARG, "hiqk_diag_batch_image: buffer too small");
+     std::memset(image, 0, hiqk_diag_batch_image_bytes());
+     uint32_t* head = static_cast<uint32_t*>(image);
+     DiagBatchParams* p = reinterpret_cast<DiagBatchParams*>(head + kBatchImageHeaderWords);
+     const int rc = fill_diag_batch(*p, nullptr, L, ops, n_ops, "hiqk_diag_batch_image");
+     if (rc != HIQ_OK) return rc;
+     int w = 0;
+     head[w++] = 0x42445148u;  // 'HQDB'
+     head[w++] = kStreamThreads;
+     head[w++] = sizeof(DiagBatchParams);
+     head[w++] = kMaxDiagOps;
+     head[w++] = 1 << kMaxUBits;
+     head[w++] = 1 << kMaxTargets;
+     head[w++] = sizeof(InsertBits);
+     head[w++] = static_cast<uint32_t>(offsetof(DiagBatchParams, n));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagBatchParams, n_chunks));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagBatchParams, n_u));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagBatchParams, ins));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagBatchParams, uoff));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagBatchParams, prog));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_s0));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_s1));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_e));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, n_s0a));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, slots));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, usel));
+     head[w++] = static_cast<uint32_t>(offsetof(DiagProg, lut));
+     return HIQ_OK;
+}
+
+extern "C" int hiqk_apply_diag_batch(void* slab, int L, const hiqk_diag_op* ops, int n_ops, void* stream)
+{
+     if (!slab || L < 0 || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag_batch: bad argument");
+     if (!ops || n_ops < 1 || n_ops > kMaxDiagOps) return set_error(HIQ_ERR_ARG, "hiqk_apply_diag_batch: need 1..16 diagonal ops");
+     static DiagBatchParams p;  // ~9 KB, launches are issued from one host thread per engine
+     static std::mutex mu;
+     std::lock_guard<std::mutex> lock(mu);
+     const int rc = fill_diag_batch(p, static_cast<double2*>(slab), L, ops, n_ops, "hiqk_apply_diag_batch");
+     if (rc != HIQ_OK) return rc;
      const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(p.n_chunks, grid_cap(static_cast<uint64_t>(num_sms()) * 4 * 8)));
      diag_batch_kernel<<<grid, kStreamThreads, 0, static_cast<cudaStream_t>(stream)>>>(p);
      count_launch();

@@ -120,6 +120,25 @@ def apply_tile_program(state, steps):
     check(lib().hiqk_apply_tile_program(p, L, len(steps), arr, _stream()))
 
 
+def diag_batch_image(L, ops) -> bytes:
+    """the kernel parameters apply_diag_batch would launch with — host only; tests/diag_emulator.py interprets them"""
+    arr = _diag_ops(ops)
+    n = lib().hiqk_diag_batch_image_bytes()
+    buf = C.create_string_buffer(n)
+    check(lib().hiqk_diag_batch_image(L, arr, len(ops), buf, n))
+    return buf.raw
+
+
+def dense_prediag_image(L, slots, matrix, pre) -> bytes:
+    """the kernel parameters apply_dense_prediag would launch with — host only; tests/diag_emulator.py interprets them"""
+    keep, mp = _cplx(matrix)
+    arr = _diag_ops(pre)
+    n = lib().hiqk_dense_prediag_image_bytes()
+    buf = C.create_string_buffer(n)
+    check(lib().hiqk_dense_prediag_image(L, len(slots), _ints(slots), mp, arr, len(pre), buf, n))
+    return buf.raw
+
+
 def tile_program_image(L, steps) -> bytes:
     """the kernel-parameter image apply_tile_program would launch with (header | parameters | table pool) — host only,
     nothing is computed; tests/tile_emulator.py interprets it"""

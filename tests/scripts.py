@@ -389,16 +389,24 @@ def decode_launch(d):
 
 
 def _apply_launch(vec, d, info):
-    """one multi-pass launch of a launch trace with the oracle kernels; tile programs additionally go through the
-    launcher's parameter image + tests/tile_emulator.py when info["tile_emulator"] is set (slab of >= 2^11 amplitudes)"""
+    """one multi-pass launch of a launch trace with the oracle kernels; when info["tile_emulator"] is set it additionally goes
+    through its launcher's parameter image and the emulator of its kernel (tests/tile_emulator.py, tests/diag_emulator.py)"""
     steps = decode_launch(d)
     emu = None
-    if d["form"] == LAUNCH_TILE and info.get("tile_emulator"):
-        import tile_emulator
+    if info.get("tile_emulator"):
         from hiqsimulator_b200 import kernels as K
         L = int(np.log2(vec.shape[0]))
         emu = vec.copy()
-        tile_emulator.run_image(K.tile_program_image(L, steps), emu)
+        if d["form"] == LAUNCH_TILE:
+            import tile_emulator
+            tile_emulator.run_image(K.tile_program_image(L, steps), emu)
+        elif d["form"] == LAUNCH_DIAG_BATCH:
+            import diag_emulator
+            diag_emulator.run_diag_batch_image(K.diag_batch_image(L, steps[0][2]), emu)
+        else:
+            import diag_emulator
+            slots, m, ops = steps[0]
+            diag_emulator.run_dense_prediag_image(K.dense_prediag_image(L, list(slots), m, ops), emu)
     for slots, m, ops in steps:
         for sl, table in ops:
             if sl:
@@ -412,8 +420,10 @@ def _apply_launch(vec, d, info):
     info["launch_forms"][key] += 1
     if emu is not None:
         err = float(np.abs(emu - vec).max())
-        assert err <= 1e-12, "tile image of a scheduled run differs from the oracle by %g" % err
-        info["tile_images_emulated"] = info.get("tile_images_emulated", 0) + 1
+        assert err <= 1e-12, "%s image of a scheduled launch differs from the oracle by %g" % (key, err)
+        if d["form"] == LAUNCH_TILE:
+            info["tile_images_emulated"] = info.get("tile_images_emulated", 0) + 1
+        info["images_emulated"] = info.get("images_emulated", 0) + 1
 _COLLECTIVE = {KIND["swap"], KIND["pauli_expect"], KIND["pauli_apply"], KIND["pauli_commit"], KIND["permute"], KIND["load"]}
 
 
