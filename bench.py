@@ -697,7 +697,7 @@ def main():
             "swap_nvlink_gbs_per_gpu": swap_gbs,
             "swap_wait_for_peers_ms_per_step": swap_wait_ms / args.steps,
             "swap_transport": {"peer_mapped_in_place": int(ds["swaps_p2p"]), "staged_nccl": int(ds["swaps_staged"]),
-                               "packed_peer_read": int(ds.get("swaps_packed", 0)), "nvlink_peak_gbs_per_dir": 900.0,
+                               "packed_push": int(ds.get("swaps_packed", 0)), "nvlink_peak_gbs_per_dir": 900.0,
                                "frac_of_nvlink": (swap_gbs / 900.0) if swap_gbs else None},
             "kernel_breakdown": breakdown,
             "host_enqueue_seconds_per_step": t_host / args.steps,

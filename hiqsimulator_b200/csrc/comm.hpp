@@ -41,9 +41,9 @@ public:
      // peer-mapping handshake tags its messages with (all ranks create their engines in the same order)
      uint64_t next_epoch() { return ++epoch_; }
 
-     // Staging of the packed exchange (engine.cpp, Engine::exchange_packed): one buffer per process, opened by the peers
-     // through CUDA IPC.  Process-wide like the communicator: an engine per circuit must not pay cudaMalloc + handle
-     // exchange + cudaIpcOpenMemHandle again.
+     // Staging of the packed exchange (engine.cpp, Engine::exchange_packed): one buffer per process, a virtual-memory
+     // allocation whose chunks the peers map through file descriptors (like the slabs).  Process-wide like the
+     // communicator: an engine per circuit must not pay the allocation and the descriptor handshake again.
      // A peer process's view of one of my buffers (or mine of its): chunks received and mapped so far, chunks sent so far.
      struct PeerView {
           PeerSlab slab;

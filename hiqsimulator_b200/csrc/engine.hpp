@@ -195,9 +195,9 @@ private:
 
      std::vector<PeerView> peer_views_;
      uint64_t epoch_ = 0;
-     int swap_mode_ = 0;        // 0 auto, 1 staged NCCL only, 2 peer-mapped only, 3 packed peer-read only
-     // packed peer-read exchange (low swapped slots): pack into a staging buffer that the group peers have opened
-     // through CUDA IPC, barrier, unpack straight from the PEER's staging buffer (contiguous NVLink loads)
+     int swap_mode_ = 0;        // 0 auto, 1 staged NCCL only, 2 peer-mapped only, 3 packed only
+     // packed exchange (low swapped slots): gather piece i straight into the PEERS' staging buffers (posted NVLink
+     // writes of whole lines), stream-ordered barrier, scatter my own staging buffer into my slab
      bool packed_enabled_ = true;       // HIQ_SWAP_PACKED=0: low swapped slots take the in-place kernel too (A/B measurements)
      int packed_below_slot_ = 3;        // auto mode: used when the lowest swapped slot is below this
      uint64_t packed_piece_cap_ = 0;    // HIQ_SWAP_PACKED_PIECE: largest piece in amplitudes (tests drive the multi-piece pipeline with it)
