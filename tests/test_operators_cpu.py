@@ -261,6 +261,41 @@ def test_oracle_emulate_math_against_reference_engine_adder(R):
     assert np.abs(got - want).max() <= 1e-12
 
 
+@pytest.mark.parametrize("R,a", [(1, 2), (2, 4), (2, 8)])
+def test_oracle_multiply_mod_15_against_reference_engine_rotation(R, a):
+    """x -> a x mod 15 for a = 2, 4, 8 on a 4-bit register is a cyclic rotation of the bits (x = 15 stays: values >= N are
+    left alone; x = 0 stays) — controlled SWAP gates on the compiled reference engine.  Pins the modular-multiplication
+    emulation of Shor's algorithm (examples/shor_mpi.py:74) incl. its control and the x >= N rule on the reference's kernels."""
+    from oracle import ref
+    if not ref.have_ref():
+        pytest.skip("oracle/_ref is not built")
+    g = R.bit_length() - 1
+    nq = 7 + g
+    rng = np.random.default_rng(70 + R + a)
+    prefix = scripts.random_script(nq, R, 151 + R + a, ngates=40, queries=False)[:-2]
+    probe = ref.run_script(prefix + [("get_local_qubits_ids",)], R, 1)
+    local_ids = [int(q) for q in probe[0][-1]]
+    reg = [int(x) for x in rng.permutation(local_ids)[:4]]
+    ctrl = [int(q) for q in range(nq) if q not in reg][:1]
+    SWAP = np.eye(4)[[0, 2, 1, 3]].astype(complex)
+    script = list(prefix)
+    for _ in range({2: 1, 4: 2, 8: 3}[a]):
+        for lo, hi in ((2, 3), (1, 2), (0, 1)):  # the content of bit i moves to bit i + 1 (mod 4)
+            script.append(("apply_controlled_gate", SWAP.tolist(), [reg[lo], reg[hi]], ctrl))
+            script.append(("run",))
+    script.append(("cheat_local",))
+    res = scripts.merge_rank_outputs(ref.run_script(script, R, 1))
+    id2pos, want = res[-1]
+
+    o = statevec.SimulatorMPI(*prefix[0][1:], R)
+    for op in prefix[1:]:
+        scripts._dispatch(o, op)
+    o.emulate_math_multiply_by_constant_modN(a, 15, reg, ctrl)
+    got_map, got = o.cheat()
+    assert dict(got_map) == dict(id2pos)
+    assert np.abs(got - want).max() <= 1e-12
+
+
 @pytest.mark.parametrize("R", [1, 2])
 def test_oracle_time_evolution_against_reference_engine_for_commuting_terms(R):
     """For a Hamiltonian of mutually commuting terms exp(-i t H) factorises exactly: every Pauli string P_k on <= 3
