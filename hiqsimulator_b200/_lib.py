@@ -74,6 +74,8 @@ _SIGNATURES = {
     "hiqk_dense_is_monomial": (C.c_int, [C.c_int, _dp]),
     "hiqk_tile_program_fits": (C.c_int, [C.c_int, C.c_int, C.POINTER(TileStep)]),
     "hiqk_apply_tile_program": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(TileStep), _vp]),
+    "hiqk_dense_image_bytes": (C.c_size_t, []),
+    "hiqk_dense_image": (C.c_int, [C.c_int, C.c_int, _ip, _dp, _u64, C.c_int, _vp, C.c_size_t]),
     "hiqk_diag_batch_image_bytes": (C.c_size_t, []),
     "hiqk_diag_batch_image": (C.c_int, [C.c_int, C.POINTER(DiagOp), C.c_int, _vp, C.c_size_t]),
     "hiqk_dense_prediag_image_bytes": (C.c_size_t, []),

@@ -534,10 +534,8 @@ static int with_ks(int ks, F&& f)
 }
 
 template <int K>
-static int launch_direct(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
-                         cudaStream_t stream, int ks = K)
+static void fill_direct(DirectParams<K>& p, double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask)
 {
-     DirectParams<K> p;
      p.psi = psi;
      const int nc = __builtin_popcountll(ctrl_mask);
      p.n_free = 1ull << (L - K - nc);
@@ -545,6 +543,14 @@ static int launch_direct(double2* psi, int L, const int* slots, const double* ma
      p.ins = make_insert_bits(slots, K, ctrl_mask);
      fill_common<K>(p.off, p.m, slots, matrix);
      fill_msum<K>(p);
+}
+
+template <int K>
+static int launch_direct(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
+                         cudaStream_t stream, int ks = K)
+{
+     DirectParams<K> p;
+     fill_direct<K>(p, psi, L, slots, matrix, ctrl_mask);
      constexpr int THREADS = (K >= 4) ? 128 : 256;
      constexpr int MINB = (K >= 5) ? 2 : (K == 4 ? 4 : 4);
      const uint64_t need = (p.n_free + THREADS - 1) / THREADS;
@@ -698,10 +704,8 @@ static int launch_direct_pre(double2* psi, int L, const int* slots, const double
 }
 
 template <int K>
-static int launch_tiled(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
-                        cudaStream_t stream)
+static int fill_tiled(TiledParams<K>& p, double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask)
 {
-     TiledParams<K> p;
      std::memset(&p, 0, sizeof(p));
      const int tb = tile_bits_for(K, L);
      if (tb < K + 3) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense: slab too small for the tiled kernel");
@@ -756,6 +760,17 @@ static int launch_tiled(double2* psi, int L, const int* slots, const double* mat
           }
      }
      std::memcpy(p.m, matrix, sizeof(double2) << (2 * K));
+     return HIQ_OK;
+}
+
+template <int K>
+static int launch_tiled(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
+                        cudaStream_t stream)
+{
+     TiledParams<K> p;
+     const int rc = fill_tiled<K>(p, psi, L, slots, matrix, ctrl_mask);
+     if (rc != HIQ_OK) return rc;
+     const int tb = p.tile_bits;
      constexpr int THREADS = 128;
      constexpr int MINB = (K >= 5) ? 2 : 4;
      const size_t smem = sizeof(double2) << tb;
@@ -771,19 +786,28 @@ static int launch_tiled(double2* psi, int L, const int* slots, const double* mat
      return check_launch("dense_tiled_kernel");
 }
 
+// the tensor-core kernel works on groups of 8 consecutive free indices
+static bool dmma_fits(int L, int k, uint64_t ctrl_mask) { return (1ull << (L - k - __builtin_popcountll(ctrl_mask))) >= 8; }
+
 template <int K>
-static int launch_dmma(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
-                       cudaStream_t stream)
+static void fill_dmma(DmmaParams<K>& p, double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask)
 {
-     DmmaParams<K> p;
      const int nc = __builtin_popcountll(ctrl_mask);
      const uint64_t n_free = 1ull << (L - K - nc);
-     if (n_free < 8) return launch_direct<K>(psi, L, slots, matrix, ctrl_mask, stream);
      p.psi = psi;
      p.n_groups = n_free >> 3;
      p.ctrl_mask = ctrl_mask;
      p.ins = make_insert_bits(slots, K, ctrl_mask);
      fill_common<K>(p.off, p.m, slots, matrix);
+}
+
+template <int K>
+static int launch_dmma(double2* psi, int L, const int* slots, const double* matrix, uint64_t ctrl_mask,
+                       cudaStream_t stream)
+{
+     DmmaParams<K> p;
+     if (!dmma_fits(L, K, ctrl_mask)) return launch_direct<K>(psi, L, slots, matrix, ctrl_mask, stream);
+     fill_dmma<K>(p, psi, L, slots, matrix, ctrl_mask);
      constexpr int THREADS = 128;
      constexpr int G = (K >= 5) ? 1 : 2;
      constexpr int MINB = (K >= 5) ? 3 : 4;
@@ -862,7 +886,142 @@ static int dispatch_k(double2* psi, int L, const int* slots, const double* matri
      }
 }
 
+// Host-only parameter image of hiqk_apply_dense (see include/hiq_b200.h): the same variant resolution and block-shape
+// permutation as dispatch_k, the same fill functions as the launchers.  Header words: magic, variant, K, mixing bits used
+// (DIRECT), three-multiplication flag, sizeof(parameters), sizeof(InsertBits), then the field offsets of the variant:
+//   DIRECT: n_free, ctrl_mask, ins, off, m, msum        DMMA: n_groups, ctrl_mask, ins, off, m
+//   TILED:  n_tiles, hi_ctrl_mask, lo_ctrl_mask, lo, tile_bits, nswz, swz_src, swz_dst, outer, inner, hoff, loff, m
+constexpr int kDenseImageHeaderWords = 32;
+
+template <int K>
+static int dense_image_k(int L, const int* slots, const double* matrix, uint64_t ctrl_mask, int variant, void* image)
+{
+     uint32_t* head = static_cast<uint32_t*>(image);
+     void* body = head + kDenseImageHeaderWords;
+     if (variant == HIQK_DENSE_AUTO) variant = pick_variant(L, K, slots);
+     if (variant == HIQK_DENSE_DMMA && (K < 2 || !dmma_fits(L, K, ctrl_mask))) variant = HIQK_DENSE_DIRECT_FULL;  // launch_dmma's fallback
+     int w = 0;
+     head[w++] = 0x4e445148u;  // 'HQDN'
+     int ks = K, m3 = 0;
+     switch (variant) {
+          case HIQK_DENSE_DIRECT:
+          case HIQK_DENSE_DIRECT_FULL: {
+               using P = DirectParams<K>;
+               P* p = static_cast<P*>(body);
+               int pslots[K];
+               double pm[2 << (2 * K)];
+               const int* use_slots = slots;
+               const double* use_m = matrix;
+               if constexpr (K >= 2 && K <= 4) {
+                    if (variant == HIQK_DENSE_DIRECT && dense_blocks_enabled()) {
+                         const DenseShape sh = dense_shape(K, matrix);
+                         if (sh.ks < K) {
+                              permute_gate(K, sh.order, slots, matrix, pslots, pm);
+                              use_slots = pslots;
+                              use_m = pm;
+                              ks = sh.ks;
+                         }
+                    }
+               }
+               fill_direct<K>(*p, nullptr, L, use_slots, use_m, ctrl_mask);
+               if (K == 4 && ks == K && dense_3m_enabled()) m3 = 1;
+               head[w++] = HIQK_DENSE_DIRECT;
+               head[w++] = K;
+               head[w++] = static_cast<uint32_t>(ks);
+               head[w++] = static_cast<uint32_t>(m3);
+               head[w++] = sizeof(P);
+               head[w++] = sizeof(InsertBits);
+               head[w++] = static_cast<uint32_t>(offsetof(P, n_free));
+               head[w++] = static_cast<uint32_t>(offsetof(P, ctrl_mask));
+               head[w++] = static_cast<uint32_t>(offsetof(P, ins));
+               head[w++] = static_cast<uint32_t>(offsetof(P, off));
+               head[w++] = static_cast<uint32_t>(offsetof(P, m));
+               head[w++] = static_cast<uint32_t>(offsetof(P, msum));
+               return HIQ_OK;
+          }
+          case HIQK_DENSE_TILED: {
+               using P = TiledParams<K>;
+               P* p = static_cast<P*>(body);
+               const int rc = fill_tiled<K>(*p, nullptr, L, slots, matrix, ctrl_mask);
+               if (rc != HIQ_OK) return rc;
+               head[w++] = HIQK_DENSE_TILED;
+               head[w++] = K;
+               head[w++] = K;
+               head[w++] = 0;
+               head[w++] = sizeof(P);
+               head[w++] = sizeof(InsertBits);
+               head[w++] = static_cast<uint32_t>(offsetof(P, n_tiles));
+               head[w++] = static_cast<uint32_t>(offsetof(P, hi_ctrl_mask));
+               head[w++] = static_cast<uint32_t>(offsetof(P, lo_ctrl_mask));
+               head[w++] = static_cast<uint32_t>(offsetof(P, lo));
+               head[w++] = static_cast<uint32_t>(offsetof(P, tile_bits));
+               head[w++] = static_cast<uint32_t>(offsetof(P, nswz));
+               head[w++] = static_cast<uint32_t>(offsetof(P, swz_src));
+               head[w++] = static_cast<uint32_t>(offsetof(P, swz_dst));
+               head[w++] = static_cast<uint32_t>(offsetof(P, outer));
+               head[w++] = static_cast<uint32_t>(offsetof(P, inner));
+               head[w++] = static_cast<uint32_t>(offsetof(P, hoff));
+               head[w++] = static_cast<uint32_t>(offsetof(P, loff));
+               head[w++] = static_cast<uint32_t>(offsetof(P, m));
+               return HIQ_OK;
+          }
+          case HIQK_DENSE_DMMA: {
+               if constexpr (K >= 2) {
+                    using P = DmmaParams<K>;
+                    P* p = static_cast<P*>(body);
+                    fill_dmma<K>(*p, nullptr, L, slots, matrix, ctrl_mask);
+                    head[w++] = HIQK_DENSE_DMMA;
+                    head[w++] = K;
+                    head[w++] = K;
+                    head[w++] = 0;
+                    head[w++] = sizeof(P);
+                    head[w++] = sizeof(InsertBits);
+                    head[w++] = static_cast<uint32_t>(offsetof(P, n_groups));
+                    head[w++] = static_cast<uint32_t>(offsetof(P, ctrl_mask));
+                    head[w++] = static_cast<uint32_t>(offsetof(P, ins));
+                    head[w++] = static_cast<uint32_t>(offsetof(P, off));
+                    head[w++] = static_cast<uint32_t>(offsetof(P, m));
+                    return HIQ_OK;
+               }
+               return set_error(HIQ_ERR_ARG, "hiqk_dense_image: the tensor-core kernel needs k >= 2");
+          }
+          default: return set_error(HIQ_ERR_ARG, "hiqk_dense_image: unknown variant");
+     }
+}
+
+constexpr size_t kDenseImageBodyBytes =
+     sizeof(DirectParams<5>) > sizeof(TiledParams<5>) ? (sizeof(DirectParams<5>) > sizeof(DmmaParams<5>) ? sizeof(DirectParams<5>) : sizeof(DmmaParams<5>))
+                                                      : (sizeof(TiledParams<5>) > sizeof(DmmaParams<5>) ? sizeof(TiledParams<5>) : sizeof(DmmaParams<5>));
+
 }  // namespace hiq
+
+extern "C" size_t hiqk_dense_image_bytes(void) { return hiq::kDenseImageHeaderWords * sizeof(uint32_t) + hiq::kDenseImageBodyBytes; }
+
+extern "C" int hiqk_dense_image(int L, int k, const int* slots, const double* matrix, uint64_t ctrl_mask, int variant, void* image,
+                                size_t image_bytes)
+{
+     using namespace hiq;
+     if (!slots || !matrix || !image) return set_error(HIQ_ERR_ARG, "hiqk_dense_image: null argument");
+     if (image_bytes < hiqk_dense_image_bytes()) return set_error(HIQ_ERR_ARG, "hiqk_dense_image: buffer too small");
+     if (k < 1 || k > kMaxTargets) return set_error(HIQ_ERR_ARG, "hiqk_dense_image: k must be 1..5");
+     if (L < k || L > 40) return set_error(HIQ_ERR_ARG, "hiqk_dense_image: bad slab size");
+     uint64_t tmask = 0;
+     for (int l = 0; l < k; ++l) {
+          if (slots[l] < 0 || slots[l] >= L || ((tmask >> slots[l]) & 1))
+               return set_error(HIQ_ERR_ARG, "hiqk_dense_image: target slots must be distinct and < L");
+          tmask |= 1ull << slots[l];
+     }
+     if ((ctrl_mask & tmask) || (L < 64 && (ctrl_mask >> L)))
+          return set_error(HIQ_ERR_ARG, "hiqk_dense_image: control mask overlaps targets or exceeds the slab");
+     std::memset(image, 0, hiqk_dense_image_bytes());
+     switch (k) {
+          case 1: return dense_image_k<1>(L, slots, matrix, ctrl_mask, variant, image);
+          case 2: return dense_image_k<2>(L, slots, matrix, ctrl_mask, variant, image);
+          case 3: return dense_image_k<3>(L, slots, matrix, ctrl_mask, variant, image);
+          case 4: return dense_image_k<4>(L, slots, matrix, ctrl_mask, variant, image);
+          default: return dense_image_k<5>(L, slots, matrix, ctrl_mask, variant, image);
+     }
+}
 
 extern "C" int hiqk_dense_pick_variant(int L, int k, const int* slots)
 {

@@ -120,6 +120,16 @@ def apply_tile_program(state, steps):
     check(lib().hiqk_apply_tile_program(p, L, len(steps), arr, _stream()))
 
 
+def dense_image(L, slots, matrix, ctrl_mask=0, variant=AUTO) -> bytes:
+    """the variant apply_dense resolves to and the kernel parameters it would launch with — host only;
+    tests/dense_emulator.py interprets them"""
+    keep, mp = _cplx(matrix)
+    n = lib().hiqk_dense_image_bytes()
+    buf = C.create_string_buffer(n)
+    check(lib().hiqk_dense_image(L, len(slots), _ints(slots), mp, ctrl_mask, variant, buf, n))
+    return buf.raw
+
+
 def diag_batch_image(L, ops) -> bytes:
     """the kernel parameters apply_diag_batch would launch with — host only; tests/diag_emulator.py interprets them"""
     arr = _diag_ops(ops)

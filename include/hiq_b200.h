@@ -107,13 +107,16 @@ int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slots, const d
  * hiqk_apply_diag_batch first). */
 int hiqk_dense_prediag_supported(int L, int k, const int* slots);
 
-/* The kernel parameters hiqk_apply_diag_batch / hiqk_apply_dense_prediag would launch with, written to host memory —
+/* The kernel parameters hiqk_apply_dense / hiqk_apply_diag_batch / hiqk_apply_dense_prediag would launch with, written to host memory —
  * no device call, no computation: how the index is split (thread | per-thread tuples | chunk), the class of every
  * diagonal factor (one per CTA and chunk / per thread and chunk / per element / on the gate's targets), the partial
  * selector tables and the class-E pattern tables, exactly as the launchers encode them.  Layout: a header of uint32 words
  * (magic, constants and the byte offset of every field; see hiqk_diag_batch_image in csrc/stream_kernels.cu and
  * direct_pre_image in csrc/apply_dense.cu) followed by the parameter structure with a null slab pointer.
  * tests/diag_emulator.py executes the images the way the kernels do.  HIQ_OK or HIQ_ERR_*. */
+size_t hiqk_dense_image_bytes(void);
+int hiqk_dense_image(int L, int k, const int* slots, const double* matrix, uint64_t ctrl_mask, int variant, void* image,
+                     size_t image_bytes); /* hiqk_apply_dense: resolved variant + its parameters (tests/dense_emulator.py) */
 size_t hiqk_diag_batch_image_bytes(void);
 int hiqk_diag_batch_image(int L, const hiqk_diag_op* ops, int n_ops, void* image, size_t image_bytes);
 size_t hiqk_dense_prediag_image_bytes(void);
