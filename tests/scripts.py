@@ -451,7 +451,19 @@ def replay_traces(traces, R, info=None):
                 elif d["kind"] == KIND["fill"]:
                     vec[r][:] = d["payload"][0]
                 elif d["kind"] == KIND["dense"]:
+                    emu = None
+                    if info.get("tile_emulator"):  # a single-gate launch: through hiqk_apply_dense's image and its kernel emulator
+                        import dense_emulator
+                        from hiqsimulator_b200 import kernels as K
+                        k = len(d["slots"])
+                        emu = vec[r].copy()
+                        dense_emulator.run_dense_image(K.dense_image(int(np.log2(emu.shape[0])), list(d["slots"]),
+                                                                     np.asarray(d["payload"]).reshape(1 << k, 1 << k), int(d["ctrl_mask"])), emu)
                     statevec.apply_dense(vec[r], list(d["slots"]), np.asarray(d["payload"]), int(d["ctrl_mask"]))
+                    if emu is not None:
+                        err = float(np.abs(emu - vec[r]).max())
+                        assert err <= 1e-12, "dense image of a scheduled launch differs from the oracle by %g" % err
+                        info["images_emulated"] = info.get("images_emulated", 0) + 1
                 elif d["kind"] == KIND["diag"]:
                     statevec.apply_diag(vec[r], list(d["slots"]), np.asarray(d["payload"]), int(d["ctrl_mask"]))
                 elif d["kind"] == KIND["scale"]:
