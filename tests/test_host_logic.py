@@ -215,6 +215,69 @@ def test_packed_exchange_scheme(L, gpos, slots, piece_bits):
     assert np.array_equal(got, full[src])
 
 
+@pytest.mark.parametrize("L,gpos,slots", [(8, [0], [0]), (8, [2], [5]), (9, [1, 0], [0, 1]), (9, [0, 2], [6, 1]), (9, [2, 1], [8, 3]),
+                                          (10, [0, 1, 2], [0, 1, 2]), (10, [2, 0, 1], [7, 0, 3]), (10, [1, 2, 0], [9, 8, 4])])
+def test_inplace_exchange_scheme(L, gpos, slots):
+    """Index logic of Engine::exchange_p2p (csrc/engine.cpp) + swap_p2p_kernel (csrc/swap_kernels.cu), restated with numpy
+    on 8 virtual ranks: rank r meets every rank that differs from it in a non-empty subset of the swapped global bits;
+    of a pair, the lower rank handles the lower half of the free indices, the higher rank the rest; for every free index
+    it handles, a rank trades its amplitude whose swapped slots spell the PEER's bits for the peer's amplitude whose
+    swapped slots spell ITS bits.  Every rank runs its own kernel; together they must perform the transposition of
+    global-index bit (L + gpos_j) with bit slots[j] — each pair element moved exactly once."""
+    g = 3
+    R = 1 << g
+    q = len(gpos)
+    rng = np.random.default_rng(3 * L + sum(slots))
+    full = rng.normal(size=R << L) + 1j * rng.normal(size=R << L)
+    vec = [full[r << L:(r + 1) << L].copy() for r in range(R)]
+    order = sorted(range(q), key=lambda j: slots[j])
+    srt = sorted(slots)
+
+    def pattern_of(r):  # bit j <-> j-th lowest swapped slot
+        return sum(((r >> gpos[order[j]]) & 1) << j for j in range(q))
+
+    def spread(pat):
+        return sum(((pat >> j) & 1) << srt[j] for j in range(q))
+
+    def deposit(f):
+        f = np.asarray(f, dtype=np.int64).copy()
+        for pos in srt:
+            f = ((f >> pos) << (pos + 1)) | (f & ((1 << pos) - 1))
+        return f
+
+    n = 1 << (L - q)
+    half = (n + 1) // 2
+    moved = [np.zeros(1 << L, dtype=np.int32) for _ in range(R)]
+    for r in range(R):  # one kernel per rank; the pairs it touches are disjoint from every other rank's
+        for x in range(1, 1 << q):
+            pr = r
+            for i in range(q):
+                if (x >> i) & 1:
+                    pr ^= 1 << gpos[i]
+            begin, count = (0, half) if r < pr else (half, n - half)
+            base = deposit(begin + np.arange(count))
+            mine = base | spread(pattern_of(pr))
+            theirs = base | spread(pattern_of(r))
+            a, b = vec[r][mine].copy(), vec[pr][theirs].copy()
+            vec[r][mine], vec[pr][theirs] = b, a
+            np.add.at(moved[r], mine, 1)
+            np.add.at(moved[pr], theirs, 1)
+    got = np.concatenate(vec)
+    gidx = np.arange(R << L, dtype=np.int64)
+    src = gidx.copy()
+    for j in range(q):
+        hi, lo = L + gpos[j], slots[j]
+        bh, bl = (src >> hi) & 1, (src >> lo) & 1
+        src = src & ~((1 << hi) | (1 << lo)) | (bl << hi) | (bh << lo)
+    assert np.array_equal(got, full[src])
+    for r in range(R):  # an amplitude moves once unless its swapped slots spell its own rank's bits (it stays)
+        idx = np.arange(1 << L)
+        stays = np.ones(1 << L, dtype=bool)
+        for j in range(q):
+            stays &= ((idx >> slots[j]) & 1) == ((r >> gpos[j]) & 1)
+        assert np.array_equal(moved[r] == 0, stays) and moved[r].max() == 1
+
+
 @pytest.mark.parametrize("kind,n,R", [("random", 13, 2), ("random", 14, 4), ("qft", 13, 8), ("random", 12, 1)])
 def test_scheduled_script_dry_run_equals_compiled_reference(kind, n, R):
     """the script tests/test_fullsize_multigpu.py diffs on the GPUs (bench pipeline -> scheduled stream), here on dry-run
