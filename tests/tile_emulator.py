@@ -69,15 +69,19 @@ def _insert_zero_bits(f, positions):
     return f
 
 
-def run_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> None:
-    """apply the program to `psi` (complex128, 2^L amplitudes) in place, the way tile_program_kernel does"""
+def run_image(raw: bytes, psi: np.ndarray | None, stats: dict | None = None, tiles=None, source=None):
+    """apply the program to `psi` (complex128, 2^L amplitudes) in place, the way tile_program_kernel does.
+    Slabs too large to hold (the bench's 2^33): pass psi=None, tiles = the tile numbers to process and source(indices) ->
+    amplitudes; returns (indices [tiles, 2^T], values [tiles, 2^T]) of what the kernel would store."""
     im = Image(raw)
     T = im.T
     THREADS = 1 << (T - 4)
     n_tiles = int(im.p("n_tiles", np.uint64))
     n_steps = int(im.p("n_steps", np.int32))
     lo = int(im.p("lo", np.int32))
-    assert n_tiles << T == psi.shape[0]
+    assert psi is None or n_tiles << T == psi.shape[0]
+    if source is None:
+        source = lambda g: psi[g]  # noqa: E731
     outer_n = int(im._arr(im.p_off["outer"], np.int32, 1)[0])
     outer_pos = im._arr(im.p_off["outer"] + 4, np.uint8, 64)[:outer_n]
     swz = [np.uint32(x) for x in im.p("swz_mask", np.uint32, 3)]
@@ -98,12 +102,14 @@ def run_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> None:
     cover = np.sort(np.concatenate([pt ^ pi[i] for i in range(16)]))
     assert np.array_equal(cover, np.arange(1 << T)), "load/store slices do not tile the buffer"
 
-    t_idx = np.arange(n_tiles, dtype=np.uint64)
+    t_idx = np.arange(n_tiles, dtype=np.uint64) if tiles is None else np.asarray(tiles, dtype=np.uint64)
+    assert int(t_idx.max()) < n_tiles
+    n_tiles = t_idx.shape[0]  # tiles processed from here on
     tbase = _insert_zero_bits(t_idx, outer_pos) << np.uint64(lo)          # [tiles]
     tile = np.zeros((n_tiles, 1 << T), dtype=np.complex128)
     for i in range(16):
         g = tbase[:, None] + goff_t[None, :] + ioff[i]
-        tile[:, pt ^ pi[i]] = psi[g]
+        tile[:, pt ^ pi[i]] = source(g)
 
     conflicts = 0
     for s in range(n_steps):
@@ -216,10 +222,16 @@ def run_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> None:
         for c in range(16):
             tile[:, cells[c]] = out[c]
 
+    out_idx = np.zeros((n_tiles, 1 << T), dtype=np.uint64)
+    out_val = np.zeros((n_tiles, 1 << T), dtype=np.complex128)
     for i in range(16):
         g = tbase[:, None] + goff_t[None, :] + ioff[i]
-        psi[g] = tile[:, pt ^ pi[i]]
+        if psi is not None:
+            psi[g] = tile[:, pt ^ pi[i]]
+        out_idx[:, i * THREADS:(i + 1) * THREADS] = g
+        out_val[:, i * THREADS:(i + 1) * THREADS] = tile[:, pt ^ pi[i]]
     if stats is not None:
         stats["tile_bits"] = T
         stats["gather_phases_with_bank_conflicts"] = conflicts
         stats["n_tiles"] = n_tiles
+    return out_idx, out_val
