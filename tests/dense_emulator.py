@@ -37,7 +37,34 @@ def _i32(raw, at):
     return struct.unpack_from("<i", raw, at)[0]
 
 
-def run_dense_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> None:
+class _Virtual:
+    """a slab too large to hold: reads come from source(indices), writes are collected"""
+
+    def __init__(self, source):
+        self.source = source
+        self.idx, self.val = [], []
+
+    def __getitem__(self, i):
+        return self.source(np.asarray(i))
+
+    def __setitem__(self, i, v):
+        self.idx.append(np.asarray(i).ravel().copy())
+        self.val.append(np.asarray(v).ravel().copy())
+
+
+def run_dense_image(raw: bytes, psi, stats: dict | None = None, sample=None, source=None):
+    """psi: complex128 array updated in place — or None with `sample` (work items to process: free indices for DIRECT,
+    groups of 8 for DMMA, tiles for TILED) and `source(indices)`: returns (indices, values) of what would be stored"""
+    virtual = psi is None
+    if virtual:
+        psi = _Virtual(source)
+    out = _run(raw, psi, stats, sample, virtual)
+    if virtual:
+        return np.concatenate(psi.idx), np.concatenate(psi.val)
+    return out
+
+
+def _run(raw, psi, stats, sample, virtual):
     head = struct.unpack_from("<32I", raw, 0)
     assert head[0] == 0x4e445148, "not a dense image"
     variant, K, ks, m3 = head[1:5]
@@ -45,7 +72,7 @@ def run_dense_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> N
     D = 1 << K
     if stats is not None:
         stats.update({"variant": variant, "K": K, "ks": ks, "m3": m3})
-    touched = np.zeros(psi.shape[0], dtype=np.int32)
+    touched = None if virtual else np.zeros(psi.shape[0], dtype=np.int32)
     if variant == DIRECT:
         off = dict(zip(["n_free", "ctrl_mask", "ins", "off", "m", "msum"], head[7:13]))
         n_free = _u64(raw, base + off["n_free"])
@@ -56,11 +83,13 @@ def run_dense_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> N
         if m3:
             msum = np.frombuffer(raw, np.float64, D * D, base + off["msum"]).reshape(D, D)
             assert K == 4 and ks == 4 and np.array_equal(msum, m.real + m.imag)
-        f = np.arange(n_free, dtype=np.uint64)
+        f = np.arange(n_free, dtype=np.uint64) if sample is None else np.asarray(sample, dtype=np.uint64)
+        assert int(f.max()) < n_free
         b = (_insert_zero_bits(f, ins) | ctrl_mask).astype(np.int64)
         x = [psi[b + int(eoff[c])] for c in range(D)]
-        for c in range(D):
-            np.add.at(touched, b + int(eoff[c]), 1)
+        if not virtual:
+            for c in range(D):
+                np.add.at(touched, b + int(eoff[c]), 1)
         DS = 1 << ks
         for r in range(D):
             lo = r & ~(DS - 1)
@@ -68,10 +97,11 @@ def run_dense_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> N
             for c in range(lo, lo + DS):
                 acc = acc + m[r, c] * x[c]
             psi[b + int(eoff[r])] = acc
-        assert touched.max() == 1, "two tuples overlap"
-        # untouched amplitudes are exactly those whose control bits are not all set
-        idx = np.arange(psi.shape[0], dtype=np.uint64)
-        assert np.array_equal(touched == 1, (idx & ctrl_mask) == ctrl_mask)
+        if not virtual:
+            assert touched.max() == 1, "two tuples overlap"
+            # untouched amplitudes are exactly those whose control bits are not all set
+            idx = np.arange(psi.shape[0], dtype=np.uint64)
+            assert np.array_equal(touched == 1, (idx & ctrl_mask) == ctrl_mask)
         return
     if variant == TILED:
         names = ["n_tiles", "hi_ctrl_mask", "lo_ctrl_mask", "lo", "tile_bits", "nswz", "swz_src", "swz_dst", "outer", "inner", "hoff", "loff", "m"]
@@ -102,11 +132,14 @@ def run_dense_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> N
         pj = swz(j).astype(np.int64)
         assert np.array_equal(np.sort(pj), np.arange(tile_amps)), "the swizzle is not a permutation of the tile"
         lo_mask = np.uint32((1 << lo) - 1)
-        t = np.arange(n_tiles, dtype=np.uint64)
+        t = np.arange(n_tiles, dtype=np.uint64) if sample is None else np.asarray(sample, dtype=np.uint64)
+        assert int(t.max()) < n_tiles
+        n_tiles = t.shape[0]
         tbase = (_insert_zero_bits(t, outer) << np.uint64(lo)) | hi_ctrl
         g = (tbase[:, None] + (j & lo_mask).astype(np.uint64)[None, :] + hoff[(j >> np.uint32(lo)).astype(np.int64)][None, :]).astype(np.int64)
-        np.add.at(touched, g.ravel(), 1)
-        assert touched.max() == 1, "two tiles overlap"
+        if not virtual:
+            np.add.at(touched, g.ravel(), 1)
+            assert touched.max() == 1, "two tiles overlap"
         tile = np.zeros((n_tiles, tile_amps), dtype=np.complex128)
         tile[:, pj] = psi[g]
         u = np.arange(tile_amps >> K, dtype=np.uint64)
@@ -141,16 +174,18 @@ def run_dense_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> N
                 r, q = 8 * nt + (lane >> 2), 4 * kt + (lane & 3)
                 e = m[r >> 1, q >> 1]
                 bs[kt, nt, lane] = e.real if (r & 1) == (q & 1) else (e.imag if (r & 1) else -e.imag)
-    grp = np.arange(n_groups, dtype=np.uint64)
+    grp = np.arange(n_groups, dtype=np.uint64) if sample is None else np.asarray(sample, dtype=np.uint64)
+    assert int(grp.max()) < n_groups
+    n_groups = grp.shape[0]
     lane = np.arange(32)
     t, j = lane >> 2, lane & 3
     tb_idx = (_insert_zero_bits(grp[:, None] * np.uint64(8) + t[None, :].astype(np.uint64), ins) | ctrl_mask).astype(np.int64)  # [groups, lanes]
-    re_im = np.stack([psi.real, psi.imag], axis=1)           # [amps, 2]: the slab as doubles
-    # A fragment: lane (t, j) loads component (j & 1) of element 2 kt + (j >> 1) of tuple t
+    # A fragment: lane (t, j) loads component (j & 1) of element 2 kt + (j >> 1) of tuple t (an 8-byte load)
     a = np.zeros((KT, n_groups, 32))
     for kt in range(KT):
         elem = 2 * kt + (j >> 1)
-        a[kt] = re_im[tb_idx + eoff[elem].astype(np.int64)[None, :], (j & 1)[None, :]]
+        amp = psi[tb_idx + eoff[elem].astype(np.int64)[None, :]]
+        a[kt] = np.where((j & 1)[None, :] == 0, amp.real, amp.imag)
     # mma.m8n8k4 (row.col): D[row][col] += sum_k A[row][k] B[k][col]; A: lane -> (row = lane / 4, k = lane % 4);
     # B: lane -> (k = lane % 4, col = lane / 4); D: lane -> (row = lane / 4, cols 2 (lane % 4), + 1)
     d = np.zeros((NT, n_groups, 8, 8))
@@ -163,8 +198,10 @@ def run_dense_image(raw: bytes, psi: np.ndarray, stats: dict | None = None) -> N
         # lane (t, j) stores (d0, d1) = D[t][2 j], D[t][2 j + 1] as the amplitude at element 4 nt + j of tuple t
         val = d[nt][:, t, 2 * j] + 1j * d[nt][:, t, 2 * j + 1]          # [groups, lanes]
         dst = tb_idx + eoff[4 * nt + j].astype(np.int64)[None, :]
-        np.add.at(touched, dst.ravel(), 1)
+        if not virtual:
+            np.add.at(touched, dst.ravel(), 1)
         psi[dst] = val
-    assert touched.max() == 1, "two lanes store the same amplitude"
-    idx = np.arange(psi.shape[0], dtype=np.uint64)
-    assert np.array_equal(touched == 1, (idx & ctrl_mask) == ctrl_mask)
+    if not virtual:
+        assert touched.max() == 1, "two lanes store the same amplitude"
+        idx = np.arange(psi.shape[0], dtype=np.uint64)
+        assert np.array_equal(touched == 1, (idx & ctrl_mask) == ctrl_mask)

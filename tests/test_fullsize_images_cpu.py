@@ -108,3 +108,56 @@ def test_bench_tile_programs_at_full_size(kind, n, ranks, rank):
             got = val[row][order]
             exp = want[np.argsort(glob)]
             assert np.abs(got - exp).max() <= 1e-12
+
+
+def _expected_amplitudes(idx, slots, m, ctrl_mask):
+    """out[i] = sum_c m[b(i)][c] * in[i with the target bits spelling c] where the control mask is satisfied, in[i] elsewhere"""
+    idx = np.asarray(idx, dtype=np.uint64)
+    k = len(slots)
+    tmask = np.uint64(sum(1 << s for s in slots))
+    b = np.zeros(idx.shape, dtype=np.int64)
+    for l, s in enumerate(slots):
+        b |= ((idx >> np.uint64(s)) & np.uint64(1)).astype(np.int64) << l
+    base = idx & ~tmask
+    out = np.zeros(idx.shape, dtype=np.complex128)
+    for c in range(1 << k):
+        off = np.uint64(sum(((c >> l) & 1) << slots[l] for l in range(k)))
+        out += m[b, c] * _source(base | off)
+    # the tile kernel also stores the amplitudes of its tile that fail a low control bit: unchanged
+    return np.where((idx & np.uint64(ctrl_mask)) == np.uint64(ctrl_mask), out, _source(idx))
+
+
+@pytest.mark.parametrize("kind,n,ranks,rank", [("random", 33, 1, 0), ("random", 35, 8, 3), ("qft", 33, 1, 0)])
+def test_bench_single_gate_launches_at_full_size(kind, n, ranks, rank):
+    """every single-gate dense launch of the bench circuits (the kernels a random circuit spends its time in: DIRECT with the
+    three-multiplication product, the tensor-core kernel for slot-0 targets) through hiqk_dense_image at the real slab
+    size and the kernel emulator on sampled work items, against the defining sum evaluated per stored amplitude"""
+    import dense_emulator
+    from hiqsimulator_b200 import kernels as K
+    L = n - (ranks.bit_length() - 1)
+    trace, st = _launch_trace(kind, n, ranks, rank)
+    gates = [d for d in trace if d["kind"] == scripts.KIND["dense"]]
+    if kind == "random":
+        assert len(gates) >= 80
+    rng = np.random.default_rng(n + rank)
+    variants = set()
+    for d in gates:
+        slots = [int(s) for s in d["slots"]]
+        k = len(slots)
+        m = np.asarray(d["payload"]).reshape(1 << k, 1 << k)
+        cm = int(d["ctrl_mask"])
+        raw = K.dense_image(L, slots, m, cm)
+        stats = {}
+        nc = bin(cm).count("1")
+        items = 1 << (L - k - nc)
+        if raw[4] == dense_emulator.DMMA:
+            items >>= 3
+        elif raw[4] == dense_emulator.TILED:
+            items = None
+        sample = [0, 1] if items is None else [0, items - 1] + [int(x) for x in rng.integers(0, items, size=30)]
+        idx, val = dense_emulator.run_dense_image(raw, None, stats, sample=sample, source=_source)
+        variants.add(stats["variant"])
+        assert np.unique(idx).size == idx.size
+        assert np.abs(val - _expected_amplitudes(idx, slots, m, cm)).max() <= 1e-12
+    if kind == "random":
+        assert {dense_emulator.DIRECT, dense_emulator.DMMA} <= variants
