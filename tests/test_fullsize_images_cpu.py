@@ -82,10 +82,10 @@ def _expected_tile(L, steps, S, t):
     return glob, x
 
 
-@pytest.mark.parametrize("kind,n,ranks,rank", [("qft", 33, 1, 0), ("random", 33, 1, 0), ("random", 34, 2, 1), ("random", 35, 8, 0),
+@pytest.mark.parametrize("kind,n,ranks,rank", [("qft", 33, 1, 0), ("random", 33, 1, 0), ("random", 34, 2, 1), ("random", 35, 4, 2), ("random", 35, 8, 0),
                                                ("random", 35, 8, 5), ("qft", 35, 8, 7)])
 def test_bench_tile_programs_at_full_size(kind, n, ranks, rank):
-    """the workloads of bench.py at N = 1, 2, 8 (and the QFT of its parity object), one rank's launches each"""
+    """the workloads of bench.py at N = 1, 2, 4, 8 (and the QFT of its parity object), one rank's launches each"""
     from hiqsimulator_b200 import kernels as K
     L = n - (ranks.bit_length() - 1)
     trace, st = _launch_trace(kind, n, ranks, rank)
@@ -127,7 +127,7 @@ def _expected_amplitudes(idx, slots, m, ctrl_mask):
     return np.where((idx & np.uint64(ctrl_mask)) == np.uint64(ctrl_mask), out, _source(idx))
 
 
-@pytest.mark.parametrize("kind,n,ranks,rank", [("random", 33, 1, 0), ("random", 35, 8, 3), ("qft", 33, 1, 0)])
+@pytest.mark.parametrize("kind,n,ranks,rank", [("random", 33, 1, 0), ("random", 35, 4, 1), ("random", 35, 8, 3), ("qft", 33, 1, 0)])
 def test_bench_single_gate_launches_at_full_size(kind, n, ranks, rank):
     """every single-gate dense launch of the bench circuits (the kernels a random circuit spends its time in: DIRECT with the
     three-multiplication product, the tensor-core kernel for slot-0 targets) through hiqk_dense_image at the real slab
