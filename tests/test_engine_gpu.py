@@ -268,8 +268,9 @@ def test_ref_kqubit_gate():  # :247-283
     _apply(sim, G.X, [4]); sim.run()
     _apply(sim, m.conj().T, [0, 1, 2, 3], [4]); sim.run()
     assert sim.get_amplitude([False] * 5, [4, 0, 1, 2, 3]) == pytest.approx(1.0)
-    with pytest.raises(RuntimeError):
+    with pytest.raises(RuntimeError):  # this engine refuses at the call, the reference at the flush (:286-305)
         sim.apply_controlled_gate(np.eye(64).tolist(), [0, 1, 2, 3, 4, 5], [])
+        sim.run()
 
 
 def test_ref_probability():  # :308-339
