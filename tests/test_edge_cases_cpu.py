@@ -98,3 +98,84 @@ def test_engine_host_logic_on_edge_cases(name):
             assert list(got) == list(want)
         else:
             assert not (isinstance(got, tuple) and got and got[0] == "error"), (op, got)
+
+
+# ------------------------------------------------------------------ several ranks: global qubits
+X = [[0, 1], [1, 0]]
+T = [[1, 0], [0, complex(np.exp(0.25j * np.pi))]]
+
+
+def _multi_rank_cases(R):
+    g = R.bit_length() - 1
+    nq = 4 + g  # 4 local slots at most, 2 at least: qubits 2 .. 2 + g - 1 are allocated global
+    pre = [("ctor", 5, 4, 2), ("allocate_qureg", list(range(nq)), 0), ("get_local_qubits_ids",), ("get_global_qubits_ids",)]
+    return {
+        "maps_after_alloc": pre + [("get_qubits_ids",)],
+        "x_on_local_ctrl_global": pre + [("apply_controlled_gate", X, [0], [2]), ("run",), ("cheat_local",)],
+        "diag_on_global": pre + [("apply_controlled_gate", H, [0], []), ("run",), ("apply_controlled_gate", T, [2], [0]), ("run",), ("cheat_local",)],
+        "nondiag_on_global_raises": pre + [("apply_controlled_gate", X, [2], []), ("run",)],
+        "swap_then_gate": pre + [("apply_controlled_gate", H, [0], []), ("run",), ("swap_qubits", [2, 0]), ("get_qubits_ids",),
+                                 ("apply_controlled_gate", H, [2], []), ("run",), ("cheat_local",)],
+        "dealloc_global_in_state_1": pre + [("swap_qubits", [2, 0]), ("apply_controlled_gate", X, [2], []), ("run",), ("swap_qubits", [0, 2]),
+                                            ("get_qubits_ids",), ("deallocate_qubit", 2), ("get_qubits_ids",), ("cheat_local",)],
+        "dealloc_global_in_state_0": pre + [("deallocate_qubit", 2), ("get_qubits_ids",), ("cheat_local",)],
+        "dealloc_local_when_few_locals": pre + [("deallocate_qubit", 0), ("get_qubits_ids",), ("deallocate_qubit", 1), ("get_qubits_ids",),
+                                                ("cheat_local",)],
+        "realloc_after_global_freed": pre + [("deallocate_qubit", 2), ("allocate_qubit", 9), ("get_qubits_ids",), ("cheat_local",)],
+        "measure_global": pre + [("apply_controlled_gate", H, [0], []), ("run",), ("swap_qubits", [2, 0]), ("measure_qubits", [0, 1]),
+                                 ("get_probability", [False], [0]), ("cheat_local",)],
+        "collapse_global": pre + [("apply_controlled_gate", H, [0], []), ("run",), ("swap_qubits", [2, 0]), ("collapse_wavefunction", [0], [True]),
+                                  ("cheat_local",)],
+        "probability_mixed": pre + [("apply_controlled_gate", H, [0], []), ("apply_controlled_gate", H, [1], []), ("run",), ("swap_qubits", [2, 0]),
+                                    ("get_probability", [True, False, False], [0, 1, 2]),
+                                    ("get_amplitude", [True] + [False] * (nq - 1), list(range(nq)))],
+        "swap_unknown_pair": pre + [("swap_qubits", [0, 2])],
+        "swap_duplicate": pre + [("swap_qubits", [2, 0, 2, 1])],
+        "entropy": pre + [("apply_controlled_gate", H, [0], []), ("run",), ("swap_qubits", [2, 0]), ("entropy",)],
+    }
+
+
+_MR = [(R, name) for R in (2, 4) for name in sorted(_multi_rank_cases(R))]
+
+
+@pytest.mark.skipif(not ref.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("R,name", _MR)
+def test_oracle_matches_the_compiled_reference_on_global_qubit_cases(R, name):
+    script = _multi_rank_cases(R)[name]
+    exp = scripts.merge_rank_outputs(ref.run_script(script, R, 1, timeout=60))
+    got = scripts.run_on_oracle(script, R)
+    scripts.assert_outputs_match(script, got, exp)
+
+
+@pytest.mark.skipif(not ref.have_ref(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("R,name", [(R, n) for R, n in _MR if n in ("maps_after_alloc", "x_on_local_ctrl_global", "diag_on_global", "swap_then_gate",
+                                                                      "nondiag_on_global_raises", "swap_unknown_pair", "swap_duplicate")])
+def test_engine_host_logic_on_global_qubit_cases(R, name):
+    """the product's host logic (one dry-run engine per rank): slot maps, error outcomes, and the launches — global-control filter,
+    per-rank slices of diagonal gates on global qubits, swap plans — replayed to the compiled reference's state"""
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    script = _multi_rank_cases(R)[name]
+    exp = scripts.merge_rank_outputs(ref.run_script(script, R, 1, timeout=60))
+    engines = []
+    for r in range(R):
+        M.init_world(r, R, b"", 0, M.FLAG_DRY_RUN)
+        engines.append(M.SimulatorMPI(*script[0][1:]))
+    M.init_world(0, 1, b"", 0, 0)
+    for op, want in zip(script[1:], exp[1:]):
+        if op[0] == "cheat_local":
+            for e in engines:
+                e.synchronize()
+            state = scripts.replay_traces([e.launch_trace() for e in engines], R, {"tile_emulator": True})
+            assert np.abs(state - want[1]).max() <= 1e-12
+            continue
+        for e in engines:
+            try:
+                got = getattr(e, op[0])(*op[1:])
+            except RuntimeError as err:
+                got = ("error", str(err))
+            if isinstance(want, tuple) and want and want[0] == "error":
+                assert isinstance(got, tuple) and got[0] == "error", (op, got)
+            elif op[0] in ("get_qubits_ids", "get_local_qubits_ids", "get_global_qubits_ids"):
+                assert list(got) == list(want)
+            else:
+                assert not (isinstance(got, tuple) and got and got[0] == "error"), (op, got)
