@@ -20,6 +20,18 @@ def test_header_declares_both_layers():
     assert len(names) >= 40
 
 
+def test_header_is_plain_c():
+    """the boundary is a C ABI: include/hiq_b200.h compiles as C99 and as C++11 on its own (no torch, no CUDA headers)"""
+    import shutil
+    import subprocess
+    hdr = os.path.join(ROOT, "include", "hiq_b200.h")
+    for cc, flags in (("gcc", ["-std=c99", "-x", "c"]), ("g++", ["-std=c++11", "-x", "c++"])):
+        if shutil.which(cc) is None:
+            continue
+        res = subprocess.run([cc, *flags, "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only", hdr], capture_output=True, text=True)
+        assert res.returncode == 0, res.stderr
+
+
 def test_library_exports_every_declared_symbol():
     from hiqsimulator_b200 import _lib
     lib = ctypes.CDLL(_lib.LIB_PATH)
