@@ -10,6 +10,8 @@ import os
 import numpy as np
 import pytest
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 from oracle import ref
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -167,6 +169,108 @@ def test_planner_equals_python_loop(kind, n, R, ml, cluster):
     assert runs[0][0] == runs[1][0]          # perm / cluster / swap sequence
     assert runs[0][1] == runs[1][1]          # final qubit maps
     assert runs[0][2] == runs[1][2]          # every descriptor the engine emitted (fused matrices bit for bit)
+
+
+def _reference_python_engine(n, cmds, R, max_local, cluster, supremacy=False):
+    """the UNMODIFIED reference _greedyscheduler.py (stand-ins for the ProjectQ classes it imports, compiled reference
+    schedulers) on the same command list, in its own process: oracle/run_reference_greedy.py"""
+    import json
+    import subprocess
+    import sys
+    import tempfile
+    job = {"n": n, "R": R, "max_local": max_local, "cluster": cluster, "supremacy": supremacy,
+           "gates": [[i, [int(q) for q in c.qubits], [int(q) for q in c.controls], bool(c.is_z)] for i, c in enumerate(cmds)]}
+    with tempfile.TemporaryDirectory() as tmp:
+        jp, op_ = os.path.join(tmp, "job.json"), os.path.join(tmp, "out.json")
+        with open(jp, "w") as f:
+            json.dump(job, f)
+        res = subprocess.run([sys.executable, "-m", "oracle.run_reference_greedy", jp, op_], cwd=ROOT, capture_output=True, text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-3000:]
+        with open(op_) as f:
+            return json.load(f)
+
+
+@pytest.mark.parametrize("kind,n,R,ml,cluster", [("random", 12, 1, 12, 4), ("random", 13, 2, 12, 4), ("random", 14, 4, 12, 3), ("random", 15, 8, 12, 4),
+                                                 ("qft", 14, 4, 12, 4), ("qft", 12, 1, 12, 5), ("grover", 9, 2, 9, 4), ("random", 13, 4, 11, 2),
+                                                 ("supremacy", 13, 4, 11, 4), ("supremacy", 12, 1, 12, 4)])
+def test_planner_equals_the_unmodified_reference_python_engine(kind, n, R, ml, cluster):
+    """Row A20 against the reference's own file: hiq/projectq/cengines/_greedyscheduler.py is loaded byte for byte (with
+    stand-ins for the few ProjectQ classes it imports and the compiled reference schedulers) and fed the circuit; the
+    product's planner must emit the same relabelling, the same clusters in the same order, the same swaps, and leave the
+    controlled-Z gates with the same target / control roles and the backend with the same slot maps."""
+    from oracle import ref, run_reference_greedy
+    if not run_reference_greedy.available() or not ref.have_ref():
+        pytest.skip("needs /root/reference and oracle/_ref")
+    from hiqsimulator_b200 import backends, cengines, circuits
+    from oracle import statevec
+    supremacy = kind == "supremacy"  # trailing controlled-Z gates are dropped (reference _greedyscheduler.py:151-173)
+    if kind in ("random", "supremacy"):
+        nq, cmds = circuits.random_circuit(n, 6, seed=n + R)
+    elif kind == "qft":
+        nq, cmds = circuits.qft_circuit(n)
+    else:
+        nq, cmds = circuits.grover_circuit(n, 2)
+    want = _reference_python_engine(nq, cmds, R, ml, cluster, supremacy)
+    # the same run is committed as a golden fixture (tests/make_golden_greedy.py), so that the pin also holds where
+    # /root/reference is absent (test_planner_equals_the_golden_reference_engine_logs)
+    golden = os.path.join(ROOT, "tests", "golden", "greedy_%s_%d_r%d_l%d_c%d.json" % (kind, n, R, ml, cluster))
+    if os.path.exists(golden):
+        with open(golden) as f:
+            assert json.load(f) == want
+    be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=ml, max_fused_qubits=cluster,
+                               backend_class=lambda s, l, c: statevec.SimulatorMPI(s, l, c, R))
+    gs = cengines.GreedyScheduler(cluster_size=cluster, supremacy_circuit=supremacy)
+    eng = cengines.HiQMainEngine(be, [gs])
+    eng.allocate_qureg(nq)
+    mine = copy.deepcopy(cmds)
+    for i, c in enumerate(mine):
+        c.uid = i
+    eng.receive(mine)
+    eng.flush()
+    got = [[k, [int(x) for x in v]] for k, v in gs.log]
+    assert got == want["log"]
+    assert len([e for e in got if e[0] == "cluster"]) > 3
+    for i, c in enumerate(mine):
+        assert [list(c.qubits), list(c.controls)] == want["gates"][str(i)], i
+    assert list(be._simulator.get_qubits_ids()) == want["maps"]
+
+
+GREEDY_GOLDEN = [("random", 12, 1, 12, 4), ("random", 13, 2, 12, 4), ("random", 14, 4, 12, 3), ("random", 15, 8, 12, 4), ("qft", 14, 4, 12, 4),
+                 ("qft", 12, 1, 12, 5), ("grover", 9, 2, 9, 4), ("random", 13, 4, 11, 2), ("supremacy", 13, 4, 11, 4), ("supremacy", 12, 1, 12, 4)]
+
+
+def greedy_case_circuit(kind, n, R):
+    from hiqsimulator_b200 import circuits
+    if kind in ("random", "supremacy"):
+        return circuits.random_circuit(n, 6, seed=n + R)
+    if kind == "qft":
+        return circuits.qft_circuit(n)
+    return circuits.grover_circuit(n, 2)
+
+
+@pytest.mark.parametrize("kind,n,R,ml,cluster", GREEDY_GOLDEN)
+def test_planner_equals_the_golden_reference_engine_logs(kind, n, R, ml, cluster):
+    """the same comparison against the committed output of the unmodified reference engine (tests/golden/greedy_*.json,
+    written by tests/make_golden_greedy.py): runs wherever the repository is, /root/reference or not"""
+    from hiqsimulator_b200 import backends, cengines
+    from oracle import statevec
+    with open(os.path.join(ROOT, "tests", "golden", "greedy_%s_%d_r%d_l%d_c%d.json" % (kind, n, R, ml, cluster))) as f:
+        want = json.load(f)
+    nq, cmds = greedy_case_circuit(kind, n, R)
+    be = backends.SimulatorMPI(gate_fusion=True, rnd_seed=1, num_local_qubits=ml, max_fused_qubits=cluster,
+                               backend_class=lambda s, l, c: statevec.SimulatorMPI(s, l, c, R))
+    gs = cengines.GreedyScheduler(cluster_size=cluster, supremacy_circuit=(kind == "supremacy"))
+    eng = cengines.HiQMainEngine(be, [gs])
+    eng.allocate_qureg(nq)
+    mine = copy.deepcopy(cmds)
+    for i, c in enumerate(mine):
+        c.uid = i
+    eng.receive(mine)
+    eng.flush()
+    assert [[k, [int(x) for x in v]] for k, v in gs.log] == want["log"]
+    for i, c in enumerate(mine):
+        assert [list(c.qubits), list(c.controls)] == want["gates"][str(i)], i
+    assert list(be._simulator.get_qubits_ids()) == want["maps"]
 
 
 def test_planner_with_supremacy_preprocessing_equals_python_loop():
