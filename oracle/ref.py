@@ -138,6 +138,47 @@ def run_script(script, world_size: int = 1, omp_threads: int | None = None, time
                 os.unlink(shm)
 
 
+def run_module_on_ranks(module: str, job_path: str, world_size: int, omp_threads: int | None = None, timeout: float = 600.0):
+    """Start `python -m <module> <job_path> <out_r.pkl>` once per reference rank (same process wiring as run_script: one OS
+    process per rank, ranks attached to one shared-memory arena through the environment) and return the unpickled outputs
+    by rank.  Used by oracle/run_reference_pipeline.py, which runs the reference's Python layers on top of the engine."""
+    with tempfile.TemporaryDirectory(prefix="hiqref_") as tmp:
+        shm = None
+        if world_size > 1:
+            shm = "/dev/shm/hiqref_%d_%s" % (os.getpid(), os.path.basename(tmp))
+            with open(shm, "wb") as f:
+                f.truncate(4096 + (1 << 20) * world_size)
+        procs = []
+        try:
+            for r in range(world_size):
+                env = dict(os.environ)
+                env["HIQ_REF_SIZE"] = str(world_size)
+                env["HIQ_REF_RANK"] = str(r)
+                if shm:
+                    env["HIQ_REF_SHM"] = shm
+                env["OMP_NUM_THREADS"] = str(omp_threads if omp_threads else 1)
+                if world_size > 1:
+                    env.pop("OMP_PROC_BIND", None)
+                env["PYTHONPATH"] = os.path.dirname(_HERE) + os.pathsep + env.get("PYTHONPATH", "")
+                procs.append(subprocess.Popen([sys.executable, "-m", module, job_path, os.path.join(tmp, "out%d.pkl" % r)],
+                                              env=env, cwd=os.path.dirname(_HERE)))
+            for p in procs:
+                rc = p.wait(timeout=timeout)
+                if rc != 0:
+                    raise RuntimeError("reference rank exited with code %d" % rc)
+            res = []
+            for r in range(world_size):
+                with open(os.path.join(tmp, "out%d.pkl" % r), "rb") as f:
+                    res.append(pickle.load(f))
+            return res
+        finally:
+            for p in procs:
+                if p.poll() is None:
+                    p.kill()
+            if shm and os.path.exists(shm):
+                os.unlink(shm)
+
+
 if __name__ == "__main__":
     with open(sys.argv[1], "rb") as f:
         _script = pickle.load(f)

@@ -3,9 +3,9 @@
 `/root/reference/hiq/projectq/cengines/_greedyscheduler.py` (class GreedyScheduler: the stage / cluster loop that calls
 ClusterScheduler / SwapScheduler) and `/root/reference/hiq/projectq/ops/_gates.py` (MetaSwap,
 AllocateQuregGate) are loaded from where they lie, byte for byte; what they import from ProjectQ (third party, absent here:
-`projectq>=0.4.0`, requirements.txt:2) is supplied by ~60 lines of stand-ins below — BasicEngine.send, Command with
-qubits / control_qubits / all_qubits, BasicQubit, the gate base classes — restating the published ProjectQ behaviour these
-two files rely on.  `hiq.projectq.cengines.SwapScheduler / ClusterScheduler` are the unmodified compiled reference
+`projectq>=0.4.0`, requirements.txt:2) is supplied by the stand-ins of oracle/projectq_stand_ins.py — BasicEngine.send,
+Command with qubits / control_qubits / all_qubits, BasicQubit, the gate base classes — restating the published ProjectQ
+behaviour these two files rely on.  `hiq.projectq.cengines.SwapScheduler / ClusterScheduler` are the unmodified compiled reference
 schedulers (oracle/_ref/_sched_cpp).  The engine drives a numpy-oracle backend (slot maps and swaps as the reference engine
 does them) and everything it emits is logged.
 
@@ -17,7 +17,6 @@ Only tests use this (tests/test_scheduler.py); it needs /root/reference, so it n
 """
 from __future__ import annotations
 
-import importlib.util
 import json
 import os
 import sys
@@ -30,129 +29,17 @@ def available() -> bool:
     return os.path.exists(os.path.join(REF, "hiq/projectq/cengines/_greedyscheduler.py"))
 
 
-def _install_projectq_stand_ins():
-    pq = types.ModuleType("projectq")
-    ce = types.ModuleType("projectq.cengines")
-    op = types.ModuleType("projectq.ops")
-    ty = types.ModuleType("projectq.types")
-    be = types.ModuleType("projectq.backends")
-    me = types.ModuleType("projectq.meta")
-
-    class BasicEngine:  # projectq/cengines/_basics.py: engines form a chain; send() hands commands to the next one
-        def __init__(self):
-            self.main_engine = None
-            self.next_engine = None
-            self.is_last_engine = False
-
-        def send(self, command_list):
-            self.next_engine.receive(command_list)
-
-    class BasicQubit:  # projectq/types/_qubit.py
-        def __init__(self, engine, idx):
-            self.engine = engine
-            self.id = idx
-
-    class WeakQubitRef(BasicQubit):
-        pass
-
-    class BasicGate:  # projectq/ops/_basics.py (generate_command / make_tuple_of_qureg)
-        @staticmethod
-        def make_tuple_of_qureg(qubits):
-            if not isinstance(qubits, tuple):
-                qubits = (qubits,)
-            qubits = list(qubits)
-            for i in range(len(qubits)):
-                if isinstance(qubits[i], BasicQubit):
-                    qubits[i] = [qubits[i]]
-            return tuple(qubits)
-
-        def generate_command(self, qubits):
-            qubits = self.make_tuple_of_qureg(qubits)
-            engines = [q.engine for reg in qubits for q in reg]
-            return Command(engines[0], self, qubits)
-
-    class ClassicalInstructionGate(BasicGate):
-        pass
-
-    class FastForwardingGate(ClassicalInstructionGate):
-        pass
-
-    class FlushGate(FastForwardingGate):
-        pass
-
-    class AllocateQubitGate(ClassicalInstructionGate):
-        pass
-
-    class DeallocateQubitGate(FastForwardingGate):
-        pass
-
-    class ZGate(BasicGate):
-        pass
-
-    class Command:  # projectq/ops/_command.py
-        def __init__(self, engine, gate, qubits, controls=(), tags=()):
-            self.engine = engine
-            self.gate = gate
-            self.qubits = tuple(list(q) for q in qubits)
-            self._control_qubits = list(controls)
-            self.tags = list(tags)
-
-        @property
-        def control_qubits(self):
-            return self._control_qubits
-
-        @control_qubits.setter
-        def control_qubits(self, qubits):
-            self._control_qubits = list(qubits)
-
-        @property
-        def all_qubits(self):
-            return (self._control_qubits,) + self.qubits
-
-    class ResourceCounter:  # only patched by hiq/projectq/ops/_gates.py, never used here
-        def _add_cmd(self, cmd):
-            pass
-
-    ce.BasicEngine = BasicEngine
-    for cls in (BasicGate, ClassicalInstructionGate, FastForwardingGate, FlushGate, AllocateQubitGate, DeallocateQubitGate, ZGate, Command):
-        setattr(op, cls.__name__, cls)
-    ty.BasicQubit, ty.WeakQubitRef = BasicQubit, WeakQubitRef
-    be.ResourceCounter = ResourceCounter
-    me.get_control_count = lambda cmd: len(cmd.control_qubits)
-    pq.cengines, pq.ops, pq.types, pq.backends, pq.meta = ce, op, ty, be, me
-    for m in (pq, ce, op, ty, be, me):
-        sys.modules[m.__name__] = m
-    return op, ty
-
-
-def _load_unmodified(name, rel):
-    spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
-    mod = importlib.util.module_from_spec(spec)
-    sys.modules[name] = mod
-    spec.loader.exec_module(mod)
-    return mod
-
-
 def main(job_path, out_path):
     with open(job_path) as f:
         job = json.load(f)
     here = os.path.dirname(os.path.abspath(__file__))
     sys.path.insert(0, os.path.dirname(here))
     from oracle import ref, statevec
-    op, ty = _install_projectq_stand_ins()
+    from oracle import projectq_stand_ins as stand_ins
+    op, ty = stand_ins.install()
     # the packages the two reference files import from: schedulers = the compiled reference, ops = the reference's own file
-    hiq = types.ModuleType("hiq")
-    hpq = types.ModuleType("hiq.projectq")
-    hce = types.ModuleType("hiq.projectq.cengines")
-    sched = ref.load_ref_sched()
-    hce.SwapScheduler, hce.ClusterScheduler = sched.SwapScheduler, sched.ClusterScheduler
-    for m in (hiq, hpq, hce):
-        sys.modules[m.__name__] = m
-    gates_mod = _load_unmodified("hiq.projectq.ops._gates", "hiq/projectq/ops/_gates.py")
-    hop = types.ModuleType("hiq.projectq.ops")
-    hop.MetaSwap, hop.AllocateQuregGate = gates_mod.MetaSwap, gates_mod.AllocateQuregGate
-    sys.modules["hiq.projectq.ops"] = hop
-    gs_mod = _load_unmodified("hiq_reference_greedyscheduler", "hiq/projectq/cengines/_greedyscheduler.py")
+    gates_mod = stand_ins.install_hiq_packages(ref.load_ref_sched())
+    gs_mod = stand_ins.load_unmodified("hiq_reference_greedyscheduler", "hiq/projectq/cengines/_greedyscheduler.py")
 
     n, R = job["n"], job["R"]
     sim = statevec.SimulatorMPI(1, job["max_local"], job["cluster"], R)
