@@ -510,7 +510,7 @@ def main():
     ap.add_argument("--qubits", type=int, default=None, help="override the number of qubits of the workload")
     ap.add_argument("--circuit", default=None, choices=[None, "qft", "random", "shor", "grover"])
     ap.add_argument("--cpu-qubits", type=int, default=None, help="size of the CPU-baseline sample")
-    ap.add_argument("--cpu-budget", type=float, default=240.0, help="seconds the timed CPU steps may take in total")
+    ap.add_argument("--cpu-budget", type=float, default=120.0, help="seconds the timed CPU steps may take in total")
     ap.add_argument("--e2e-steps", type=int, default=None, help="end-to-end steps (default min(steps, 5))")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-swap-baseline", action="store_true")
