@@ -1155,6 +1155,7 @@ extern "C" int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slo
      using namespace hiq;
      if (!slab || !slots || !matrix) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: null argument");
      if (n_pre == 0) return hiqk_apply_dense(slab, L, k, slots, matrix, 0, HIQK_DENSE_DIRECT, stream);
+     if (n_pre < 0 || !pre) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: null diagonal ops or negative count");
      double2* psi = static_cast<double2*>(slab);
      cudaStream_t st = static_cast<cudaStream_t>(stream);
      int pslots[kMaxTargets];

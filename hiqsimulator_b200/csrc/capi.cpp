@@ -30,6 +30,11 @@ static int guarded(F&& f)
 
 #define NEED(e) \
      if (!(e)) return set_error(HIQ_ERR_ARG, "null engine handle")
+// an input array: a null pointer is fine for an empty list only
+#define NEED_ARRAY(who, p, n) \
+     if ((n) < 0 || ((n) > 0 && !(p))) return set_error(HIQ_ERR_ARG, who ": null array or negative length")
+#define NEED_OUT(who, p) \
+     if (!(p)) return set_error(HIQ_ERR_ARG, who ": null output")
 
 static std::vector<Index> vec_ids(const int64_t* p, int n) { return std::vector<Index>(p, p + (n > 0 ? n : 0)); }
 static std::vector<bool> vec_bits(const uint8_t* p, int n)
@@ -64,6 +69,7 @@ int hiq_allocate_qubit(hiq_engine* e, int64_t id)
 int hiq_allocate_qureg(hiq_engine* e, const int64_t* ids, int n, double init_re, double init_im)
 {
      NEED(e);
+     NEED_ARRAY("hiq_allocate_qureg", ids, n);
      return guarded([&] { e->impl.allocate_qureg(vec_ids(ids, n), cplx(init_re, init_im)); });
 }
 
@@ -77,6 +83,8 @@ int hiq_apply_controlled_gate(hiq_engine* e, const double* matrix, int dim, cons
                               int n_ctrls)
 {
      NEED(e);
+     NEED_ARRAY("hiq_apply_controlled_gate", ids, n_ids);
+     NEED_ARRAY("hiq_apply_controlled_gate", ctrls, n_ctrls);
      if (!matrix || dim < 1 || dim > 32) return set_error(HIQ_ERR_ARG, "hiq_apply_controlled_gate: bad matrix");
      return guarded([&] {
           GateMatrix m(dim);
@@ -94,12 +102,15 @@ int hiq_run(hiq_engine* e)
 int hiq_swap_qubits(hiq_engine* e, const int64_t* pairs, int n)
 {
      NEED(e);
+     NEED_ARRAY("hiq_swap_qubits", pairs, n);
      return guarded([&] { e->impl.swap_qubits_stage(vec_ids(pairs, n)); });
 }
 
 int hiq_measure_qubits(hiq_engine* e, const int64_t* ids, int n, uint8_t* out_bits)
 {
      NEED(e);
+     NEED_ARRAY("hiq_measure_qubits", ids, n);
+     if (n > 0) NEED_OUT("hiq_measure_qubits", out_bits);
      return guarded([&] {
           auto r = e->impl.measure_qubits(vec_ids(ids, n));
           for (int i = 0; i < n; ++i) out_bits[i] = r[i] ? 1 : 0;
@@ -109,12 +120,18 @@ int hiq_measure_qubits(hiq_engine* e, const int64_t* ids, int n, uint8_t* out_bi
 int hiq_get_probability(hiq_engine* e, const uint8_t* bits, const int64_t* ids, int n, double* out)
 {
      NEED(e);
+     NEED_ARRAY("hiq_get_probability", ids, n);
+     NEED_ARRAY("hiq_get_probability", bits, n);
+     NEED_OUT("hiq_get_probability", out);
      return guarded([&] { *out = e->impl.get_probability(vec_bits(bits, n), vec_ids(ids, n)); });
 }
 
 int hiq_get_amplitude(hiq_engine* e, const uint8_t* bits, const int64_t* ids, int n, double* out_re_im)
 {
      NEED(e);
+     NEED_ARRAY("hiq_get_amplitude", ids, n);
+     NEED_ARRAY("hiq_get_amplitude", bits, n);
+     NEED_OUT("hiq_get_amplitude", out_re_im);
      return guarded([&] {
           const cplx v = e->impl.get_amplitude(vec_bits(bits, n), vec_ids(ids, n));
           out_re_im[0] = v.real();
@@ -125,18 +142,22 @@ int hiq_get_amplitude(hiq_engine* e, const uint8_t* bits, const int64_t* ids, in
 int hiq_collapse_wavefunction(hiq_engine* e, const int64_t* ids, const uint8_t* values, int n)
 {
      NEED(e);
+     NEED_ARRAY("hiq_collapse_wavefunction", ids, n);
+     NEED_ARRAY("hiq_collapse_wavefunction", values, n);
      return guarded([&] { e->impl.collapse_wavefunction(vec_ids(ids, n), vec_bits(values, n)); });
 }
 
 int hiq_entropy(hiq_engine* e, double* out)
 {
      NEED(e);
+     NEED_OUT("hiq_entropy", out);
      return guarded([&] { *out = e->impl.entropy(); });
 }
 
 int hiq_get_qubits_ids(hiq_engine* e, int kind, int64_t* out, int cap, int* n)
 {
      NEED(e);
+     NEED_OUT("hiq_get_qubits_ids", n);
      return guarded([&] {
           std::vector<Index> v = kind == 0 ? e->impl.qubits_permutation() : (kind == 1 ? e->impl.locals() : e->impl.globals());
           *n = static_cast<int>(v.size());
@@ -150,6 +171,7 @@ int hiq_get_qubits_ids(hiq_engine* e, int kind, int64_t* out, int cap, int* n)
 int hiq_set_qubits_perm(hiq_engine* e, const int64_t* p, int n)
 {
      NEED(e);
+     NEED_ARRAY("hiq_set_qubits_perm", p, n);
      return guarded([&] { e->impl.set_qubits_permutation(vec_ids(p, n)); });
 }
 
@@ -212,6 +234,7 @@ int hiq_get_expectation_value(hiq_engine* e, const int* term_offsets, const int*
                               const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids, double* out)
 {
      NEED(e);
+     NEED_ARRAY("hiq_get_expectation_value", ids, n_ids);
      if (!out) return set_error(HIQ_ERR_ARG, "hiq_get_expectation_value: null output");
      return guarded([&] {
           *out = e->impl.get_expectation_value(pauli_terms(term_offsets, factor_index, factor_pauli, coefs_re_im, n_terms), vec_ids(ids, n_ids));
@@ -222,6 +245,7 @@ int hiq_apply_qubit_operator(hiq_engine* e, const int* term_offsets, const int* 
                              const double* coefs_re_im, int n_terms, const int64_t* ids, int n_ids)
 {
      NEED(e);
+     NEED_ARRAY("hiq_apply_qubit_operator", ids, n_ids);
      return guarded([&] {
           e->impl.apply_qubit_operator(pauli_terms(term_offsets, factor_index, factor_pauli, coefs_re_im, n_terms), vec_ids(ids, n_ids));
      });
@@ -232,6 +256,8 @@ int hiq_emulate_time_evolution(hiq_engine* e, const int* term_offsets, const int
                                const int64_t* ctrls, int n_ctrls)
 {
      NEED(e);
+     NEED_ARRAY("hiq_emulate_time_evolution", ids, n_ids);
+     NEED_ARRAY("hiq_emulate_time_evolution", ctrls, n_ctrls);
      return guarded([&] {
           e->impl.emulate_time_evolution(pauli_terms(term_offsets, factor_index, factor_pauli, coefs_re_im, n_terms), time,
                                          vec_ids(ids, n_ids), vec_ids(ctrls, n_ctrls));
@@ -241,6 +267,8 @@ int hiq_emulate_time_evolution(hiq_engine* e, const int* term_offsets, const int
 int hiq_set_wavefunction(hiq_engine* e, const double* amps_re_im, uint64_t n_amps, const int64_t* ids, int n_ids)
 {
      NEED(e);
+     NEED_ARRAY("hiq_set_wavefunction", ids, n_ids);
+     if (n_amps > 0) NEED_OUT("hiq_set_wavefunction (amplitudes)", amps_re_im);
      return guarded([&] { e->impl.set_wavefunction(reinterpret_cast<const cplx*>(amps_re_im), n_amps, vec_ids(ids, n_ids)); });
 }
 
@@ -248,6 +276,8 @@ int hiq_emulate_math_table(hiq_engine* e, const uint64_t* table, uint64_t table_
                            const int64_t* ctrls, int n_ctrls)
 {
      NEED(e);
+     NEED_ARRAY("hiq_emulate_math_table", reg_ids, n_reg);
+     NEED_ARRAY("hiq_emulate_math_table", ctrls, n_ctrls);
      if (!table) return set_error(HIQ_ERR_ARG, "hiq_emulate_math_table: null table");
      return guarded([&] {
           e->impl.emulate_math(HIQK_PERM_TABLE, 0, 0, std::vector<uint64_t>(table, table + table_len), vec_ids(reg_ids, n_reg),
@@ -259,6 +289,8 @@ int hiq_emulate_math_const(hiq_engine* e, int kind, uint64_t a, uint64_t N, cons
                            int n_ctrls)
 {
      NEED(e);
+     NEED_ARRAY("hiq_emulate_math_const", reg_ids, n_reg);
+     NEED_ARRAY("hiq_emulate_math_const", ctrls, n_ctrls);
      if (kind != HIQK_PERM_ADD && kind != HIQK_PERM_ADD_MOD && kind != HIQK_PERM_MUL_MOD)
           return set_error(HIQ_ERR_ARG, "hiq_emulate_math_const: kind must be HIQK_PERM_ADD, _ADD_MOD or _MUL_MOD");
      return guarded([&] { e->impl.emulate_math(kind, a, N, {}, vec_ids(reg_ids, n_reg), vec_ids(ctrls, n_ctrls)); });
@@ -267,6 +299,8 @@ int hiq_emulate_math_const(hiq_engine* e, int kind, uint64_t a, uint64_t N, cons
 int hiq_local_slab(hiq_engine* e, void** dev_ptr, int* L)
 {
      NEED(e);
+     NEED_OUT("hiq_local_slab", dev_ptr);
+     NEED_OUT("hiq_local_slab", L);
      return guarded([&] {
           if (e->impl.dry_run()) throw EngineError(HIQ_ERR_RUNTIME, "hiq_local_slab: dry-run engine has no slab");
           *dev_ptr = e->impl.slab_ptr();
@@ -277,6 +311,7 @@ int hiq_local_slab(hiq_engine* e, void** dev_ptr, int* L)
 int hiq_set_local_slab(hiq_engine* e, const void* host_src, uint64_t n_amps)
 {
      NEED(e);
+     if (n_amps > 0) NEED_OUT("hiq_set_local_slab (source)", host_src);
      return guarded([&] { e->impl.copy_slab_from_host(host_src, n_amps); });
 }
 
@@ -289,6 +324,8 @@ int hiq_synchronize(hiq_engine* e)
 int hiq_rank(hiq_engine* e, int* rank, int* world_size)
 {
      NEED(e);
+     NEED_OUT("hiq_rank", rank);
+     NEED_OUT("hiq_rank", world_size);
      *rank = e->impl.rank();
      *world_size = e->impl.world_size();
      return HIQ_OK;
@@ -304,6 +341,7 @@ int hiq_set_dense_variant(hiq_engine* e, int variant)
 int hiq_get_stats(hiq_engine* e, hiq_stats* out)
 {
      NEED(e);
+     NEED_OUT("hiq_get_stats", out);
      const EngineStats& s = e->impl.stats();
      out->total_gates = s.total_gates;
      out->total_runs = s.total_runs;
@@ -336,6 +374,8 @@ int hiq_get_stats(hiq_engine* e, hiq_stats* out)
 int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* variant, int* n_ref, int cap, int* n)
 {
      NEED(e);
+     NEED_OUT("hiq_collect_timings", n);
+     if (cap > 0 && (!ms || !kind || !k || !variant)) return set_error(HIQ_ERR_ARG, "hiq_collect_timings: null output");
      return guarded([&] {
           auto t = e->impl.collect_timings();
           *n = static_cast<int>(t.size());
@@ -353,6 +393,7 @@ int hiq_collect_timings(hiq_engine* e, double* ms, int* kind, int* k, int* varia
 int hiq_stream(hiq_engine* e, void** stream)
 {
      NEED(e);
+     NEED_OUT("hiq_stream", stream);
      *stream = e->impl.stream();
      return HIQ_OK;
 }
@@ -362,6 +403,7 @@ int hiq_stream(hiq_engine* e, void** stream)
 namespace {
 int trace_get(const std::vector<Descriptor>& t, int i, hiq_descriptor* d, double* payload, int cap_payload, int64_t* aux, int cap_aux)
 {
+     if (!d) return set_error(HIQ_ERR_ARG, "hiq_trace_get: null descriptor");
      if (i < 0 || i >= static_cast<int>(t.size())) return set_error(HIQ_ERR_ARG, "hiq_trace_get: index out of range");
      const Descriptor& s = t[i];
      d->kind = s.kind;
@@ -387,6 +429,7 @@ extern "C" {
 int hiq_trace_count(hiq_engine* e, int* n)
 {
      NEED(e);
+     NEED_OUT("hiq_trace_count", n);
      *n = static_cast<int>(e->impl.trace().size());
      return HIQ_OK;
 }
@@ -400,6 +443,7 @@ int hiq_trace_get(hiq_engine* e, int i, hiq_descriptor* d, double* payload, int 
 int hiq_launch_trace_count(hiq_engine* e, int* n)
 {
      NEED(e);
+     NEED_OUT("hiq_launch_trace_count", n);
      *n = static_cast<int>(e->impl.launch_trace().size());
      return HIQ_OK;
 }
