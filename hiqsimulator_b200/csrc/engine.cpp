@@ -726,11 +726,13 @@ void Engine::run()
      GateMatrix m;
      std::vector<Index> ids, ctrls;
      bool diag = true;
+     // refused BEFORE the product is formed: a cluster of n qubits costs 4^n memory and 8^n time to fuse, and a caller that
+     // keeps queueing gates after this error (the cluster stays queued, as in the reference) must not pay that every time
+     if (fused_.num_qubits() > 5) fail("Run(): cannot apply " + std::to_string(fused_.num_qubits()) + " qubits gate");
      fused_.fuse(m, ids, ctrls, diag);
      Descriptor d;
      d.ctrl_mask = ids_to_bits(ctrls, locals_);
      d.k = static_cast<int>(ids.size());
-     if (d.k > 5) fail("Run(): cannot apply " + std::to_string(d.k) + " qubits gate");
      for (int l = 0; l < d.k; ++l) d.slots[l] = static_cast<int>(find_sure(locals_, ids[l]));
      if (d.k == 0) {
           if (m.at(0, 0) != cplx(1.0)) {

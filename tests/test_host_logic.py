@@ -395,3 +395,25 @@ def test_shor_period_read_out_is_exact_beyond_53_bits():
         y = sum(bits[2 * n - 1 - i] * 1.0 / (1 << (i + 1)) for i in range(2 * n))
         float_misses += Fraction(y).limit_denominator(N - 1).denominator != r
     assert float_misses > 0
+
+
+def test_too_wide_cluster_is_refused_before_the_product_is_formed():
+    """Run() on a cluster of more than 5 qubits raises the reference's error (SimulatorMPI.cpp:516-523) WITHOUT first
+    multiplying the cluster out — 14 queued one-qubit gates would otherwise cost a 2^14 x 2^14 matrix (4 GiB) per attempt,
+    and the cluster stays queued after the error as in the reference, so every later call would pay it again"""
+    import time
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    M.init_world(0, 1, b"", 0, M.FLAG_DRY_RUN)
+    try:
+        e = M.SimulatorMPI(1, 16, 16)
+        e.allocate_qureg(list(range(16)), 0)
+        h = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+        for q in range(14):
+            e.apply_controlled_matrix(h, [q], [])
+        t0 = time.perf_counter()
+        for _ in range(3):
+            with pytest.raises(RuntimeError, match="cannot apply 14 qubits gate"):
+                e.run()
+        assert time.perf_counter() - t0 < 1.0
+    finally:
+        M.init_world(0, 1, b"", 0, 0)
