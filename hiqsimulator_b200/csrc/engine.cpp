@@ -206,6 +206,11 @@ void Engine::allocate_qubit(Index id)
 {
      // policy of the reference (SimulatorMPI.cpp:184-216)
      const auto t0 = Clock::now();
+     // the reference does not look (a second allocation of a live id leaves it in two places of the maps, -1 is its mark
+     // of an empty global position); refused here, on every rank alike
+     if (id < 0) fail("AllocateQubit(): qubit ids must be non-negative");
+     if (find(locals_, id) != kNpos || find(globals_, id) != kNpos)
+          fail("AllocateQubit(): qubit " + std::to_string(id) + " is already allocated");
      const size_t nloc = locals_.size();
      if (nloc < min_local_) allocate_local(id);
      else if (find(globals_, kNone) != kNpos) allocate_global(id);
@@ -340,7 +345,20 @@ void Engine::deallocate_qubit(Index id)
 void Engine::apply_gate(GateMatrix m, std::vector<Index> ids, std::vector<Index> ctrls)
 {
      // per-rank preprocessing of the reference (SimulatorMPI.cpp:710-815)
-     if (m.dim != (1 << ids.size())) fail("ApplyGate(): matrix size does not match the number of target qubits");
+     if (ids.size() > 30 || m.dim != (1 << ids.size())) fail("ApplyGate(): matrix size does not match the number of target qubits");
+     // Checked here, on every rank alike (the id lists are the same everywhere), before the rank-dependent control filter:
+     // the reference meets an unknown qubit in Run() on the ranks that kept the gate only, which then leave the collective
+     // sequence the other ranks stay in.
+     for (const std::vector<Index>* list: {&ids, &ctrls})
+          for (Index q: *list)
+               if (q < 0 || (find(locals_, q) == kNpos && find(globals_, q) == kNpos))
+                    fail("ArrayFindSure(): Can't find " + std::to_string(q) + " in " + list_str(locals_));
+     {
+          std::vector<Index> all(ids);
+          all.insert(all.end(), ctrls.begin(), ctrls.end());
+          std::sort(all.begin(), all.end());
+          if (std::adjacent_find(all.begin(), all.end()) != all.end()) fail("ApplyGate(): target and control qubits must be distinct");
+     }
      const bool diag = is_diagonal(m);
      const uint64_t global_id_mask = ids_to_bits(ids, globals_);
      const uint64_t global_ctrl_mask = ids_to_bits(ctrls, globals_);
@@ -353,6 +371,9 @@ void Engine::apply_gate(GateMatrix m, std::vector<Index> ids, std::vector<Index>
      // Deviation: the reference tests this only on ranks that pass the control filter below and
      // then blocks in a barrier the other ranks never reach; here every rank raises together.
      if (global_id_mask != 0 && !diag) fail("ApplyGate(): can't apply non-diagonal gate to global qubits");
+     // a gate wider than the cluster goes to the fusion as it is (below, as in the reference, which then cannot find the
+     // global target in Run() on the ranks that kept the gate): refused here, on every rank
+     if (huge && global_id_mask != 0) fail("ApplyGate(): a gate wider than the cluster size cannot act on global qubits");
      if ((static_cast<uint64_t>(rank_) & global_ctrl_mask) != global_ctrl_mask) return;  // not this rank
 
      ++stats_.total_gates;
@@ -983,6 +1004,14 @@ void Engine::set_qubits_permutation(const std::vector<Index>& p)
 {
      // relabel only, no data motion (reference: SimulatorMPI.cpp:661-667)
      if (p.size() < locals_.size() || p.size() < globals_.size()) fail("SetQubitsPermutation(): permutation too short");
+     {
+          // a relabelling: the same labels (empty global positions included) in another order — anything else would put a
+          // qubit in two places of the maps or drop one (the reference takes the list as it comes)
+          std::vector<Index> a = qubits_permutation(), b = p;
+          std::sort(a.begin(), a.end());
+          std::sort(b.begin(), b.end());
+          if (a != b) fail("SetQubitsPermutation(): not a permutation of the current qubit ids " + list_str(qubits_permutation()));
+     }
      locals_.assign(p.begin(), p.begin() + locals_.size());
      globals_.assign(p.end() - globals_.size(), p.end());
 }
@@ -1031,6 +1060,10 @@ void Engine::swap_qubits(const std::vector<Index>& pairs)
 {
      // pairs = [global id, local id, ...]; afterwards the ids trade places (reference: SimulatorMPI.cpp:1085-1138)
      if (pairs.size() % 2) fail("SwapQubits(): odd number of ids");
+     // gates still waiting in the fusion were given for the layout as it is: they go out before qubits trade places (the
+     // reference's wrapper runs before every swap / allocation / measurement, _simulator_mpi.py:505-507; a caller of the
+     // class that does not would find its gate's qubit global in Run(), on the ranks that kept the gate)
+     if (!fused_.empty()) run();
      std::map<Index, size_t> pos;
      for (size_t i = 0; i < pairs.size(); i += 2) {
           pos[pairs[i]] = find_sure(globals_, pairs[i]);

@@ -417,3 +417,92 @@ def test_too_wide_cluster_is_refused_before_the_product_is_formed():
         assert time.perf_counter() - t0 < 1.0
     finally:
         M.init_world(0, 1, b"", 0, 0)
+
+
+def _all_ranks(R, seed, max_local, max_cluster):
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    es = []
+    for r in range(R):
+        M.init_world(r, R, b"", 0, M.FLAG_DRY_RUN)
+        es.append(M.SimulatorMPI(seed, max_local, max_cluster))
+    M.init_world(0, 1, b"", 0, 0)
+    return es
+
+
+def _outcomes(es, name, *args):
+    out = []
+    for e in es:
+        try:
+            getattr(e, name)(*args)
+            out.append(None)
+        except RuntimeError as ex:
+            out.append(str(ex))
+    return out
+
+
+def test_invalid_arguments_are_refused_on_every_rank_alike():
+    """A call that raises on some ranks only leaves the others waiting in the next collective.  The reference meets an
+    unallocated qubit in Run(), on the ranks whose global-control bits kept the gate (SimulatorMPI.cpp:466-468, after the
+    filter of :736-739); this engine refuses at the call, before any rank-dependent decision (found by
+    tools/fuzz_invalid_arguments.py --ranks)."""
+    es = _all_ranks(4, 1, 4, 3)
+    for e in es:
+        e.allocate_qureg(list(range(6)), 0)
+    loc, glo = es[0].get_local_qubits_ids(), [q for q in es[0].get_global_qubits_ids() if q >= 0]
+    assert len(loc) == 4 and len(glo) == 2
+    D = np.diag(np.exp(1j * np.arange(4)))
+    H = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+
+    def refused_everywhere(name, *args, match):
+        out = _outcomes(es, name, *args)
+        assert all(o is not None and match in o for o in out), out
+
+    # unallocated target behind a global control: only the ranks with that control bit set would ever look at the gate
+    refused_everywhere("apply_controlled_matrix", H, [42], [glo[0]], match="Can't find 42")
+    refused_everywhere("apply_controlled_matrix", H, [loc[0]], [glo[0], 77], match="Can't find 77")
+    refused_everywhere("apply_controlled_matrix", H, [-1], [], match="Can't find -1")  # -1 marks an empty global position
+    # a qubit twice, or target and control at once
+    refused_everywhere("apply_controlled_matrix", D, [loc[0], loc[0]], [], match="must be distinct")
+    refused_everywhere("apply_controlled_matrix", H, [loc[1]], [loc[1]], match="must be distinct")
+    # wider than the cluster (3) with a global target: the reference queues it as it is and fails in Run() on some ranks
+    D4 = np.diag(np.exp(1j * np.arange(16)))
+    refused_everywhere("apply_controlled_matrix", D4, [loc[0], loc[1], loc[2], glo[1]], [glo[0]], match="wider than the cluster")
+    # allocation of a live or negative id, relabelling that is not a permutation
+    refused_everywhere("allocate_qubit", loc[2], match="already allocated")
+    refused_everywhere("allocate_qubit", glo[0], match="already allocated")
+    refused_everywhere("allocate_qubit", -1, match="non-negative")
+    refused_everywhere("set_qubits_perm", [loc[0]] * 4 + glo, match="not a permutation")
+    refused_everywhere("set_qubits_perm", loc + [glo[0], 99], match="not a permutation")
+    # nothing was queued or changed by the refused calls: the engines still take a valid relabelling and a valid gate
+    for e in es:
+        assert e.get_local_qubits_ids() == loc
+        e.set_qubits_perm(loc[::-1] + glo)
+        assert e.get_local_qubits_ids() == loc[::-1]
+        e.apply_controlled_matrix(H, [loc[0]], [glo[0]])
+        e.run()
+    runs = [sum(1 for d in e.trace() if d["kind"] == DESC_DENSE) for e in es]
+    assert runs == [0, 1, 0, 1]  # global position 0 <-> rank bit 0
+
+
+DESC_DENSE, DESC_SWAP = 1, 4  # HIQ_DESC_DENSE / HIQ_DESC_SWAP (include/hiq_b200.h)
+
+
+def test_gates_waiting_in_the_fusion_go_out_before_a_swap():
+    """The reference's wrapper runs before every swap (_simulator_mpi.py:505-507); a direct caller of the class that swaps
+    with a gate still queued must get that gate applied to the layout it was given for, on every rank, not an
+    ArrayFindSure error in the next Run() on the ranks that kept it."""
+    from hiqsimulator_b200 import _cppsim_mpi as M
+    es = _all_ranks(2, 1, 4, 3)
+    for e in es:
+        e.allocate_qureg(list(range(5)), 0)
+    loc, glo = es[0].get_local_qubits_ids(), [q for q in es[0].get_global_qubits_ids() if q >= 0]
+    H = np.array([[1, 1], [1, -1]], dtype=complex) / np.sqrt(2)
+    for e in es:
+        e.clear_trace()
+        e.apply_controlled_matrix(H, [loc[-1]], [glo[0]])   # kept by rank 1 only; no run()
+        e.swap_qubits([glo[0], loc[-1]])                    # loc[-1] becomes global
+        e.run()
+    kinds = [[d["kind"] for d in e.trace() if d["kind"] in (DESC_DENSE, DESC_SWAP)] for e in es]
+    assert kinds[0] == [DESC_SWAP]
+    assert kinds[1] == [DESC_DENSE, DESC_SWAP]
+    assert es[1].trace()[0]["slots"] == [len(loc) - 1]

@@ -1,13 +1,18 @@
 """Crash / hang fuzz of the reference-facing class WITHOUT a GPU: random call sequences with invalid arguments (unallocated,
 duplicated, negative and huge qubit ids, matrices of the wrong size, bit strings of the wrong length, empty lists, operators
 on qubits outside the register) on dry-run engines of 1, 2 and 4 virtual ranks.  Every call must either succeed or raise;
-a crash shows as a signal, a hang as the caller's timeout.    python tools/fuzz_invalid_arguments.py <first seed> <last seed>"""
+a crash shows as a signal, a hang as the caller's timeout.    python tools/fuzz_invalid_arguments.py <first seed> <last seed>
+With --ranks: every call goes to the engines of ALL ranks of a 2 / 4 / 8-rank world and must be accepted by all of them or
+refused by all of them (a call that raises on some ranks only would leave the others waiting in the next collective on
+hardware); prints DIVERGE lines otherwise."""
 import sys, os, faulthandler
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from hiqsimulator_b200 import _cppsim_mpi as M
 faulthandler.enable()
 lo, hi = int(sys.argv[1]), int(sys.argv[2])
+ALL_RANKS = '--ranks' in sys.argv
+n_div = 0
 def rid(rng, nq):
     r = rng.random()
     if r < 0.7: return int(rng.integers(0, nq))
@@ -28,16 +33,38 @@ def rmat(rng, k=None):
         dd = int(rng.integers(1, 40)); m = rng.normal(size=(dd, dd)) + 0j
     return m
 n_exc = n_ok = 0
+class AllRanks:
+    def __init__(s, es, seed): s.es = es; s.seed = seed
+    def __getattr__(s, name):
+        def g(*a):
+            global n_div
+            outs = []
+            for e in s.es:
+                try:
+                    getattr(e, name)(*a); outs.append(('ok', None))
+                except Exception as ex:
+                    outs.append((type(ex).__name__, str(ex)))
+            if len(set(o[0] for o in outs)) > 1:
+                n_div += 1
+                print('DIVERGE seed', s.seed, name, [x.shape if hasattr(x, 'shape') else x for x in a], outs, flush=True)
+            if outs[0][0] != 'ok':
+                raise RuntimeError(outs[0][1])
+        return g
+
 for seed in range(lo, hi):
     rng = np.random.default_rng(seed)
-    R = int(rng.choice([1, 2, 4]))
+    R = int(rng.choice([2, 4, 8] if ALL_RANKS else [1, 2, 4]))
     r = int(rng.integers(0, R))
     L = int(rng.integers(3, 9)); mc = int(rng.integers(1, 6))
-    M.init_world(r, R, b"", 0, M.FLAG_DRY_RUN)
-    try:
+    if ALL_RANKS:
+        es = []
+        for rr in range(R):
+            M.init_world(rr, R, b"", 0, M.FLAG_DRY_RUN)
+            es.append(M.SimulatorMPI(seed, L, mc))
+        e = AllRanks(es, seed)
+    else:
+        M.init_world(r, R, b"", 0, M.FLAG_DRY_RUN)
         e = M.SimulatorMPI(seed, L, mc)
-    except Exception:
-        n_exc += 1; continue
     nq = L + R.bit_length() - 1
     for step in range(int(rng.integers(5, 60))):
         c = int(rng.integers(0, 22))
@@ -88,4 +115,4 @@ for seed in range(lo, hi):
             n_exc += 1
     del e
 M.init_world(0, 1, b"", 0, 0)
-print("seeds", lo, hi, "calls ok", n_ok, "refused", n_exc)
+print("seeds", lo, hi, "calls ok", n_ok, "refused", n_exc, *(("rank-divergent", n_div) if ALL_RANKS else ()))
