@@ -354,6 +354,11 @@ void Engine::apply_gate(GateMatrix m, std::vector<Index> ids, std::vector<Index>
                if (q < 0 || (find(locals_, q) == kNpos && find(globals_, q) == kNpos))
                     fail("ArrayFindSure(): Can't find " + std::to_string(q) + " in " + list_str(locals_));
      {
+          // a control named twice (nested Control blocks on one qubit) is one control
+          std::vector<Index> once;
+          for (Index c: ctrls)
+               if (std::find(once.begin(), once.end(), c) == once.end()) once.push_back(c);
+          ctrls.swap(once);
           std::vector<Index> all(ids);
           all.insert(all.end(), ctrls.begin(), ctrls.end());
           std::sort(all.begin(), all.end());
