@@ -789,7 +789,7 @@ extern "C" int hiqk_tile_program_fits(int L, int n_steps, const hiqk_tile_step* 
      if (!choose_tile(L, n_steps, steps, pl, why)) return 0;
      int lut = 0;
      for (int s = 0; s < n_steps; ++s) {
-          if (steps[s].n_pre < 0 || steps[s].n_pre > kTileMaxOps) return 0;
+          if (steps[s].n_pre < 0 || steps[s].n_pre > kTileMaxOps || (steps[s].n_pre && !steps[s].pre)) return 0;
           for (int j = 0; j < steps[s].n_pre; ++j) {
                if (steps[s].pre[j].k < 0 || steps[s].pre[j].k > kMaxTargets) return 0;
                lut += 1 << steps[s].pre[j].k;
