@@ -1047,7 +1047,7 @@ extern "C" int hiqk_dense_direct_mixing_bits(int k, const double* matrix)
 
 extern "C" int hiqk_dense_prediag_supported(int L, int k, const int* slots)
 {
-     if (!slots || k < 1 || k > 4 || L < k) return 0;
+     if (!slots || k < 1 || k > 4 || L < k || L > 40) return 0;
      return hiq::pick_variant(L, k, slots) == HIQK_DENSE_DIRECT ? 1 : 0;
 }
 
@@ -1135,6 +1135,7 @@ extern "C" int hiqk_dense_prediag_image(int L, int k, const int* slots, const do
      using namespace hiq;
      if (!slots || !matrix || !pre || !image) return set_error(HIQ_ERR_ARG, "hiqk_dense_prediag_image: null argument");
      if (image_bytes < hiqk_dense_prediag_image_bytes()) return set_error(HIQ_ERR_ARG, "hiqk_dense_prediag_image: buffer too small");
+     if (n_pre < 1 || n_pre > HIQK_MAX_DIAG_OPS) return set_error(HIQ_ERR_ARG, "hiqk_dense_prediag_image: needs 1..16 diagonal ops");
      int pslots[kMaxTargets];
      double pm[2 << (2 * 4)];
      int ks = k;
@@ -1155,7 +1156,8 @@ extern "C" int hiqk_apply_dense_prediag(void* slab, int L, int k, const int* slo
      using namespace hiq;
      if (!slab || !slots || !matrix) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: null argument");
      if (n_pre == 0) return hiqk_apply_dense(slab, L, k, slots, matrix, 0, HIQK_DENSE_DIRECT, stream);
-     if (n_pre < 0 || !pre) return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: null diagonal ops or negative count");
+     if (n_pre < 0 || n_pre > HIQK_MAX_DIAG_OPS || !pre)
+          return set_error(HIQ_ERR_ARG, "hiqk_apply_dense_prediag: needs 0..16 diagonal ops and a non-null op array");
      double2* psi = static_cast<double2*>(slab);
      cudaStream_t st = static_cast<cudaStream_t>(stream);
      int pslots[kMaxTargets];

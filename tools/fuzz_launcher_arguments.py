@@ -36,15 +36,15 @@ for seed in range(lo, hi):
     slots = (ctypes.c_int * 8)(*[rslot(rng, L) for _ in range(8)])
     m = (ctypes.c_double * 2048)(*rng.normal(size=2048))
     n_ops = int(rng.choice([-1, 0, 1, 2, 5, 16, 17, 1000]))
-    ops = (DiagOp * 20)(*[rop(rng, L) for _ in range(20)])
+    ops = (DiagOp * 1000)(*[rop(rng, L) for _ in range(20)])  # the arrays are as long as the counts claim: only the geometry lies
     which = int(rng.integers(0, 6))
     if os.environ.get("FZ_VERBOSE"): print(seed, which, L, k, list(slots), n_ops, file=sys.stderr, flush=True)
     if which == 0:
         rc = lib.hiqk_dense_image(L, k, slots, m, ctypes.c_uint64(int(rng.integers(0, 2**62)) if rng.random() < 0.5 else 0), int(rng.integers(-1, 7)), bufs[0], ctypes.c_size_t(nb[0]))
     elif which == 1:
-        rc = lib.hiqk_diag_batch_image(L, ops, min(n_ops, 20) if n_ops != 1000 else 1000, bufs[1], ctypes.c_size_t(nb[1]))
+        rc = lib.hiqk_diag_batch_image(L, ops, n_ops, bufs[1], ctypes.c_size_t(nb[1]))
     elif which == 2:
-        rc = lib.hiqk_dense_prediag_image(L, k, slots, m, ops, min(n_ops, 20) if n_ops != 1000 else 1000, bufs[2], ctypes.c_size_t(nb[2]))
+        rc = lib.hiqk_dense_prediag_image(L, k, slots, m, ops, n_ops, bufs[2], ctypes.c_size_t(nb[2]))
     elif which in (3, 4):
         ns = int(rng.choice([-1, 0, 1, 2, 3, 4, 5, 100]))
         steps = (TileStep * 6)()
