@@ -414,7 +414,7 @@ int trace_get(const std::vector<Descriptor>& t, int i, hiq_descriptor* d, double
      d->n_aux = static_cast<int>(s.aux.size());
      if (payload) {
           if (cap_payload < d->n_payload) return set_error(HIQ_ERR_ARG, "hiq_trace_get: payload buffer too small");
-          std::memcpy(payload, s.payload.data(), sizeof(cplx) * s.payload.size());
+          if (!s.payload.empty()) std::memcpy(payload, s.payload.data(), sizeof(cplx) * s.payload.size());
      }
      if (aux) {
           if (cap_aux < d->n_aux) return set_error(HIQ_ERR_ARG, "hiq_trace_get: aux buffer too small");
